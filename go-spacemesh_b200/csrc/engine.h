@@ -1,0 +1,89 @@
+// engine.h — host runtime of the B200 POST label engine: per-device scratch, wave scheduling,
+// double-buffered result staging.  C++ because the reference's host side for this path is compiled
+// code (Go: activation/post.go PostSetupManager, activation/post_verifier.go); the Go toolchain is
+// absent in this image (INTEGRATION.md shows the cgo binding that sits on top of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <string>
+
+#include "label_kernels.cuh"
+
+namespace b200post {
+
+struct Options {
+    std::atomic<int64_t> romix_variant{ROMIX_DIRECT};
+    std::atomic<int64_t> mulwide_mask{0};
+    std::atomic<int64_t> tpb{128};
+    std::atomic<int64_t> ctas_per_sm{0};       // 0 = occupancy maximum
+    std::atomic<int64_t> max_scratch_mib{0};   // 0 = 90 % of free HBM
+};
+Options &options();
+
+extern std::atomic<uint64_t> g_launches;
+
+struct VrfResult { bool found = false; uint64_t index = 0; uint8_t label32[32] = {0}; };
+
+void set_error(const std::string &msg);
+const char *last_error();
+
+class DeviceEngine {
+public:
+    explicit DeviceEngine(int device);
+    ~DeviceEngine();
+    DeviceEngine(const DeviceEngine &) = delete;
+
+    // out_host / out_dev: at most one non-null (both null = discard).  Returns a B200POST_* code.
+    int labels_range(const uint8_t commitment[32], uint64_t N, uint64_t start, uint64_t count, uint8_t *out_host,
+                     uint8_t *out_dev, const uint8_t *vrf_difficulty, VrfResult *vrf, const volatile int *cancel);
+    int labels_gather(size_t n_items, const uint8_t *commitments, const uint64_t *indices, uint64_t N, uint8_t *out_host);
+    void romix_time(double *ms_total, uint64_t *launches, bool reset);
+    int device() const { return dev_; }
+    const cudaDeviceProp &prop() const { return prop_; }
+
+private:
+    int ensure(uint64_t N, uint64_t want_slots);   // (re)allocates scratch; sets wave_slots_
+    void release();
+    int run_wave(const LabelJob &job, uint32_t n_slots, uint64_t N, uint8_t *d_out, const uint32_t *d_diff, int buf);
+    void harvest(int buf);
+
+    int dev_;
+    cudaDeviceProp prop_{};
+    std::mutex mu_;
+    cudaStream_t stream_ = nullptr;
+    // scratch
+    uint4 *V_ = nullptr;
+    size_t v_bytes_ = 0;
+    uint4 *X_ = nullptr;
+    uint32_t alloc_slots_ = 0;   // capacity of the per-slot buffers below
+    uint32_t wave_slots_ = 0;    // slots per wave for the current (N, options)
+    uint8_t *d_out_[2] = {nullptr, nullptr};
+    uint8_t *h_out_[2] = {nullptr, nullptr};   // pinned
+    uint8_t *d_commit_ = nullptr;
+    uint64_t *d_idx_ = nullptr;
+    uint8_t *h_commit_ = nullptr;              // pinned staging for gather inputs
+    uint64_t *h_idx_ = nullptr;
+    uint32_t *d_mid_ = nullptr;
+    uint32_t *d_diff_ = nullptr;
+    VrfCandidate *d_cta_cand_ = nullptr;
+    VrfCandidate *d_running_ = nullptr;
+    VrfCandidate *h_running_ = nullptr;        // pinned
+    cudaEvent_t ev_done_[2] = {nullptr, nullptr};
+    cudaEvent_t ev_k2a_[2] = {nullptr, nullptr}, ev_k2b_[2] = {nullptr, nullptr};
+    bool k2_pending_[2] = {false, false};
+    double romix_ms_ = 0;
+    uint64_t romix_launches_ = 0;
+    // current tuning
+    int variant_ = 0, mw_ = 0, tpb_ = 128;
+};
+
+// registry: lazily created engine per CUDA ordinal (nullptr + error text if the device is unusable)
+DeviceEngine *engine_for(uint32_t provider);
+int device_count();
+void shutdown_all();
+
+}  // namespace b200post

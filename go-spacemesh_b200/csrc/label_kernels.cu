@@ -1,0 +1,453 @@
+// label_kernels.cu — hand-written sm_100a kernels for the POST label path (see label_kernels.cuh).
+#include "label_kernels.cuh"
+
+namespace b200post {
+
+// =================================================================================================
+// PTX helpers
+// =================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4 &v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// TMA 1-D bulk copy shared -> global, tracked by the thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N_PENDING>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N_PENDING) : "memory"); }
+template <int N_PENDING>
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N_PENDING) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// chunk k (0..7) of a 32-word row held as lo[16] || hi[16]
+#define ROW_CHUNK(lo, hi, k) \
+    ((k) < 4 ? make_uint4(lo[4 * (k)], lo[4 * (k) + 1], lo[4 * (k) + 2], lo[4 * (k) + 3]) \
+             : make_uint4(hi[4 * (k) - 16], hi[4 * (k) - 15], hi[4 * (k) - 14], hi[4 * (k) - 13]))
+__device__ __forceinline__ void set_chunk(uint32_t (&lo)[16], uint32_t (&hi)[16], int k, const uint4 &v) {
+    // k is always a compile-time constant after unrolling
+    if (k < 4) { lo[4 * k] = v.x; lo[4 * k + 1] = v.y; lo[4 * k + 2] = v.z; lo[4 * k + 3] = v.w; }
+    else { hi[4 * k - 16] = v.x; hi[4 * k - 15] = v.y; hi[4 * k - 14] = v.z; hi[4 * k - 13] = v.w; }
+}
+
+// =================================================================================================
+// K0: HMAC midstates
+// =================================================================================================
+__global__ void hmac_midstates_kernel(const uint8_t *__restrict__ commitments, uint32_t n, uint32_t *__restrict__ mid) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t key[8];
+    const uint32_t *c = reinterpret_cast<const uint32_t *>(commitments) + 8 * (size_t)i;
+#pragma unroll
+    for (int k = 0; k < 8; k++) key[k] = bswap32(c[k]);
+    HmacMid m;
+    hmac_midstates(key, m);
+#pragma unroll
+    for (int k = 0; k < 8; k++) { mid[16 * (size_t)i + k] = m.inner[k]; mid[16 * (size_t)i + 8 + k] = m.outer[k]; }
+}
+
+__device__ __forceinline__ void load_mid(const LabelJob &job, uint32_t slot, HmacMid &m) {
+    const uint32_t *p = job.mid + (size_t)job.mid_stride * slot;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { m.inner[k] = p[k]; m.outer[k] = p[8 + k]; }
+}
+__device__ __forceinline__ uint64_t slot_index(const LabelJob &job, uint32_t slot) {
+    if (job.indices) return slot < job.n_valid ? job.indices[slot] : 0;
+    return job.start + slot;
+}
+
+// =================================================================================================
+// K1: PBKDF2 expand  (8 SHA-256 compressions per label)
+// =================================================================================================
+__global__ void __launch_bounds__(128) pbkdf2_expand_kernel(LabelJob job, uint4 *__restrict__ X, uint32_t x_stride, uint32_t n_slots) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    HmacMid m;
+    load_mid(job, slot < job.n_valid ? slot : 0, m);
+    uint32_t lo[16], hi[16];
+    pbkdf2_expand(m, slot_index(job, slot), lo, hi);
+#pragma unroll
+    for (int k = 0; k < 8; k++) X[(size_t)k * x_stride + slot] = ROW_CHUNK(lo, hi, k);
+}
+
+// =================================================================================================
+// K2: ROMix.  V layout (all variants): per-warp interleave, row j of lane t at
+//     V + ((warp * N + j) * 32 + t) * 8 uint4      => in phase 1 a warp writes 4 KiB contiguous per j,
+//     and one lane's phase-2 reads stay inside its warp's 128*N*32-byte region (TLB-friendly).
+// COALESCED and BULK store rows "swizzled": chunk k of lane t sits at chunk position k ^ (t & 7).  V is
+// private scratch, so any layout is legal as long as reads undo it; the swizzle makes the dense
+// 32 x 128-B shared-memory tile bank-conflict-free in both the row-wise and the transposed access.
+// =================================================================================================
+template <int VARIANT, int MW, int TPB>
+__global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const uint32_t slot = blockIdx.x * TPB + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
+    if (slot >= p.n_slots) return;   // n_slots is a multiple of 32: whole warps leave together
+    const uint32_t N = p.N, mask = N - 1;
+    const RotConsts rc = p.rc;
+
+    uint32_t lo[16], hi[16];
+#pragma unroll
+    for (int k = 0; k < 8; k++) set_chunk(lo, hi, k, p.X[(size_t)k * p.x_stride + slot]);
+
+    uint4 *const Vw = p.V + (size_t)(slot >> 5) * N * 256;   // this warp's region; row j at Vw + j*256
+    const uint32_t swz = lane & 7;
+
+    if (VARIANT == ROMIX_DIRECT) {
+        uint4 *const Vt = Vw + lane * 8;
+        for (uint32_t i = 0; i < N; i++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) st_stream(Vt + (size_t)i * 256 + k, ROW_CHUNK(lo, hi, k));
+            blockmix_r1<MW>(lo, hi, rc);
+        }
+        for (uint32_t i = 0; i < N; i++) {
+            const uint32_t j = hi[0] & mask;
+            uint32_t vlo[16], vhi[16];
+#pragma unroll
+            for (int k = 0; k < 8; k++) set_chunk(vlo, vhi, k, ld_stream(Vt + (size_t)j * 256 + k));
+            blockmix_r1_xor<MW>(lo, hi, vlo, vhi, rc);
+        }
+    } else if (VARIANT == ROMIX_COALESCED) {
+        const uint32_t tile = smem_u32(smem_raw) + warp_in_cta * 4096;
+        const uint32_t own = tile + lane * 128;
+        const uint32_t tr_row = lane >> 3, tr_c = lane & 7;   // transposed role: row k*4+tr_row, chunk position tr_c
+        for (uint32_t i = 0; i < N; i++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) sts128(own + ((k ^ swz) << 4), ROW_CHUNK(lo, hi, k));
+            __syncwarp();
+            uint4 *const dst = Vw + (size_t)i * 256 + lane;   // + k*32: the warp writes 512 contiguous bytes per k
+#pragma unroll
+            for (int k = 0; k < 8; k++) st_stream(dst + k * 32, lds128(tile + (k * 4 + tr_row) * 128 + (tr_c << 4)));
+            __syncwarp();
+            blockmix_r1<MW>(lo, hi, rc);
+        }
+        for (uint32_t i = 0; i < N; i++) {
+            const uint32_t j = hi[0] & mask;
+            uint4 t[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t jr = __shfl_sync(0xffffffffu, j, k * 4 + tr_row);
+                t[k] = ld_stream(Vw + (size_t)jr * 256 + k * 32 + lane);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) sts128(tile + (k * 4 + tr_row) * 128 + (tr_c << 4), t[k]);
+            __syncwarp();
+            uint32_t vlo[16], vhi[16];
+#pragma unroll
+            for (int k = 0; k < 8; k++) set_chunk(vlo, vhi, k, lds128(own + ((k ^ swz) << 4)));
+            __syncwarp();
+            blockmix_r1_xor<MW>(lo, hi, vlo, vhi, rc);
+        }
+    } else if (VARIANT == ROMIX_BULK) {
+        // per warp: two 4-KiB tiles (double-buffered bulk stores in phase 1) + one mbarrier
+        constexpr uint32_t WARPS = TPB / 32;
+        const uint32_t tile0 = smem_u32(smem_raw) + warp_in_cta * 8192;
+        const uint32_t bar = smem_u32(smem_raw) + WARPS * 8192 + warp_in_cta * 8;
+        if (lane == 0) mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+        for (uint32_t i = 0; i < N; i++) {
+            const uint32_t tile = tile0 + (i & 1) * 4096;
+            if (lane == 0) bulk_wait_read<1>();   // the store issued two iterations ago has drained this tile
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; k++) sts128(tile + lane * 128 + ((k ^ swz) << 4), ROW_CHUNK(lo, hi, k));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { bulk_s2g(Vw + (size_t)i * 256, tile, 4096); bulk_commit(); }
+            blockmix_r1<MW>(lo, hi, rc);
+        }
+        if (lane == 0) bulk_wait_all<0>();
+        __syncwarp();
+        const uint32_t own = tile0 + lane * 128;
+        uint32_t parity = 0;
+        for (uint32_t i = 0; i < N; i++) {
+            const uint32_t j = hi[0] & mask;
+            if (lane == 0) mbar_expect_tx(bar, 4096);
+            __syncwarp();
+            bulk_g2s(own, Vw + (size_t)j * 256 + lane * 8, 128, bar);
+            mbar_wait(bar, parity);
+            parity ^= 1;
+            uint32_t vlo[16], vhi[16];
+#pragma unroll
+            for (int k = 0; k < 8; k++) set_chunk(vlo, vhi, k, lds128(own + ((k ^ swz) << 4)));
+            blockmix_r1_xor<MW>(lo, hi, vlo, vhi, rc);
+        }
+    } else {   // ROMIX_NOMEM: same arithmetic, no scratchpad (ALU ceiling probe only)
+        for (uint32_t i = 0; i < N; i++) blockmix_r1<MW>(lo, hi, rc);
+        for (uint32_t i = 0; i < N; i++) {
+            uint32_t vlo[16], vhi[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) { vlo[k] = hi[(k + 1) & 15] + i; vhi[k] = lo[(k + 3) & 15]; }
+            blockmix_r1_xor<MW>(lo, hi, vlo, vhi, rc);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) p.X[(size_t)k * p.x_stride + slot] = ROW_CHUNK(lo, hi, k);
+}
+
+// =================================================================================================
+// K3: PBKDF2 final + label output (TMA bulk store) + VRF candidate per CTA
+// =================================================================================================
+constexpr int FINAL_TPB = 128;
+
+// lexicographic (label_be[0..7], index) "a < b"
+__device__ __forceinline__ bool cand_less(const uint32_t (&a)[8], uint64_t ai, const uint32_t (&b)[8], uint64_t bi) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (a[k] != b[k]) return a[k] < b[k];
+    }
+    return ai < bi;
+}
+
+__global__ void __launch_bounds__(FINAL_TPB) pbkdf2_final_kernel(LabelJob job, const uint4 *__restrict__ X, uint32_t x_stride,
+                                                                 uint32_t n_slots, uint8_t *__restrict__ out16,
+                                                                 const uint32_t *__restrict__ vrf_be,
+                                                                 VrfCandidate *__restrict__ cta_cand) {
+    __shared__ __align__(128) uint4 stage[FINAL_TPB];
+    __shared__ VrfCandidate warp_best[FINAL_TPB / 32];
+    const uint32_t slot = blockIdx.x * FINAL_TPB + threadIdx.x;
+    const bool valid = slot < job.n_valid;
+    uint32_t lab[8];
+    uint64_t index = 0;
+    if (slot < n_slots) {
+        HmacMid m;
+        load_mid(job, valid ? slot : 0, m);
+        uint32_t lo[16], hi[16];
+#pragma unroll
+        for (int k = 0; k < 8; k++) set_chunk(lo, hi, k, X[(size_t)k * x_stride + slot]);
+        pbkdf2_final(m, lo, hi, lab);
+        index = slot_index(job, slot);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) lab[k] = 0xffffffffu;
+    }
+    // label = first 16 of the 32 output bytes; bytes are the big-endian serialisation of lab[]
+    stage[threadIdx.x] = make_uint4(bswap32(lab[0]), bswap32(lab[1]), bswap32(lab[2]), bswap32(lab[3]));
+    fence_proxy_async_smem();
+    __syncthreads();
+    const uint32_t cta_first = blockIdx.x * FINAL_TPB;
+    if (threadIdx.x == 0 && cta_first < job.n_valid) {
+        const uint32_t n_here = min((uint32_t)FINAL_TPB, job.n_valid - cta_first);
+        // one TMA bulk store per CTA: n_here x 16 contiguous bytes (16-B aligned, multiple of 16)
+        bulk_s2g(out16 + (size_t)cta_first * 16, smem_u32(stage), n_here * 16);
+        bulk_commit();
+        bulk_wait_all<0>();
+    }
+    if (vrf_be == nullptr) return;
+
+    // ---- VRF nonce candidate: min over valid slots with label32 < difficulty (strict), lowest index on ties
+    uint32_t diff[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) diff[k] = vrf_be[k];
+    bool cand = valid && cand_less(lab, 0, diff, 0) ;
+    if (cand) {   // cand_less with equal labels compares indices 0 < 0 = false => strict '<' on the label
+    }
+    if (!__syncthreads_or(cand)) {
+        if (threadIdx.x == 0) cta_cand[blockIdx.x].found = 0;
+        return;
+    }
+    // rare path: warp argmin by shuffles, then thread 0 merges the per-warp winners
+    uint32_t best[8];
+    uint64_t best_i = index;
+    uint32_t has = cand ? 1u : 0u;
+#pragma unroll
+    for (int k = 0; k < 8; k++) best[k] = lab[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        uint32_t o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = __shfl_xor_sync(0xffffffffu, best[k], off);
+        const uint64_t oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+        const uint32_t oh = __shfl_xor_sync(0xffffffffu, has, off);
+        const bool take = oh && (!has || cand_less(o, oi, best, best_i));
+        if (take) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) best[k] = o[k];
+            best_i = oi; has = 1;
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        VrfCandidate &w = warp_best[threadIdx.x >> 5];
+#pragma unroll
+        for (int k = 0; k < 8; k++) w.label_be[k] = best[k];
+        w.index = best_i; w.found = has; w.pad = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        VrfCandidate r = warp_best[0];
+        for (int wv = 1; wv < FINAL_TPB / 32; wv++) {
+            const VrfCandidate c = warp_best[wv];
+            if (c.found && (!r.found || cand_less(c.label_be, c.index, r.label_be, r.index))) r = c;
+        }
+        cta_cand[blockIdx.x] = r;
+    }
+}
+
+// K4: merge the per-CTA candidates of one wave into the running minimum (1 CTA, 256 threads)
+__global__ void __launch_bounds__(256) vrf_merge_kernel(const VrfCandidate *__restrict__ cta_cand, uint32_t n_cta,
+                                                         VrfCandidate *__restrict__ running) {
+    __shared__ VrfCandidate sh[256];
+    VrfCandidate r;
+    r.found = 0; r.index = 0; r.pad = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.label_be[k] = 0xffffffffu;
+    for (uint32_t i = threadIdx.x; i < n_cta; i += 256) {
+        const VrfCandidate c = cta_cand[i];
+        if (c.found && (!r.found || cand_less(c.label_be, c.index, r.label_be, r.index))) r = c;
+    }
+    sh[threadIdx.x] = r;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            const VrfCandidate c = sh[threadIdx.x + s];
+            VrfCandidate &m = sh[threadIdx.x];
+            if (c.found && (!m.found || cand_less(c.label_be, c.index, m.label_be, m.index))) m = c;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const VrfCandidate c = sh[0];
+        VrfCandidate m = *running;
+        if (c.found && (!m.found || cand_less(c.label_be, c.index, m.label_be, m.index))) *running = c;
+    }
+}
+
+// =================================================================================================
+// launch table
+// =================================================================================================
+cudaError_t launch_hmac_midstates(const uint8_t *d_commitments, uint32_t n, uint32_t *d_mid, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    hmac_midstates_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_commitments, n, d_mid);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pbkdf2_expand(const LabelJob &job, uint4 *X, uint32_t x_stride, uint32_t n_slots, cudaStream_t s) {
+    if (n_slots == 0) return cudaSuccess;
+    pbkdf2_expand_kernel<<<(n_slots + 127) / 128, 128, 0, s>>>(job, X, x_stride, n_slots);
+    return cudaGetLastError();
+}
+
+uint32_t pbkdf2_final_ctas(uint32_t n_slots) { return (n_slots + FINAL_TPB - 1) / FINAL_TPB; }
+
+cudaError_t launch_pbkdf2_final(const LabelJob &job, const uint4 *X, uint32_t x_stride, uint32_t n_slots, uint8_t *out16,
+                                const uint32_t *vrf_difficulty_be, VrfCandidate *cta_cand, cudaStream_t s) {
+    if (n_slots == 0) return cudaSuccess;
+    pbkdf2_final_kernel<<<pbkdf2_final_ctas(n_slots), FINAL_TPB, 0, s>>>(job, X, x_stride, n_slots, out16,
+                                                                         vrf_difficulty_be, cta_cand);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_vrf_merge(const VrfCandidate *cta_cand, uint32_t n_cta, VrfCandidate *running, cudaStream_t s) {
+    vrf_merge_kernel<<<1, 256, 0, s>>>(cta_cand, n_cta, running);
+    return cudaGetLastError();
+}
+
+size_t romix_smem_bytes(int variant, int tpb) {
+    const size_t warps = (size_t)tpb / 32;
+    if (variant == ROMIX_COALESCED) return warps * 4096;
+    if (variant == ROMIX_BULK) return warps * 8192 + warps * 8;
+    return 0;
+}
+
+const char *romix_variant_name(int variant) {
+    switch (variant) {
+        case ROMIX_DIRECT: return "direct";
+        case ROMIX_COALESCED: return "coalesced";
+        case ROMIX_BULK: return "bulk";
+        case ROMIX_NOMEM: return "nomem";
+    }
+    return "?";
+}
+
+typedef void (*romix_fn)(const RomixParams);
+
+template <int VARIANT, int MW>
+static romix_fn pick_tpb(int tpb) {
+    switch (tpb) {
+        case 64: return romix_kernel<VARIANT, MW, 64>;
+        case 128: return romix_kernel<VARIANT, MW, 128>;
+        case 256: return romix_kernel<VARIANT, MW, 256>;
+    }
+    return nullptr;
+}
+template <int VARIANT>
+static romix_fn pick_mw(int mw, int tpb) {
+    switch (mw) {
+        case 0: return pick_tpb<VARIANT, 0>(tpb);
+        case 5: return pick_tpb<VARIANT, 5>(tpb);
+        case 10: return pick_tpb<VARIANT, 10>(tpb);
+        case 15: return pick_tpb<VARIANT, 15>(tpb);
+    }
+    return nullptr;
+}
+static romix_fn pick(int variant, int mw, int tpb) {
+    switch (variant) {
+        case ROMIX_DIRECT: return pick_mw<ROMIX_DIRECT>(mw, tpb);
+        case ROMIX_COALESCED: return pick_mw<ROMIX_COALESCED>(mw, tpb);
+        case ROMIX_BULK: return pick_mw<ROMIX_BULK>(mw, tpb);
+        case ROMIX_NOMEM: return pick_mw<ROMIX_NOMEM>(mw, tpb);
+    }
+    return nullptr;
+}
+
+int romix_max_ctas_per_sm(int variant, int mulwide_mask, int tpb) {
+    romix_fn fn = pick(variant, mulwide_mask, tpb);
+    if (!fn) return 0;
+    const size_t smem = romix_smem_bytes(variant, tpb);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, tpb, smem) != cudaSuccess) return 0;
+    return n;
+}
+
+cudaError_t launch_romix(int variant, int mulwide_mask, int tpb, const RomixParams &p, cudaStream_t s) {
+    if (p.n_slots == 0) return cudaSuccess;
+    romix_fn fn = pick(variant, mulwide_mask, tpb);
+    if (!fn) return cudaErrorInvalidValue;
+    const size_t smem = romix_smem_bytes(variant, tpb);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    fn<<<(p.n_slots + tpb - 1) / tpb, tpb, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace b200post

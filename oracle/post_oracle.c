@@ -1,0 +1,529 @@
+/*
+ * post_oracle.c — CPU ORACLE (test infrastructure, see post_oracle.h for the parity status).
+ *
+ * Follows, by specification section rather than by any source file (the reference tree
+ * contains none of this arithmetic — SURVEY.md "Three facts" #1):
+ *   SHA-256 ............ FIPS 180-4 §6.2
+ *   HMAC ............... FIPS 198-1 §4
+ *   PBKDF2 ............. RFC 8018 §5.2
+ *   Salsa20/8, BlockMix, ROMix, scrypt ... RFC 7914 §3-§6
+ *   BLAKE3 ............. BLAKE3 paper §2 (zeebo/blake3 v0.2.4 is what hash/hash.go:16-25 calls)
+ *   AES-128 ............ FIPS-197
+ * Call-site anchors in the reference: activation/post.go:295,355-361 (init),
+ * activation/post_verifier.go:159 (verify), activation/validation.go:261-282 (VRF nonce).
+ */
+#define _POSIX_C_SOURCE 200809L
+#include "post_oracle.h"
+
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+/* ======================================================================== SHA-256 */
+static const uint32_t K256[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+    0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+    0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+    0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+
+typedef struct {
+    uint32_t h[8];
+    uint8_t buf[64];
+    uint64_t total;
+} sha256_ctx;
+
+static inline uint32_t ror32(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+static inline uint32_t rol32(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
+static inline uint32_t be32(const uint8_t *p) {
+    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+}
+static inline void put_be32(uint8_t *p, uint32_t v) {
+    p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v;
+}
+static inline uint32_t le32(const uint8_t *p) {
+    return ((uint32_t)p[3] << 24) | ((uint32_t)p[2] << 16) | ((uint32_t)p[1] << 8) | p[0];
+}
+static inline void put_le32(uint8_t *p, uint32_t v) {
+    p[3] = (uint8_t)(v >> 24); p[2] = (uint8_t)(v >> 16); p[1] = (uint8_t)(v >> 8); p[0] = (uint8_t)v;
+}
+
+static void sha256_compress(uint32_t h[8], const uint8_t blk[64]) {
+    uint32_t w[64];
+    for (int i = 0; i < 16; i++) w[i] = be32(blk + 4 * i);
+    for (int i = 16; i < 64; i++) {
+        uint32_t s0 = ror32(w[i - 15], 7) ^ ror32(w[i - 15], 18) ^ (w[i - 15] >> 3);
+        uint32_t s1 = ror32(w[i - 2], 17) ^ ror32(w[i - 2], 19) ^ (w[i - 2] >> 10);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+    for (int i = 0; i < 64; i++) {
+        uint32_t S1 = ror32(e, 6) ^ ror32(e, 11) ^ ror32(e, 25);
+        uint32_t ch = (e & f) ^ (~e & g);
+        uint32_t t1 = hh + S1 + ch + K256[i] + w[i];
+        uint32_t S0 = ror32(a, 2) ^ ror32(a, 13) ^ ror32(a, 22);
+        uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+        uint32_t t2 = S0 + mj;
+        hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+
+static void sha256_init(sha256_ctx *c) {
+    static const uint32_t iv[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a,
+                                   0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    memcpy(c->h, iv, sizeof iv);
+    c->total = 0;
+}
+static void sha256_update(sha256_ctx *c, const uint8_t *p, size_t n) {
+    size_t fill = (size_t)(c->total & 63);
+    c->total += n;
+    if (fill) {
+        size_t take = 64 - fill;
+        if (take > n) take = n;
+        memcpy(c->buf + fill, p, take);
+        p += take; n -= take; fill += take;
+        if (fill < 64) return;
+        sha256_compress(c->h, c->buf);
+    }
+    while (n >= 64) { sha256_compress(c->h, p); p += 64; n -= 64; }
+    if (n) memcpy(c->buf, p, n);
+}
+static void sha256_final(sha256_ctx *c, uint8_t out[32]) {
+    uint64_t bits = c->total * 8;
+    uint8_t pad[72];
+    size_t fill = (size_t)(c->total & 63);
+    size_t padlen = (fill < 56) ? (56 - fill) : (120 - fill);
+    memset(pad, 0, sizeof pad);
+    pad[0] = 0x80;
+    for (int i = 0; i < 8; i++) pad[padlen + i] = (uint8_t)(bits >> (56 - 8 * i));
+    sha256_update(c, pad, padlen + 8);
+    for (int i = 0; i < 8; i++) put_be32(out + 4 * i, c->h[i]);
+}
+
+void oracle_sha256(const uint8_t *msg, size_t len, uint8_t out[32]) {
+    sha256_ctx c;
+    sha256_init(&c);
+    sha256_update(&c, msg, len);
+    sha256_final(&c, out);
+}
+
+/* ======================================================================== HMAC / PBKDF2 */
+typedef struct { sha256_ctx inner, outer; } hmac_ctx;
+
+static void hmac_init(hmac_ctx *h, const uint8_t *key, size_t klen) {
+    uint8_t k[64], pad[64];
+    memset(k, 0, 64);
+    if (klen > 64) oracle_sha256(key, klen, k); else memcpy(k, key, klen);
+    for (int i = 0; i < 64; i++) pad[i] = k[i] ^ 0x36;
+    sha256_init(&h->inner); sha256_update(&h->inner, pad, 64);
+    for (int i = 0; i < 64; i++) pad[i] = k[i] ^ 0x5c;
+    sha256_init(&h->outer); sha256_update(&h->outer, pad, 64);
+}
+static void hmac_final(hmac_ctx *h, uint8_t out[32]) {
+    uint8_t d[32];
+    sha256_final(&h->inner, d);
+    sha256_update(&h->outer, d, 32);
+    sha256_final(&h->outer, out);
+}
+
+void oracle_hmac_sha256(const uint8_t *key, size_t klen, const uint8_t *msg, size_t mlen, uint8_t out[32]) {
+    hmac_ctx h;
+    hmac_init(&h, key, klen);
+    sha256_update(&h.inner, msg, mlen);
+    hmac_final(&h, out);
+}
+
+void oracle_pbkdf2_sha256(const uint8_t *pw, size_t pwlen, const uint8_t *salt, size_t saltlen,
+                          uint32_t iters, uint8_t *out, size_t dklen) {
+    hmac_ctx base;
+    hmac_init(&base, pw, pwlen);
+    uint32_t blk = 1;
+    while (dklen) {
+        uint8_t u[32], t[32], ctr[4];
+        hmac_ctx h = base;
+        put_be32(ctr, blk);
+        sha256_update(&h.inner, salt, saltlen);
+        sha256_update(&h.inner, ctr, 4);
+        hmac_final(&h, u);
+        memcpy(t, u, 32);
+        for (uint32_t i = 1; i < iters; i++) {
+            h = base;
+            sha256_update(&h.inner, u, 32);
+            hmac_final(&h, u);
+            for (int j = 0; j < 32; j++) t[j] ^= u[j];
+        }
+        size_t take = dklen < 32 ? dklen : 32;
+        memcpy(out, t, take);
+        out += take; dklen -= take; blk++;
+    }
+}
+
+/* ======================================================================== scrypt */
+void oracle_salsa20_8(uint32_t b[16]) {
+    uint32_t x[16];
+    memcpy(x, b, 64);
+#define QR(a, b_, c, d) \
+    x[b_] ^= rol32(x[a] + x[d], 7); x[c] ^= rol32(x[b_] + x[a], 9); \
+    x[d] ^= rol32(x[c] + x[b_], 13); x[a] ^= rol32(x[d] + x[c], 18);
+    for (int i = 0; i < 4; i++) {
+        /* column round */
+        QR(0, 4, 8, 12) QR(5, 9, 13, 1) QR(10, 14, 2, 6) QR(15, 3, 7, 11)
+        /* row round */
+        QR(0, 1, 2, 3) QR(5, 6, 7, 4) QR(10, 11, 8, 9) QR(15, 12, 13, 14)
+    }
+#undef QR
+    for (int i = 0; i < 16; i++) b[i] += x[i];
+}
+
+void oracle_blockmix(uint32_t *b, uint32_t *y, uint32_t r) {
+    uint32_t x[16];
+    memcpy(x, b + (2 * r - 1) * 16, 64);
+    for (uint32_t i = 0; i < 2 * r; i++) {
+        for (int k = 0; k < 16; k++) x[k] ^= b[i * 16 + k];
+        oracle_salsa20_8(x);
+        /* even blocks to the first half, odd blocks to the second (RFC 7914 §4 step 3) */
+        memcpy(y + ((i & 1) ? (r + i / 2) : (i / 2)) * 16, x, 64);
+    }
+    memcpy(b, y, 128 * (size_t)r);
+}
+
+static void romix(uint32_t *x, uint32_t *v, uint32_t *y, uint64_t N, uint32_t r) {
+    const size_t words = 32 * (size_t)r;
+    for (uint64_t i = 0; i < N; i++) {
+        memcpy(v + i * words, x, words * 4);
+        oracle_blockmix(x, y, r);
+    }
+    for (uint64_t i = 0; i < N; i++) {
+        /* Integerify: first 8 bytes of the last 64-byte sub-block, little-endian, mod N */
+        uint64_t j = ((uint64_t)x[(2 * r - 1) * 16] | ((uint64_t)x[(2 * r - 1) * 16 + 1] << 32)) & (N - 1);
+        const uint32_t *vj = v + j * words;
+        for (size_t k = 0; k < words; k++) x[k] ^= vj[k];
+        oracle_blockmix(x, y, r);
+    }
+}
+
+int oracle_scrypt(const uint8_t *pw, size_t pwlen, const uint8_t *salt, size_t saltlen,
+                  uint64_t N, uint32_t r, uint32_t p, uint8_t *out, size_t dklen) {
+    if (N < 2 || (N & (N - 1)) || r == 0 || p == 0) return -1;
+    const size_t blk = 128 * (size_t)r;
+    uint8_t *B = (uint8_t *)malloc(blk * p);
+    uint32_t *x = (uint32_t *)malloc(blk), *y = (uint32_t *)malloc(blk);
+    uint32_t *v = (uint32_t *)malloc(blk * N);
+    if (!B || !x || !y || !v) { free(B); free(x); free(y); free(v); return -1; }
+    oracle_pbkdf2_sha256(pw, pwlen, salt, saltlen, 1, B, blk * p);
+    for (uint32_t i = 0; i < p; i++) {
+        for (size_t k = 0; k < blk / 4; k++) x[k] = le32(B + i * blk + 4 * k);
+        romix(x, v, y, N, r);
+        for (size_t k = 0; k < blk / 4; k++) put_le32(B + i * blk + 4 * k, x[k]);
+    }
+    oracle_pbkdf2_sha256(pw, pwlen, B, blk * p, 1, out, dklen);
+    free(B); free(x); free(y); free(v);
+    return 0;
+}
+
+/* ======================================================================== BLAKE3 */
+static const uint32_t B3_IV[8] = {0x6A09E667, 0xBB67AE85, 0x3C6EF372, 0xA54FF53A,
+                                  0x510E527F, 0x9B05688C, 0x1F83D9AB, 0x5BE0CD19};
+static const uint8_t B3_PERM[16] = {2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8};
+enum { B3_CHUNK_START = 1, B3_CHUNK_END = 2, B3_PARENT = 4, B3_ROOT = 8 };
+
+static void b3_g(uint32_t *s, int a, int b, int c, int d, uint32_t mx, uint32_t my) {
+    s[a] = s[a] + s[b] + mx; s[d] = ror32(s[d] ^ s[a], 16);
+    s[c] = s[c] + s[d];      s[b] = ror32(s[b] ^ s[c], 12);
+    s[a] = s[a] + s[b] + my; s[d] = ror32(s[d] ^ s[a], 8);
+    s[c] = s[c] + s[d];      s[b] = ror32(s[b] ^ s[c], 7);
+}
+/* full 16-word compression output */
+static void b3_compress(const uint32_t cv[8], const uint32_t block[16], uint64_t counter,
+                        uint32_t block_len, uint32_t flags, uint32_t out[16]) {
+    uint32_t s[16], m[16], t[16];
+    memcpy(s, cv, 32);
+    memcpy(s + 8, B3_IV, 16);
+    s[12] = (uint32_t)counter; s[13] = (uint32_t)(counter >> 32); s[14] = block_len; s[15] = flags;
+    memcpy(m, block, 64);
+    for (int r = 0; r < 7; r++) {
+        b3_g(s, 0, 4, 8, 12, m[0], m[1]);   b3_g(s, 1, 5, 9, 13, m[2], m[3]);
+        b3_g(s, 2, 6, 10, 14, m[4], m[5]);  b3_g(s, 3, 7, 11, 15, m[6], m[7]);
+        b3_g(s, 0, 5, 10, 15, m[8], m[9]);  b3_g(s, 1, 6, 11, 12, m[10], m[11]);
+        b3_g(s, 2, 7, 8, 13, m[12], m[13]); b3_g(s, 3, 4, 9, 14, m[14], m[15]);
+        for (int i = 0; i < 16; i++) t[i] = m[B3_PERM[i]];
+        memcpy(m, t, 64);
+    }
+    for (int i = 0; i < 8; i++) { out[i] = s[i] ^ s[i + 8]; out[i + 8] = s[i + 8] ^ cv[i]; }
+}
+
+/* An "output" node: everything needed to finalise either as a chaining value or as root. */
+typedef struct { uint32_t cv[8]; uint32_t block[16]; uint64_t counter; uint32_t block_len, flags; } b3_output;
+
+static void b3_words(const uint8_t *p, size_t n, uint32_t w[16]) {
+    uint8_t tmp[64];
+    memset(tmp, 0, 64);
+    memcpy(tmp, p, n);
+    for (int i = 0; i < 16; i++) w[i] = le32(tmp + 4 * i);
+}
+/* hash one chunk (<= 1024 bytes) up to, but not including, its final compression */
+static b3_output b3_chunk(const uint8_t *p, size_t n, uint64_t chunk_counter) {
+    b3_output o;
+    uint32_t cv[8], full[16];
+    memcpy(cv, B3_IV, 32);
+    uint32_t flags = B3_CHUNK_START;
+    while (n > 64) {
+        b3_words(p, 64, o.block);
+        b3_compress(cv, o.block, chunk_counter, 64, flags, full);
+        memcpy(cv, full, 32);
+        flags = 0; p += 64; n -= 64;
+    }
+    memcpy(o.cv, cv, 32);
+    b3_words(p, n, o.block);
+    o.counter = chunk_counter; o.block_len = (uint32_t)n; o.flags = flags | B3_CHUNK_END;
+    return o;
+}
+static void b3_output_cv(const b3_output *o, uint32_t cv[8]) {
+    uint32_t full[16];
+    b3_compress(o->cv, o->block, o->counter, o->block_len, o->flags, full);
+    memcpy(cv, full, 32);
+}
+static b3_output b3_parent(const uint32_t l[8], const uint32_t r[8]) {
+    b3_output o;
+    memcpy(o.cv, B3_IV, 32);
+    memcpy(o.block, l, 32); memcpy(o.block + 8, r, 32);
+    o.counter = 0; o.block_len = 64; o.flags = B3_PARENT;
+    return o;
+}
+
+void oracle_blake3_xof(const uint8_t *msg, size_t len, uint8_t *out, size_t outlen) {
+    uint32_t stack[54][8];
+    int sp = 0;
+    uint64_t chunk = 0;
+    b3_output cur;
+    for (;;) {
+        size_t take = len > 1024 ? 1024 : len;
+        cur = b3_chunk(msg, take, chunk);
+        msg += take; len -= take;
+        if (len == 0) break;
+        /* not the last chunk: push its CV, merging completed subtrees */
+        uint32_t cv[8];
+        b3_output_cv(&cur, cv);
+        chunk++;
+        uint64_t total = chunk;
+        while ((total & 1) == 0) {
+            b3_output par = b3_parent(stack[--sp], cv);
+            b3_output_cv(&par, cv);
+            total >>= 1;
+        }
+        memcpy(stack[sp++], cv, 32);
+    }
+    while (sp > 0) {
+        uint32_t cv[8];
+        b3_output_cv(&cur, cv);
+        cur = b3_parent(stack[--sp], cv);
+    }
+    uint64_t ctr = 0;
+    while (outlen) {
+        uint32_t full[16];
+        uint8_t bytes[64];
+        b3_compress(cur.cv, cur.block, ctr++, cur.block_len, cur.flags | B3_ROOT, full);
+        for (int i = 0; i < 16; i++) put_le32(bytes + 4 * i, full[i]);
+        size_t take = outlen < 64 ? outlen : 64;
+        memcpy(out, bytes, take);
+        out += take; outlen -= take;
+    }
+}
+void oracle_blake3_256(const uint8_t *msg, size_t len, uint8_t out[32]) { oracle_blake3_xof(msg, len, out, 32); }
+
+/* ======================================================================== AES-128 */
+static uint8_t AES_SBOX[256];
+static int aes_ready;
+static uint8_t gf_mul(uint8_t a, uint8_t b) {
+    uint8_t p = 0;
+    while (b) { if (b & 1) p ^= a; a = (uint8_t)((a << 1) ^ ((a & 0x80) ? 0x1b : 0)); b >>= 1; }
+    return p;
+}
+static void aes_init_sbox(void) {
+    /* S(x) = affine(x^-1) over GF(2^8)/0x11b (FIPS-197 §5.1.1) */
+    for (int x = 0; x < 256; x++) {
+        uint8_t inv = 0;
+        if (x) for (int y = 1; y < 256; y++) if (gf_mul((uint8_t)x, (uint8_t)y) == 1) { inv = (uint8_t)y; break; }
+        uint8_t s = inv, r = inv;
+        for (int i = 0; i < 4; i++) { r = (uint8_t)((r << 1) | (r >> 7)); s ^= r; }
+        AES_SBOX[x] = s ^ 0x63;
+    }
+    aes_ready = 1;
+}
+void oracle_aes128_encrypt(const uint8_t key[16], const uint8_t in[16], uint8_t out[16]) {
+    if (!aes_ready) aes_init_sbox();
+    uint8_t rk[176], s[16];
+    memcpy(rk, key, 16);
+    uint8_t rcon = 1;
+    for (int i = 16; i < 176; i += 4) {
+        uint8_t t[4] = {rk[i - 4], rk[i - 3], rk[i - 2], rk[i - 1]};
+        if (i % 16 == 0) {
+            uint8_t u = t[0];
+            t[0] = AES_SBOX[t[1]] ^ rcon; t[1] = AES_SBOX[t[2]]; t[2] = AES_SBOX[t[3]]; t[3] = AES_SBOX[u];
+            rcon = (uint8_t)((rcon << 1) ^ ((rcon & 0x80) ? 0x1b : 0));
+        }
+        for (int k = 0; k < 4; k++) rk[i + k] = rk[i - 16 + k] ^ t[k];
+    }
+    for (int i = 0; i < 16; i++) s[i] = in[i] ^ rk[i];
+    for (int round = 1; round <= 10; round++) {
+        uint8_t t[16];
+        for (int i = 0; i < 16; i++) t[i] = AES_SBOX[s[i]];
+        /* ShiftRows: state is column-major, byte index = 4*col + row */
+        for (int c = 0; c < 4; c++)
+            for (int r = 0; r < 4; r++) s[4 * c + r] = t[4 * ((c + r) & 3) + r];
+        if (round != 10) {
+            for (int c = 0; c < 4; c++) {
+                uint8_t a0 = s[4 * c], a1 = s[4 * c + 1], a2 = s[4 * c + 2], a3 = s[4 * c + 3];
+                s[4 * c + 0] = (uint8_t)(gf_mul(a0, 2) ^ gf_mul(a1, 3) ^ a2 ^ a3);
+                s[4 * c + 1] = (uint8_t)(a0 ^ gf_mul(a1, 2) ^ gf_mul(a2, 3) ^ a3);
+                s[4 * c + 2] = (uint8_t)(a0 ^ a1 ^ gf_mul(a2, 2) ^ gf_mul(a3, 3));
+                s[4 * c + 3] = (uint8_t)(gf_mul(a0, 3) ^ a1 ^ a2 ^ gf_mul(a3, 2));
+            }
+        }
+        for (int i = 0; i < 16; i++) s[i] ^= rk[16 * round + i];
+    }
+    memcpy(out, s, 16);
+}
+
+/* ======================================================================== label path */
+void oracle_commitment(const uint8_t node_id[32], const uint8_t commitment_atx[32], uint8_t out[32]) {
+    uint8_t buf[64];
+    memcpy(buf, node_id, 32);
+    memcpy(buf + 32, commitment_atx, 32);
+    oracle_blake3_256(buf, 64, out);
+}
+
+/* r = p = 1 fast path used for every label: one allocation-free ROMix over caller scratch. */
+static void label32_r1(const uint8_t commitment[32], uint64_t index, uint64_t N, uint32_t *v, uint8_t out[32]) {
+    uint8_t salt[8], B[128];
+    uint32_t x[32], y[32];
+    for (int i = 0; i < 8; i++) salt[i] = (uint8_t)(index >> (8 * i)); /* LE64(index) — ASSUMED */
+    oracle_pbkdf2_sha256(commitment, 32, salt, 8, 1, B, 128);
+    for (int k = 0; k < 32; k++) x[k] = le32(B + 4 * k);
+    romix(x, v, y, N, 1);
+    for (int k = 0; k < 32; k++) put_le32(B + 4 * k, x[k]);
+    oracle_pbkdf2_sha256(commitment, 32, B, 128, 1, out, 32);
+}
+
+int oracle_label32(const uint8_t commitment[32], uint64_t index, uint64_t N, uint32_t r, uint32_t p,
+                   uint8_t out[32]) {
+    uint8_t salt[8];
+    for (int i = 0; i < 8; i++) salt[i] = (uint8_t)(index >> (8 * i));
+    return oracle_scrypt(commitment, 32, salt, 8, N, r, p, out, 32);
+}
+
+void oracle_vrf_difficulty(uint64_t num_labels, uint8_t out[32]) {
+    /* long division of 2^256 (33 bytes: 0x01 then 32 zero bytes) by num_labels, big-endian.
+     * num_labels <= 1 would need 2^256 itself, which does not fit: saturate to 0xff..ff. */
+    if (num_labels <= 1) { memset(out, 0xff, 32); return; }
+    unsigned __int128 rem = 1; /* the leading 0x01 byte; its quotient digit is 0 for n > 1 */
+    for (int i = 0; i < 32; i++) {
+        rem <<= 8;
+        out[i] = (uint8_t)(rem / num_labels);
+        rem %= num_labels;
+    }
+}
+
+typedef struct {
+    const uint8_t *commitment;      /* range mode: one commitment; gather mode: n x 32 */
+    const uint64_t *indices;        /* gather mode only */
+    uint64_t N, start, count;
+    uint8_t *out16;
+    const uint8_t *vrf_difficulty;
+    int tid, nthreads, gather;
+    int found; uint64_t best_index; uint8_t best[32];
+    int rc;
+} worker_arg;
+
+static void *worker(void *p) {
+    worker_arg *a = (worker_arg *)p;
+    uint32_t *v = (uint32_t *)malloc(128 * (size_t)a->N);
+    if (!v) { a->rc = -1; return NULL; }
+    /* contiguous sub-range per thread so that "first index wins ties" is easy to merge */
+    uint64_t per = (a->count + a->nthreads - 1) / a->nthreads;
+    uint64_t lo = per * a->tid, hi = lo + per;
+    if (hi > a->count) hi = a->count;
+    a->found = 0;
+    if (a->vrf_difficulty) memcpy(a->best, a->vrf_difficulty, 32);
+    for (uint64_t k = lo; k < hi; k++) {
+        uint8_t l32[32];
+        if (a->gather) label32_r1(a->commitment + 32 * k, a->indices[k], a->N, v, l32);
+        else label32_r1(a->commitment, a->start + k, a->N, v, l32);
+        if (a->out16) memcpy(a->out16 + 16 * k, l32, 16);
+        if (a->vrf_difficulty && memcmp(l32, a->best, 32) < 0) {
+            memcpy(a->best, l32, 32); a->best_index = a->start + k; a->found = 1;
+        }
+    }
+    free(v);
+    a->rc = 0;
+    return NULL;
+}
+
+static int run_workers(worker_arg *proto, int threads, int *found, uint64_t *best_index, uint8_t best_label32[32]) {
+    if (threads < 1) threads = 1;
+    if ((uint64_t)threads > proto->count && proto->count > 0) threads = (int)proto->count;
+    worker_arg *args = (worker_arg *)calloc((size_t)threads, sizeof *args);
+    pthread_t *th = (pthread_t *)calloc((size_t)threads, sizeof *th);
+    if (!args || !th) { free(args); free(th); return -1; }
+    for (int t = 0; t < threads; t++) {
+        args[t] = *proto; args[t].tid = t; args[t].nthreads = threads;
+        if (threads == 1) worker(&args[t]);
+        else if (pthread_create(&th[t], NULL, worker, &args[t])) { args[t].rc = -2; worker(&args[t]); th[t] = 0; }
+    }
+    int rc = 0;
+    for (int t = 0; t < threads; t++) {
+        if (threads > 1 && th[t]) pthread_join(th[t], NULL);
+        if (args[t].rc) rc = -1;
+    }
+    if (proto->vrf_difficulty && found) {
+        uint8_t best[32];
+        memcpy(best, proto->vrf_difficulty, 32);
+        *found = 0;
+        for (int t = 0; t < threads; t++) /* ascending index order + strict '<' keeps the first index on ties */
+            if (args[t].found && memcmp(args[t].best, best, 32) < 0) {
+                memcpy(best, args[t].best, 32); *found = 1;
+                if (best_index) *best_index = args[t].best_index;
+            }
+        if (*found && best_label32) memcpy(best_label32, best, 32);
+    }
+    free(args); free(th);
+    return rc;
+}
+
+int oracle_labels_range(const uint8_t commitment[32], uint64_t N, uint32_t r, uint32_t p,
+                        uint64_t start, uint64_t count, uint8_t *out16,
+                        const uint8_t *vrf_difficulty, int *found, uint64_t *best_index,
+                        uint8_t best_label32[32], int threads) {
+    if (N < 2 || (N & (N - 1)) || r != 1 || p != 1) return -1;
+    if (found) *found = 0;
+    if (count == 0) return 0;
+    worker_arg a;
+    memset(&a, 0, sizeof a);
+    a.commitment = commitment; a.N = N; a.start = start; a.count = count; a.out16 = out16;
+    a.vrf_difficulty = vrf_difficulty; a.gather = 0;
+    return run_workers(&a, threads, found, best_index, best_label32);
+}
+
+int oracle_labels_gather(size_t n, const uint8_t *commitments, const uint64_t *indices,
+                         uint64_t N, uint32_t r, uint32_t p, uint8_t *out16, int threads) {
+    if (N < 2 || (N & (N - 1)) || r != 1 || p != 1) return -1;
+    if (n == 0) return 0;
+    worker_arg a;
+    memset(&a, 0, sizeof a);
+    a.commitment = commitments; a.indices = indices; a.N = N; a.count = n; a.out16 = out16; a.gather = 1;
+    return run_workers(&a, threads, NULL, NULL, NULL);
+}
+
+double oracle_time_labels(const uint8_t commitment[32], uint64_t N, uint64_t start, uint64_t count,
+                          int threads, uint8_t *out16) {
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    oracle_labels_range(commitment, N, 1, 1, start, count, out16, NULL, NULL, NULL, NULL, threads);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}

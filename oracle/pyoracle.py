@@ -1,0 +1,199 @@
+"""CPU ORACLE, Python side — TEST INFRASTRUCTURE ONLY (see oracle/post_oracle.h for parity status).
+
+Two independent restatements of the POST label function live here:
+
+* ``py_*``  — OpenSSL ``hashlib.scrypt`` + the ``blake3`` wheel: trusted third-party primitives,
+  used to pin the C oracle and to generate tests/golden/*.json (oracle/gen_golden.py).
+* ``c_*``   — ctypes bindings of oracle/libpost_oracle.so (post_oracle.c), the fast checker the
+  GPU parity tests and bench.py's cpu_baseline use.
+
+Reference anchors: activation/post.go:295,355-361 (Initialize), activation/post_verifier.go:159
+(Verify), activation/validation.go:261-282 (VerifyVRFNonce), hash/hash.go:16-25 (blake3).
+Conventions marked ASSUMED in SURVEY.md Appendix A are "parity unpinned".
+
+Nothing in the product package imports this module.
+"""
+from __future__ import annotations
+
+import ctypes
+import hashlib
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "libpost_oracle.so"
+_lib = None
+
+
+def build(force: bool = False) -> Path:
+    """Compile oracle/libpost_oracle.so with the committed Makefile (gcc only)."""
+    src = _HERE / "post_oracle.c"
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(_HERE), "-s"] + (["-B"] if force else []), check=True)
+    return _LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(str(_LIB_PATH))
+        u8p, u64 = ctypes.c_char_p, ctypes.c_uint64
+        L.oracle_scrypt.argtypes = [u8p, ctypes.c_size_t, u8p, ctypes.c_size_t, u64, ctypes.c_uint32,
+                                    ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t]
+        L.oracle_scrypt.restype = ctypes.c_int
+        L.oracle_labels_range.argtypes = [u8p, u64, ctypes.c_uint32, ctypes.c_uint32, u64, u64, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(u64),
+                                          ctypes.c_void_p, ctypes.c_int]
+        L.oracle_labels_range.restype = ctypes.c_int
+        L.oracle_labels_gather.argtypes = [ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, u64, ctypes.c_uint32,
+                                           ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int]
+        L.oracle_labels_gather.restype = ctypes.c_int
+        L.oracle_time_labels.argtypes = [u8p, u64, u64, u64, ctypes.c_int, ctypes.c_void_p]
+        L.oracle_time_labels.restype = ctypes.c_double
+        L.oracle_label32.argtypes = [u8p, u64, u64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]
+        L.oracle_label32.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+# ----------------------------------------------------------------------------- python restatement
+def py_commitment(node_id: bytes, commitment_atx: bytes) -> bytes:
+    import blake3  # third-party wheel, present in this image
+
+    assert len(node_id) == 32 and len(commitment_atx) == 32
+    return blake3.blake3(node_id + commitment_atx).digest()
+
+
+def py_label32(commitment: bytes, index: int, n: int, r: int = 1, p: int = 1) -> bytes:
+    return hashlib.scrypt(commitment, salt=int(index).to_bytes(8, "little"), n=n, r=r, p=p, dklen=32,
+                          maxmem=256 * 1024 * 1024)
+
+
+def py_labels_range(commitment: bytes, n: int, start: int, count: int) -> bytes:
+    return b"".join(py_label32(commitment, start + i, n)[:16] for i in range(count))
+
+
+def py_vrf_difficulty(num_labels: int) -> bytes:
+    if num_labels <= 1:
+        return b"\xff" * 32
+    return ((1 << 256) // num_labels).to_bytes(32, "big")
+
+
+def py_vrf_scan(commitment: bytes, n: int, start: int, count: int, difficulty: bytes):
+    best, best_idx = difficulty, None
+    for i in range(start, start + count):
+        l32 = py_label32(commitment, i, n)
+        if l32 < best:
+            best, best_idx = l32, i
+    return best_idx, (best if best_idx is not None else None)
+
+
+# ----------------------------------------------------------------------------- C oracle wrappers
+def _buf(b):
+    return ctypes.c_char_p(bytes(b))
+
+
+def c_scrypt(pw: bytes, salt: bytes, n: int, r: int, p: int, dklen: int) -> bytes:
+    out = ctypes.create_string_buffer(dklen)
+    rc = lib().oracle_scrypt(pw, len(pw), salt, len(salt), n, r, p, out, dklen)
+    if rc:
+        raise ValueError("oracle_scrypt: bad parameters")
+    return out.raw
+
+
+def _hash32(fn_name: str, msg: bytes) -> bytes:
+    out = ctypes.create_string_buffer(32)
+    getattr(lib(), fn_name)(msg, ctypes.c_size_t(len(msg)), out)
+    return out.raw
+
+
+def c_sha256(msg: bytes) -> bytes:
+    return _hash32("oracle_sha256", msg)
+
+
+def c_blake3(msg: bytes, outlen: int = 32) -> bytes:
+    out = ctypes.create_string_buffer(outlen)
+    lib().oracle_blake3_xof(msg, ctypes.c_size_t(len(msg)), out, ctypes.c_size_t(outlen))
+    return out.raw
+
+
+def c_hmac_sha256(key: bytes, msg: bytes) -> bytes:
+    out = ctypes.create_string_buffer(32)
+    lib().oracle_hmac_sha256(key, ctypes.c_size_t(len(key)), msg, ctypes.c_size_t(len(msg)), out)
+    return out.raw
+
+
+def c_pbkdf2(pw: bytes, salt: bytes, iters: int, dklen: int) -> bytes:
+    out = ctypes.create_string_buffer(dklen)
+    lib().oracle_pbkdf2_sha256(pw, ctypes.c_size_t(len(pw)), salt, ctypes.c_size_t(len(salt)),
+                               ctypes.c_uint32(iters), out, ctypes.c_size_t(dklen))
+    return out.raw
+
+
+def c_aes128(key: bytes, block: bytes) -> bytes:
+    out = ctypes.create_string_buffer(16)
+    lib().oracle_aes128_encrypt(key, block, out)
+    return out.raw
+
+
+def c_commitment(node_id: bytes, commitment_atx: bytes) -> bytes:
+    out = ctypes.create_string_buffer(32)
+    lib().oracle_commitment(node_id, commitment_atx, out)
+    return out.raw
+
+
+def c_vrf_difficulty(num_labels: int) -> bytes:
+    out = ctypes.create_string_buffer(32)
+    lib().oracle_vrf_difficulty(ctypes.c_uint64(num_labels), out)
+    return out.raw
+
+
+def c_label32(commitment: bytes, index: int, n: int, r: int = 1, p: int = 1) -> bytes:
+    out = ctypes.create_string_buffer(32)
+    if lib().oracle_label32(commitment, index, n, r, p, out):
+        raise ValueError("oracle_label32: bad parameters")
+    return out.raw
+
+
+def default_threads() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def c_labels_range(commitment: bytes, n: int, start: int, count: int, vrf_difficulty: bytes | None = None,
+                   threads: int | None = None):
+    """Returns (labels uint8[count,16], found, best_index, best_label32)."""
+    out = np.empty((count, 16), dtype=np.uint8)
+    found = ctypes.c_int(0)
+    best_idx = ctypes.c_uint64(0)
+    best = ctypes.create_string_buffer(32)
+    rc = lib().oracle_labels_range(commitment, n, 1, 1, start, count, out.ctypes.data,
+                                   ctypes.cast(ctypes.c_char_p(vrf_difficulty), ctypes.c_void_p)
+                                   if vrf_difficulty is not None else None,
+                                   ctypes.byref(found), ctypes.byref(best_idx), best,
+                                   threads or default_threads())
+    if rc:
+        raise ValueError("oracle_labels_range failed")
+    if vrf_difficulty is None or not found.value:
+        return out, False, None, None
+    return out, True, best_idx.value, best.raw
+
+
+def c_labels_gather(commitments: np.ndarray, indices: np.ndarray, n: int, threads: int | None = None) -> np.ndarray:
+    commitments = np.ascontiguousarray(commitments, dtype=np.uint8).reshape(-1, 32)
+    indices = np.ascontiguousarray(indices, dtype=np.uint64)
+    assert commitments.shape[0] == indices.shape[0]
+    out = np.empty((indices.shape[0], 16), dtype=np.uint8)
+    rc = lib().oracle_labels_gather(indices.shape[0], commitments.ctypes.data, indices.ctypes.data, n, 1, 1,
+                                    out.ctypes.data, threads or default_threads())
+    if rc:
+        raise ValueError("oracle_labels_gather failed")
+    return out
+
+
+def c_time_labels(commitment: bytes, n: int, start: int, count: int, threads: int) -> float:
+    out = np.empty((count, 16), dtype=np.uint8)
+    return float(lib().oracle_time_labels(commitment, n, start, count, threads, out.ctypes.data))
