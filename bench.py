@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py — POST label throughput (labels/s) of the B200 engine, per the driver's contract.
+
+Workload (BASELINE.json configs[1]): 4-SU init, scrypt N = 8192, r = p = 1, single B200, labels
+discarded ("/dev/null").  One *step* = one batch of `--batch` consecutive labels of the 2^34-label
+index space (default: 4 waves of resident scratchpads), exactly what one `initialize(start, end)`
+call of the reference's initializer does per ComputeBatchSize batch (activation/post.go:295).
+
+  value      labels/s with the output resident in HBM (b200post_labels_range_dev), device-timed
+  e2e        labels/s through the host-buffer C-ABI call (b200post_labels_range): commitment H2D and
+             16 B/label D2H inside the timed region
+  roofline   the ROMix kernel against the measured HBM copy bandwidth; algorithmic bytes =
+             2*128*N + 16 = 2 097 168 B/label
+  cpu_baseline  the oracle port on this box's host cores (bounded sample)
+
+N > 1 (torchrun): one process per GPU, contiguous index shards, no data-path collective; the only
+exchange is an NCCL all-gather of one 48-byte VRF candidate per rank per step.
+
+`--impl reference` times the CPU oracle (the reference's own provider cannot be built here:
+DESIGN.md §3) on rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_SCRYPT = 8192
+BYTES_PER_LABEL = 2 * 128 * N_SCRYPT + 16          # algorithmic HBM bytes per label
+NUM_LABELS_4SU = 4 * 2**32
+METRIC = "POST labels/sec (scrypt N=8192 init)"
+HBM_FALLBACK_GBS = 6650.0                          # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:  # noqa: BLE001
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(orc, seconds_target: float = 12.0) -> dict:
+    """Oracle port timed on all host cores on a bounded sample of the same workload."""
+    cores = orc.default_threads()
+    commitment = bytes(range(32))
+    probe = max(cores * 8, 64)
+    t = orc.c_time_labels(commitment, N_SCRYPT, 0, probe, cores)
+    rate = probe / t
+    sample = int(max(cores * 32, min(rate * seconds_target, 1 << 20)))
+    t = orc.c_time_labels(commitment, N_SCRYPT, 1 << 20, sample, cores)
+    return {"value": sample / t, "unit": "labels/s", "cores": cores, "kind": "port",
+            "sample": f"{sample} labels of the N=8192 init (oracle/post_oracle.c, {cores} pthreads, {t:.1f} s)"}
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    """--impl reference: the CPU oracle (port) on rank 0; other ranks exit 0 without work."""
+    if rank != 0:
+        return
+    from oracle import pyoracle as orc
+    orc.build()
+    cores = orc.default_threads()
+    commitment = bytes(range(32))
+    per_step = max(cores * 64, 256)      # bounded sample per step (~0.2 s per 64 labels per core)
+    for w in range(args.warmup):
+        orc.c_time_labels(commitment, N_SCRYPT, w * per_step, min(per_step, cores * 8), cores)
+    t_total = 0.0
+    for s in range(args.steps):
+        t_total += orc.c_time_labels(commitment, N_SCRYPT, (1 << 24) + s * per_step, per_step, cores)
+    value = per_step * args.steps / t_total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "labels/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "4-SU POST init (2^34 labels), scrypt N=8192 r=1 p=1, labels discarded",
+                       "step": f"bounded sample: {per_step} labels per step on {cores} host threads"},
+            "cpu_baseline": {"value": value, "unit": "labels/s", "cores": cores, "kind": "port",
+                             "sample": f"{per_step} labels/step x {args.steps} steps, oracle/post_oracle.c"},
+            "e2e": {"value": value, "unit": "labels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="labels per step per GPU (0 = 4 waves)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    b2 = importlib.import_module("go-spacemesh_b200")
+    if not b2.LIB_PATH.exists():
+        raise SystemExit("libb200post.so missing: run __graft_entry__.build() (no fallback path exists)")
+    if not torch.cuda.is_available() or not b2.providers():
+        raise SystemExit("bench.py needs a CUDA device: the label engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    prov = b2.providers()[local_rank]
+    commitment = b2.commitment(bytes(range(32)), bytes(range(32, 64)))
+    diff = b2.vrf_difficulty(NUM_LABELS_4SU * world)
+
+    wave = b2.wave_slots(N_SCRYPT, provider=local_rank)                    # resident scratchpads per wave
+    tpb = b2.get_option("tpb")
+    batch = args.batch or 4 * wave
+    d_out = torch.empty((batch, 16), dtype=torch.uint8, device=dev)        # labels stay in HBM for `value`
+    h_out = np.empty((batch, 16), dtype=np.uint8)                          # host sink for `e2e`
+
+    def shard_start(step: int) -> int:
+        # weak scaling: every rank initialises its own contiguous slice of a (4*world)-SU space
+        return rank * NUM_LABELS_4SU + step * batch
+
+    cand = torch.zeros((12,), dtype=torch.int64, device=dev)               # 48-byte VRF record + padding
+    gathered = [torch.zeros_like(cand) for _ in range(world)] if world > 1 else None
+
+    def exchange(vrf):
+        """The path's only exchange step: min-reduction of the VRF nonce candidate over ranks."""
+        if world == 1:
+            return vrf
+        rec = np.zeros(12, dtype=np.int64)
+        if vrf is not None:
+            rec[0] = 1
+            rec[1] = np.int64(np.uint64(vrf[0]).astype(np.int64))
+            rec[2:6] = np.frombuffer(vrf[1], dtype=">u8").astype(np.uint64).view(np.int64)
+        cand.copy_(torch.from_numpy(rec), non_blocking=False)
+        dist.all_gather(gathered, cand)
+        best = None
+        for g in gathered:
+            r = g.cpu().numpy()
+            if r[0]:
+                key = (tuple(int(x) for x in r[2:6].view(np.uint64)), int(np.uint64(r[1])))
+                if best is None or key < best:
+                    best = key
+        return best
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps: int, first_step: int):
+        """K steps bracketed by barrier + synchronize; returns (wall seconds max over ranks, device ms sum)."""
+        barrier()
+        t0 = time.perf_counter()
+        dev_ms = 0.0
+        for s in range(steps):
+            fn(first_step + s)
+            dev_ms += b2.last_call_ms(local_rank)
+        barrier()
+        el = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([el, dev_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el, dev_ms = float(t[0]), float(t[1])
+        return el, dev_ms
+
+    def step_dev(s: int):
+        vrf = b2.labels_range_dev(commitment, N_SCRYPT, shard_start(s), batch, d_out.data_ptr(), provider=local_rank,
+                                  vrf_difficulty_=diff)
+        exchange(vrf)
+
+    def step_e2e(s: int):
+        nonce = b2.VrfNonce()
+        import ctypes
+        rc = b2.lib().b200post_labels_range(local_rank, commitment, N_SCRYPT, shard_start(s), batch, h_out.ctypes.data,
+                                            ctypes.cast(ctypes.c_char_p(diff), ctypes.c_void_p), ctypes.byref(nonce), None)
+        if rc:
+            raise RuntimeError(b2.lib().b200post_last_error().decode())
+        exchange((int(nonce.index), bytes(nonce.label32)) if nonce.found else None)
+
+    # ---- device-resident arm (value)
+    for w in range(args.warmup):
+        step_dev(w)
+    b2.romix_time(provider=local_rank, reset=True)
+    launches0 = b2.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    wall, dev_ms = timed(step_dev, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = b2.launch_count() - launches0
+    romix_ms, romix_k = b2.romix_time(provider=local_rank, reset=True)
+
+    # ---- end-to-end arm (host buffers through the reference-facing C-ABI call)
+    for w in range(2):
+        step_e2e(args.warmup + args.steps + w)
+    wall_e2e, _ = timed(step_e2e, args.steps, 2 * args.warmup + args.steps + 2)
+
+    total_labels = batch * args.steps * world
+    # device-event time is the clock for `value` (max over ranks); wall clock is the cross-check
+    value = total_labels / (dev_ms / 1e3) if dev_ms > 0 else total_labels / wall
+    value_wall = total_labels / wall
+    e2e_value = total_labels / wall_e2e
+
+    peak, peak_src = measured_peaks()
+    labels_per_launch = batch * args.steps / max(romix_k, 1)
+    romix_avg_ms = romix_ms / max(romix_k, 1)
+    achieved = labels_per_launch * BYTES_PER_LABEL / (romix_avg_ms / 1e3) / 1e9 if romix_avg_ms > 0 else 0.0
+    traffic = None
+    tfile = ROOT / "profiles" / "romix_dram_bytes_per_launch.json"
+    if tfile.exists():
+        try:
+            traffic = json.loads(tfile.read_text()).get("dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            traffic = None
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "labels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "4-SU POST init (2^34 labels/GPU), scrypt N=8192 r=1 p=1, labels discarded (/dev/null sink)",
+                       "labels_per_step_per_gpu": batch, "wave_slots": wave, "provider": prov["model"],
+                       "romix_variant": b2.get_option("romix_variant"), "mulwide_mask": b2.get_option("mulwide_mask"),
+                       "tpb": tpb, "l2": "working set = wave_slots x 1 MiB scratch >> 126 MB L2; every step uses fresh indices",
+                       "parallelism": f"index-range shards x{world}, NCCL all-gather of one 48-B VRF record per step" if world > 1 else "single GPU",
+                       "timer": "CUDA events on the engine stream, summed over steps, max over ranks",
+                       "value_wall_clock": value_wall},
+            "e2e": {"value": e2e_value, "unit": "labels/s", "h2d_bytes_per_step": 32 + 32, "d2h_bytes_per_step": batch * 16 + 48},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "romix_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+                         "bytes_per_label": BYTES_PER_LABEL, "labels_per_launch": labels_per_launch,
+                         "avg_launch_ms": romix_avg_ms, "launches_timed": int(romix_k),
+                         "kernel_share_of_step": (romix_ms / dev_ms) if dev_ms else None},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            from oracle import pyoracle as orc
+            orc.build()
+            line["cpu_baseline"] = cpu_baseline(orc)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

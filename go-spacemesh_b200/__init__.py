@@ -86,6 +86,9 @@ def lib() -> ctypes.CDLL:
     L.b200post_benchmark.argtypes = [u32, u64, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
     L.b200post_launch_count.restype = ctypes.c_uint64
     L.b200post_romix_time.argtypes = [u32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64), ctypes.c_int]
+    L.b200post_last_call_ms.argtypes = [u32]
+    L.b200post_last_call_ms.restype = ctypes.c_double
+    L.b200post_wave_slots.argtypes = [u32, u64, ctypes.POINTER(u64)]
     L.b200post_shutdown.restype = None
     _lib = L
     return L
@@ -215,6 +218,18 @@ def romix_time(provider: int = 0, reset: bool = False) -> tuple[float, int]:
     ms, k = ctypes.c_double(0), ctypes.c_uint64(0)
     _check(lib().b200post_romix_time(provider, ctypes.byref(ms), ctypes.byref(k), int(reset)))
     return ms.value, int(k.value)
+
+
+def last_call_ms(provider: int = 0) -> float:
+    """Device time (CUDA events on the engine's stream) of the last labels_* call on `provider`."""
+    return float(lib().b200post_last_call_ms(provider))
+
+
+def wave_slots(n: int = 8192, provider: int = 0) -> int:
+    """Labels one wave holds (= ROMix scratchpads resident at once) for scrypt-N."""
+    v = ctypes.c_uint64(0)
+    _check(lib().b200post_wave_slots(provider, n, ctypes.byref(v)))
+    return int(v.value)
 
 
 def shutdown() -> None:

@@ -71,7 +71,9 @@ int b200post_set_option(const char *key, int64_t value) {
     Options &o = options();
     const std::string k(key);
     if (k == "romix_variant" && value >= 0 && value <= 3) { o.romix_variant = value; return B200POST_OK; }
-    if (k == "mulwide_mask" && (value == 0 || value == 5 || value == 10 || value == 15)) { o.mulwide_mask = value; return B200POST_OK; }
+    if (k == "mulwide_mask" && (value == 0 || value == 5 || value == 15)) { o.mulwide_mask = value; return B200POST_OK; }
+    if (k == "mem_policy" && value >= 0 && value <= 2) { o.mem_policy = value; return B200POST_OK; }
+    if (k == "debug_skip_phase" && value >= 0 && value <= 3) { o.debug_skip_phase = value; return B200POST_OK; }
     if (k == "tpb" && (value == 64 || value == 128 || value == 256)) { o.tpb = value; return B200POST_OK; }
     if (k == "ctas_per_sm" && value >= 0 && value <= 32) { o.ctas_per_sm = value; return B200POST_OK; }
     if (k == "max_scratch_mib" && value >= 0) { o.max_scratch_mib = value; return B200POST_OK; }
@@ -86,6 +88,8 @@ int64_t b200post_get_option(const char *key) {
     if (k == "romix_variant") return o.romix_variant;
     if (k == "mulwide_mask") return o.mulwide_mask;
     if (k == "tpb") return o.tpb;
+    if (k == "mem_policy") return o.mem_policy;
+    if (k == "debug_skip_phase") return o.debug_skip_phase;
     if (k == "ctas_per_sm") return o.ctas_per_sm;
     if (k == "max_scratch_mib") return o.max_scratch_mib;
     return -1;
@@ -206,6 +210,19 @@ int b200post_romix_time(uint32_t provider, double *ms_total, uint64_t *launches,
     if (!e) return B200POST_ERR_NO_DEVICE;
     e->romix_time(ms_total, launches, reset != 0);
     return B200POST_OK;
+}
+
+int b200post_wave_slots(uint32_t provider, uint64_t n, uint64_t *slots) {
+    if (!slots || !valid_n(n)) { set_error("invalid argument"); return B200POST_ERR_INVALID_ARGUMENT; }
+    DeviceEngine *e = engine_for(provider);
+    if (!e) return provider == B200POST_CPU_PROVIDER_ID ? B200POST_ERR_UNSUPPORTED : B200POST_ERR_NO_DEVICE;
+    *slots = e->wave_slots(n);
+    return *slots ? B200POST_OK : B200POST_ERR_CUDA;
+}
+
+double b200post_last_call_ms(uint32_t provider) {
+    DeviceEngine *e = engine_for(provider);
+    return e ? e->last_call_ms() : -1.0;
 }
 
 void b200post_shutdown(void) { shutdown_all(); }

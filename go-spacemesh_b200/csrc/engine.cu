@@ -53,7 +53,8 @@ void DeviceEngine::release() {
         if (ev_done_[b]) cudaEventDestroy(ev_done_[b]);
         if (ev_k2a_[b]) cudaEventDestroy(ev_k2a_[b]);
         if (ev_k2b_[b]) cudaEventDestroy(ev_k2b_[b]);
-        ev_done_[b] = ev_k2a_[b] = ev_k2b_[b] = nullptr;
+        if (ev_call_[b]) cudaEventDestroy(ev_call_[b]);
+        ev_done_[b] = ev_k2a_[b] = ev_k2b_[b] = ev_call_[b] = nullptr;
         k2_pending_[b] = false;
     }
     cudaFree(d_commit_); d_commit_ = nullptr;
@@ -81,13 +82,14 @@ int DeviceEngine::ensure(uint64_t N, uint64_t want_slots) {
             CU_TRY(cudaEventCreateWithFlags(&ev_done_[b], cudaEventDisableTiming));
             CU_TRY(cudaEventCreate(&ev_k2a_[b]));
             CU_TRY(cudaEventCreate(&ev_k2b_[b]));
+            CU_TRY(cudaEventCreate(&ev_call_[b]));
         }
         CU_TRY(cudaMalloc(&d_diff_, 32));
         CU_TRY(cudaMalloc(&d_running_, sizeof(VrfCandidate)));
         CU_TRY(cudaMallocHost(&h_running_, sizeof(VrfCandidate)));
     }
-    variant_ = variant; mw_ = mw; tpb_ = tpb;
-    int ctas = romix_max_ctas_per_sm(variant, mw, tpb);
+    variant_ = variant; mw_ = mw; tpb_ = tpb; policy_ = (int)o.mem_policy.load();
+    int ctas = romix_max_ctas_per_sm(variant, mw, policy_, tpb);
     if (ctas <= 0) { set_error("romix kernel cannot be resident (bad variant/mask/tpb?)"); return B200POST_ERR_INVALID_ARGUMENT; }
     const int64_t want_ctas = o.ctas_per_sm.load();
     if (want_ctas > 0) ctas = std::min<int>(ctas, (int)want_ctas);
@@ -152,9 +154,10 @@ int DeviceEngine::run_wave(const LabelJob &job, uint32_t n_slots, uint64_t N, ui
     CU_TRY(launch_pbkdf2_expand(job, X_, alloc_slots_, n_slots, stream_));
     RomixParams rp;
     rp.V = V_; rp.X = X_; rp.x_stride = alloc_slots_; rp.N = (uint32_t)N; rp.n_slots = n_slots;
+    rp.flags = (uint32_t)options().debug_skip_phase.load();
     rp.rc = RotConsts{1u << 7, 1u << 9, 1u << 13, 1u << 18};
     CU_TRY(cudaEventRecord(ev_k2a_[buf], stream_));
-    CU_TRY(launch_romix(variant_, mw_, tpb_, rp, stream_));
+    CU_TRY(launch_romix(variant_, mw_, policy_, tpb_, rp, stream_));
     CU_TRY(cudaEventRecord(ev_k2b_[buf], stream_));
     k2_pending_[buf] = true;
     CU_TRY(launch_pbkdf2_final(job, X_, alloc_slots_, n_slots, d_out, d_diff, d_cta_cand_, stream_));
@@ -175,6 +178,7 @@ int DeviceEngine::labels_range(const uint8_t commitment[32], uint64_t N, uint64_
     int rc = ensure(N, count);
     if (rc) return rc;
 
+    CU_TRY(cudaEventRecord(ev_call_[0], stream_));
     // per-call constants: commitment -> HMAC midstates (K0), VRF threshold, running candidate
     CU_TRY(cudaMemcpyAsync(d_commit_, commitment, 32, cudaMemcpyHostToDevice, stream_));
     CU_TRY(launch_hmac_midstates(d_commit_, 1, d_mid_, stream_));
@@ -233,7 +237,9 @@ int DeviceEngine::labels_range(const uint8_t commitment[32], uint64_t N, uint64_
             }
         }
     }
+    CU_TRY(cudaEventRecord(ev_call_[1], stream_));
     CU_TRY(cudaStreamSynchronize(stream_));
+    { float ms = 0; if (cudaEventElapsedTime(&ms, ev_call_[0], ev_call_[1]) == cudaSuccess) last_call_ms_ = ms; }
     if (status == B200POST_ERR_CANCELLED) set_error("cancelled");
     return status;
 }
@@ -244,6 +250,7 @@ int DeviceEngine::labels_gather(size_t n_items, const uint8_t *commitments, cons
     if (n_items == 0) return B200POST_OK;
     int rc = ensure(N, n_items);
     if (rc) return rc;
+    CU_TRY(cudaEventRecord(ev_call_[0], stream_));
     const uint64_t wave = std::min<uint64_t>(wave_slots_, alloc_slots_);
     uint64_t done = 0;
     // single-buffered inputs (they are consumed by K0/K1 at the head of the wave), double-buffered outputs
@@ -279,8 +286,22 @@ int DeviceEngine::labels_gather(size_t n_items, const uint8_t *commitments, cons
         w++;
     }
     for (int k = 0; k < 2; k++) if ((rc = retire((w + k) & 1))) return rc;
+    CU_TRY(cudaEventRecord(ev_call_[1], stream_));
     CU_TRY(cudaStreamSynchronize(stream_));
+    { float ms = 0; if (cudaEventElapsedTime(&ms, ev_call_[0], ev_call_[1]) == cudaSuccess) last_call_ms_ = ms; }
     return B200POST_OK;
+}
+
+uint32_t DeviceEngine::wave_slots(uint64_t N) {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (cudaSetDevice(dev_) != cudaSuccess) return 0;
+    if (ensure(N, 32) != B200POST_OK) return 0;
+    return wave_slots_;
+}
+
+double DeviceEngine::last_call_ms() {
+    std::lock_guard<std::mutex> lk(mu_);
+    return last_call_ms_;
 }
 
 void DeviceEngine::romix_time(double *ms_total, uint64_t *launches, bool reset) {

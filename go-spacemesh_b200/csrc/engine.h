@@ -19,6 +19,8 @@ struct Options {
     std::atomic<int64_t> romix_variant{ROMIX_DIRECT};
     std::atomic<int64_t> mulwide_mask{0};
     std::atomic<int64_t> tpb{128};
+    std::atomic<int64_t> mem_policy{0};        // 0 ld.cs/st.cs, 1 default, 2 .cg
+    std::atomic<int64_t> debug_skip_phase{0};  // diagnostics only: bit0 skip fill, bit1 skip mix (labels become garbage)
     std::atomic<int64_t> ctas_per_sm{0};       // 0 = occupancy maximum
     std::atomic<int64_t> max_scratch_mib{0};   // 0 = 90 % of free HBM
 };
@@ -42,6 +44,10 @@ public:
                      uint8_t *out_dev, const uint8_t *vrf_difficulty, VrfResult *vrf, const volatile int *cancel);
     int labels_gather(size_t n_items, const uint8_t *commitments, const uint64_t *indices, uint64_t N, uint8_t *out_host);
     void romix_time(double *ms_total, uint64_t *launches, bool reset);
+    // device time (CUDA events on the engine's stream) of the last labels_range / labels_gather call
+    double last_call_ms();
+    // slots (labels) one wave holds for scrypt-N under the current options; 0 + error text on failure
+    uint32_t wave_slots(uint64_t N);
     int device() const { return dev_; }
     const cudaDeviceProp &prop() const { return prop_; }
 
@@ -75,10 +81,12 @@ private:
     cudaEvent_t ev_done_[2] = {nullptr, nullptr};
     cudaEvent_t ev_k2a_[2] = {nullptr, nullptr}, ev_k2b_[2] = {nullptr, nullptr};
     bool k2_pending_[2] = {false, false};
+    cudaEvent_t ev_call_[2] = {nullptr, nullptr};
+    double last_call_ms_ = 0;
     double romix_ms_ = 0;
     uint64_t romix_launches_ = 0;
     // current tuning
-    int variant_ = 0, mw_ = 0, tpb_ = 128;
+    int variant_ = 0, mw_ = 0, tpb_ = 128, policy_ = 0;
 };
 
 // registry: lazily created engine per CUDA ordinal (nullptr + error text if the device is unusable)

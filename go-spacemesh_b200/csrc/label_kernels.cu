@@ -8,13 +8,21 @@ namespace b200post {
 // =================================================================================================
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
+// Scratchpad access policies (V is written once and read ~once: nothing is worth keeping in cache):
+//   0: ld.cs / st.cs (evict-first streaming)   1: default ld / st   2: ld.cg / st.cg (L2 only)
+template <int POLICY>
+__device__ __forceinline__ uint4 ld_v(const uint4 *p) {
     uint4 v;
-    asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    if (POLICY == 0) asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else if (POLICY == 1) asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
-__device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
-    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+template <int POLICY>
+__device__ __forceinline__ void st_v(uint4 *p, const uint4 &v) {
+    if (POLICY == 0) asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else if (POLICY == 1) asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t a, const uint4 &v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -113,13 +121,15 @@ __global__ void __launch_bounds__(128) pbkdf2_expand_kernel(LabelJob job, uint4 
 // private scratch, so any layout is legal as long as reads undo it; the swizzle makes the dense
 // 32 x 128-B shared-memory tile bank-conflict-free in both the row-wise and the transposed access.
 // =================================================================================================
-template <int VARIANT, int MW, int TPB>
+template <int VARIANT, int MW, int TPB, int POLICY>
 __global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t slot = blockIdx.x * TPB + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
     if (slot >= p.n_slots) return;   // n_slots is a multiple of 32: whole warps leave together
     const uint32_t N = p.N, mask = N - 1;
+    // diagnostics only (b200post_set_option("debug_skip_phase")): bit0 skips the fill loop, bit1 the mix loop
+    const uint32_t n1 = (p.flags & 1) ? 0 : N, n2 = (p.flags & 2) ? 0 : N;
     const RotConsts rc = p.rc;
 
     uint32_t lo[16], hi[16];
@@ -131,39 +141,39 @@ __global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
 
     if (VARIANT == ROMIX_DIRECT) {
         uint4 *const Vt = Vw + lane * 8;
-        for (uint32_t i = 0; i < N; i++) {
+        for (uint32_t i = 0; i < n1; i++) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) st_stream(Vt + (size_t)i * 256 + k, ROW_CHUNK(lo, hi, k));
+            for (int k = 0; k < 8; k++) st_v<POLICY>(Vt + (size_t)i * 256 + k, ROW_CHUNK(lo, hi, k));
             blockmix_r1<MW>(lo, hi, rc);
         }
-        for (uint32_t i = 0; i < N; i++) {
+        for (uint32_t i = 0; i < n2; i++) {
             const uint32_t j = hi[0] & mask;
             uint32_t vlo[16], vhi[16];
 #pragma unroll
-            for (int k = 0; k < 8; k++) set_chunk(vlo, vhi, k, ld_stream(Vt + (size_t)j * 256 + k));
+            for (int k = 0; k < 8; k++) set_chunk(vlo, vhi, k, ld_v<POLICY>(Vt + (size_t)j * 256 + k));
             blockmix_r1_xor<MW>(lo, hi, vlo, vhi, rc);
         }
     } else if (VARIANT == ROMIX_COALESCED) {
         const uint32_t tile = smem_u32(smem_raw) + warp_in_cta * 4096;
         const uint32_t own = tile + lane * 128;
         const uint32_t tr_row = lane >> 3, tr_c = lane & 7;   // transposed role: row k*4+tr_row, chunk position tr_c
-        for (uint32_t i = 0; i < N; i++) {
+        for (uint32_t i = 0; i < n1; i++) {
 #pragma unroll
             for (int k = 0; k < 8; k++) sts128(own + ((k ^ swz) << 4), ROW_CHUNK(lo, hi, k));
             __syncwarp();
             uint4 *const dst = Vw + (size_t)i * 256 + lane;   // + k*32: the warp writes 512 contiguous bytes per k
 #pragma unroll
-            for (int k = 0; k < 8; k++) st_stream(dst + k * 32, lds128(tile + (k * 4 + tr_row) * 128 + (tr_c << 4)));
+            for (int k = 0; k < 8; k++) st_v<POLICY>(dst + k * 32, lds128(tile + (k * 4 + tr_row) * 128 + (tr_c << 4)));
             __syncwarp();
             blockmix_r1<MW>(lo, hi, rc);
         }
-        for (uint32_t i = 0; i < N; i++) {
+        for (uint32_t i = 0; i < n2; i++) {
             const uint32_t j = hi[0] & mask;
             uint4 t[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const uint32_t jr = __shfl_sync(0xffffffffu, j, k * 4 + tr_row);
-                t[k] = ld_stream(Vw + (size_t)jr * 256 + k * 32 + lane);
+                t[k] = ld_v<POLICY>(Vw + (size_t)jr * 256 + k * 32 + lane);
             }
 #pragma unroll
             for (int k = 0; k < 8; k++) sts128(tile + (k * 4 + tr_row) * 128 + (tr_c << 4), t[k]);
@@ -182,7 +192,7 @@ __global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
         if (lane == 0) mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncwarp();
-        for (uint32_t i = 0; i < N; i++) {
+        for (uint32_t i = 0; i < n1; i++) {
             const uint32_t tile = tile0 + (i & 1) * 4096;
             if (lane == 0) bulk_wait_read<1>();   // the store issued two iterations ago has drained this tile
             __syncwarp();
@@ -197,7 +207,7 @@ __global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
         __syncwarp();
         const uint32_t own = tile0 + lane * 128;
         uint32_t parity = 0;
-        for (uint32_t i = 0; i < N; i++) {
+        for (uint32_t i = 0; i < n2; i++) {
             const uint32_t j = hi[0] & mask;
             if (lane == 0) mbar_expect_tx(bar, 4096);
             __syncwarp();
@@ -210,8 +220,8 @@ __global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
             blockmix_r1_xor<MW>(lo, hi, vlo, vhi, rc);
         }
     } else {   // ROMIX_NOMEM: same arithmetic, no scratchpad (ALU ceiling probe only)
-        for (uint32_t i = 0; i < N; i++) blockmix_r1<MW>(lo, hi, rc);
-        for (uint32_t i = 0; i < N; i++) {
+        for (uint32_t i = 0; i < n1; i++) blockmix_r1<MW>(lo, hi, rc);
+        for (uint32_t i = 0; i < n2; i++) {
             uint32_t vlo[16], vhi[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) { vlo[k] = hi[(k + 1) & 15] + i; vhi[k] = lo[(k + 3) & 15]; }
@@ -398,37 +408,46 @@ const char *romix_variant_name(int variant) {
 
 typedef void (*romix_fn)(const RomixParams);
 
-template <int VARIANT, int MW>
+template <int VARIANT, int MW, int POLICY>
 static romix_fn pick_tpb(int tpb) {
     switch (tpb) {
-        case 64: return romix_kernel<VARIANT, MW, 64>;
-        case 128: return romix_kernel<VARIANT, MW, 128>;
-        case 256: return romix_kernel<VARIANT, MW, 256>;
+        case 64: return romix_kernel<VARIANT, MW, 64, POLICY>;
+        case 128: return romix_kernel<VARIANT, MW, 128, POLICY>;
+        case 256: return romix_kernel<VARIANT, MW, 256, POLICY>;
     }
     return nullptr;
+}
+template <int VARIANT, int MW>
+static romix_fn pick_policy(int policy, int tpb) {
+    if (VARIANT == ROMIX_DIRECT || VARIANT == ROMIX_COALESCED) {
+        switch (policy) {
+            case 1: return pick_tpb<VARIANT, MW, 1>(tpb);
+            case 2: return pick_tpb<VARIANT, MW, 2>(tpb);
+        }
+    }
+    return pick_tpb<VARIANT, MW, 0>(tpb);
 }
 template <int VARIANT>
-static romix_fn pick_mw(int mw, int tpb) {
+static romix_fn pick_mw(int mw, int policy, int tpb) {
     switch (mw) {
-        case 0: return pick_tpb<VARIANT, 0>(tpb);
-        case 5: return pick_tpb<VARIANT, 5>(tpb);
-        case 10: return pick_tpb<VARIANT, 10>(tpb);
-        case 15: return pick_tpb<VARIANT, 15>(tpb);
+        case 0: return pick_policy<VARIANT, 0>(policy, tpb);
+        case 5: return pick_policy<VARIANT, 5>(policy, tpb);
+        case 15: return pick_policy<VARIANT, 15>(policy, tpb);
     }
     return nullptr;
 }
-static romix_fn pick(int variant, int mw, int tpb) {
+static romix_fn pick(int variant, int mw, int policy, int tpb) {
     switch (variant) {
-        case ROMIX_DIRECT: return pick_mw<ROMIX_DIRECT>(mw, tpb);
-        case ROMIX_COALESCED: return pick_mw<ROMIX_COALESCED>(mw, tpb);
-        case ROMIX_BULK: return pick_mw<ROMIX_BULK>(mw, tpb);
-        case ROMIX_NOMEM: return pick_mw<ROMIX_NOMEM>(mw, tpb);
+        case ROMIX_DIRECT: return pick_mw<ROMIX_DIRECT>(mw, policy, tpb);
+        case ROMIX_COALESCED: return pick_mw<ROMIX_COALESCED>(mw, policy, tpb);
+        case ROMIX_BULK: return pick_mw<ROMIX_BULK>(mw, policy, tpb);
+        case ROMIX_NOMEM: return pick_mw<ROMIX_NOMEM>(mw, policy, tpb);
     }
     return nullptr;
 }
 
-int romix_max_ctas_per_sm(int variant, int mulwide_mask, int tpb) {
-    romix_fn fn = pick(variant, mulwide_mask, tpb);
+int romix_max_ctas_per_sm(int variant, int mulwide_mask, int policy, int tpb) {
+    romix_fn fn = pick(variant, mulwide_mask, policy, tpb);
     if (!fn) return 0;
     const size_t smem = romix_smem_bytes(variant, tpb);
     if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -437,9 +456,9 @@ int romix_max_ctas_per_sm(int variant, int mulwide_mask, int tpb) {
     return n;
 }
 
-cudaError_t launch_romix(int variant, int mulwide_mask, int tpb, const RomixParams &p, cudaStream_t s) {
+cudaError_t launch_romix(int variant, int mulwide_mask, int policy, int tpb, const RomixParams &p, cudaStream_t s) {
     if (p.n_slots == 0) return cudaSuccess;
-    romix_fn fn = pick(variant, mulwide_mask, tpb);
+    romix_fn fn = pick(variant, mulwide_mask, policy, tpb);
     if (!fn) return cudaErrorInvalidValue;
     const size_t smem = romix_smem_bytes(variant, tpb);
     if (smem > 48 * 1024) {

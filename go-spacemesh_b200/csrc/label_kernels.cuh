@@ -34,6 +34,7 @@ struct RomixParams {
     uint32_t x_stride;   // slots in the wave buffer (multiple of 32)
     uint32_t N;          // scrypt N (power of two, >= 2)
     uint32_t n_slots;    // active slots this wave (multiple of 32)
+    uint32_t flags;      // diagnostics: bit0 skip fill loop, bit1 skip mix loop (0 in production)
     RotConsts rc;
 };
 
@@ -53,7 +54,7 @@ struct VrfCandidate {           // 48 bytes
 
 cudaError_t launch_hmac_midstates(const uint8_t *d_commitments, uint32_t n, uint32_t *d_mid, cudaStream_t s);
 cudaError_t launch_pbkdf2_expand(const LabelJob &job, uint4 *X, uint32_t x_stride, uint32_t n_slots, cudaStream_t s);
-cudaError_t launch_romix(int variant, int mulwide_mask, int tpb, const RomixParams &p, cudaStream_t s);
+cudaError_t launch_romix(int variant, int mulwide_mask, int policy, int tpb, const RomixParams &p, cudaStream_t s);
 // out16: n_valid x 16 bytes (device).  vrf_difficulty_be: 8 big-endian words (device) or nullptr.
 // cta_cand: one VrfCandidate per CTA (device), only touched when vrf_difficulty_be != nullptr.
 cudaError_t launch_pbkdf2_final(const LabelJob &job, const uint4 *X, uint32_t x_stride, uint32_t n_slots,
@@ -64,7 +65,7 @@ uint32_t pbkdf2_final_ctas(uint32_t n_slots);
 // bytes of dynamic shared memory the ROMix variant needs per CTA
 size_t romix_smem_bytes(int variant, int tpb);
 // occupancy query helper: max resident CTAs/SM for (variant, mask, tpb)
-int romix_max_ctas_per_sm(int variant, int mulwide_mask, int tpb);
+int romix_max_ctas_per_sm(int variant, int mulwide_mask, int policy, int tpb);
 const char *romix_variant_name(int variant);
 
 }  // namespace b200post

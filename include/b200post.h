@@ -125,6 +125,11 @@ int b200post_benchmark(uint32_t provider, uint64_t n, double seconds, double *la
  * accumulated device time (ms, CUDA events on the launching stream) of the ROMix kernel. */
 uint64_t b200post_launch_count(void);
 int b200post_romix_time(uint32_t provider, double *ms_total, uint64_t *launches, int reset);
+/* Device time in ms (CUDA events recorded on the engine's own stream at the start and end of the call)
+ * of the most recent labels_range* / labels_gather call on `provider`; < 0 if the provider is unusable. */
+double b200post_last_call_ms(uint32_t provider);
+/* Labels one wave holds for scrypt-N on `provider` under the current options (= resident scratchpads). */
+int b200post_wave_slots(uint32_t provider, uint64_t n, uint64_t *slots);
 
 /* Frees scratch and streams of every device (optional; also runs at library unload). */
 void b200post_shutdown(void);

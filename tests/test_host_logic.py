@@ -1,0 +1,91 @@
+"""CPU tier: the product's host-side logic and the kernels' arithmetic (compiled for the host)."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_device_arithmetic_on_host_matches_oracle(host_emul, orc):
+    """post_device.cuh (SHA-256, PBKDF2, Salsa20/8, BlockMix exactly as the kernels inline them) == oracle."""
+    rng = np.random.default_rng(21)
+    for n in (2, 4, 64, 1024, 8192):
+        for idx in (0, 1, 2**32 - 1, 2**32, 2**40 + 12345, 2**64 - 1, int(rng.integers(0, 2**63))):
+            c = bytes(rng.integers(0, 256, 32, dtype=np.uint8))
+            out = ctypes.create_string_buffer(32)
+            host_emul.emul_label32(c, ctypes.c_uint64(idx), n, out)
+            assert out.raw == orc.c_label32(c, idx, n), (n, idx)
+
+
+def test_device_arithmetic_golden(host_emul, golden):
+    for it in golden["gather"]["items"]:
+        out = ctypes.create_string_buffer(32)
+        host_emul.emul_label32(bytes.fromhex(it["commitment"]), ctypes.c_uint64(it["index"]), it["N"], out)
+        assert out.raw.hex() == it["label32"]
+
+
+def test_library_exports_every_declared_symbol(b2):
+    """The C-ABI library loads on a CPU-only box and exports everything include/*.h declares."""
+    lib = b2.lib()
+    declared = set()
+    for hdr in ("b200post.h", "post_compat.h", "b200post_verify.h"):
+        p = ROOT / "include" / hdr
+        if not p.exists():
+            continue
+        text = re.sub(r"/\*.*?\*/", "", p.read_text(), flags=re.S)
+        declared |= set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", text))
+    declared -= {"defined"}
+    assert {"b200post_labels_range", "b200post_labels_gather", "initialize", "new_initializer"} <= declared
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, f"declared in include/ but not exported: {missing}"
+
+
+def test_commitment_and_difficulty_host_helpers(b2, orc, golden):
+    rng = np.random.default_rng(22)
+    for _ in range(8):
+        a = bytes(rng.integers(0, 256, 32, dtype=np.uint8)); b = bytes(rng.integers(0, 256, 32, dtype=np.uint8))
+        assert b2.commitment(a, b) == orc.py_commitment(a, b)
+    for n, hx in golden["vrf_difficulty"].items():
+        assert b2.vrf_difficulty(int(n)).hex() == hx
+
+
+def test_no_cpu_fallback(b2):
+    """Without a GPU every compute entry point must fail loudly; the CPU provider id is refused outright."""
+    if b2.providers():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(b2.B200PostError) as e:
+        b2.labels_range(bytes(32), 2, 0, 8)
+    assert e.value.code == b2.ERR_NO_DEVICE
+    with pytest.raises(b2.B200PostError) as e:
+        b2.labels_gather(np.zeros((1, 32), np.uint8), np.zeros(1, np.uint64), 2)
+    assert e.value.code == b2.ERR_NO_DEVICE
+    with pytest.raises(b2.B200PostError) as e:
+        b2.labels_range(bytes(32), 2, 0, 8, provider=b2.CPU_PROVIDER_ID)
+    assert e.value.code == b2.ERR_UNSUPPORTED
+
+
+def test_argument_validation(b2):
+    for n in (0, 1, 3, 12, 2**32):
+        with pytest.raises(b2.B200PostError) as e:
+            b2.labels_range(bytes(32), n, 0, 8)
+        assert e.value.code == b2.ERR_INVALID_ARGUMENT
+    with pytest.raises(b2.B200PostError) as e:
+        b2.labels_range(bytes(32), 2, 2**64 - 4, 8)   # index overflow
+    assert e.value.code == b2.ERR_INVALID_ARGUMENT
+    with pytest.raises(b2.B200PostError):
+        b2.set_option("romix_variant", 9)
+    with pytest.raises(b2.B200PostError):
+        b2.set_option("no_such_option", 1)
+
+
+def test_product_does_not_reference_the_oracle():
+    """The shipped sources must not import, link or call anything under oracle/."""
+    pkg = ROOT / "go-spacemesh_b200"
+    for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.cpp")) + list(pkg.rglob("*.h")) + list(pkg.rglob("Makefile")):
+        if "build" in p.parts:
+            continue
+        text = p.read_text()
+        assert "post_oracle" not in text and "pyoracle" not in text and "from oracle" not in text, p

@@ -1,0 +1,119 @@
+"""CPU tier: the oracle against public KATs, the committed golden vectors and the OpenSSL restatement."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+
+def test_rfc7914_scrypt_vectors(orc, golden):
+    for v in golden["kat_primitives"]["scrypt"]:
+        got = orc.c_scrypt(v["P"].encode(), v["S"].encode(), v["N"], v["r"], v["p"], v["dkLen"])
+        assert got.hex() == v["out"]
+
+
+def test_pbkdf2_vectors(orc, golden):
+    for v in golden["kat_primitives"]["pbkdf2_sha256"]:
+        assert orc.c_pbkdf2(v["P"].encode(), v["S"].encode(), v["c"], v["dkLen"]).hex() == v["out"]
+
+
+def test_sha256_and_hmac_against_hashlib(orc):
+    import hmac
+    rng = np.random.default_rng(11)
+    for n in [0, 1, 55, 56, 63, 64, 65, 119, 120, 127, 128, 1000]:
+        m = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+        assert orc.c_sha256(m) == hashlib.sha256(m).digest()
+        for klen in (0, 32, 64, 65, 200):
+            k = bytes(rng.integers(0, 256, klen, dtype=np.uint8))
+            assert orc.c_hmac_sha256(k, m) == hmac.new(k, m, "sha256").digest()
+
+
+def test_blake3_against_wheel(orc):
+    blake3 = pytest.importorskip("blake3")
+    rng = np.random.default_rng(12)
+    for n in [0, 1, 63, 64, 65, 1023, 1024, 1025, 2048, 2049, 3072, 3073, 4096, 5000, 8192, 8193, 31744, 100000]:
+        m = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+        assert orc.c_blake3(m) == blake3.blake3(m).digest()
+        assert orc.c_blake3(m, 131) == blake3.blake3(m).digest(131)
+
+
+def test_aes128_fips197(orc, golden):
+    for v in golden["kat_primitives"]["aes128"]:
+        assert orc.c_aes128(bytes.fromhex(v["key"]), bytes.fromhex(v["pt"])).hex() == v["ct"]
+
+
+def test_aes128_against_cryptography(orc):
+    ciphers = pytest.importorskip("cryptography.hazmat.primitives.ciphers")
+    rng = np.random.default_rng(13)
+    for _ in range(32):
+        k = bytes(rng.integers(0, 256, 16, dtype=np.uint8)); b = bytes(rng.integers(0, 256, 16, dtype=np.uint8))
+        enc = ciphers.Cipher(ciphers.algorithms.AES(k), ciphers.modes.ECB()).encryptor()
+        assert enc.update(b) == orc.c_aes128(k, b)
+
+
+def test_vrf_difficulty_table(orc, golden):
+    for n, hx in golden["vrf_difficulty"].items():
+        assert orc.c_vrf_difficulty(int(n)).hex() == hx
+        assert orc.py_vrf_difficulty(int(n)).hex() == hx
+    assert orc.c_vrf_difficulty(1) == b"\xff" * 32 and orc.c_vrf_difficulty(0) == b"\xff" * 32
+
+
+def test_survey_candidate_vectors(orc):
+    """SURVEY.md §8c candidate vectors (inputs of activation/validation_test.go:35-36)."""
+    c = orc.c_commitment(bytes(32), bytes(32))
+    assert c.hex() == "4d006976636a8696d909a630a4081aad4d7c50f81afdee04020bf05086ab6a55"
+    assert orc.c_label32(c, 0, 2).hex() == "816a047977c79c85a5ba00fec5fd81794c8b56c87e4c084aa95f68d388318fac"
+    assert orc.c_label32(c, 0, 8192).hex() == "3ea1a34b8a3e719839095e30f38533019c9fab5a9e73eebccd28363363e96fde"
+
+
+def test_label_golden_vectors(orc, golden):
+    for case in golden["labels"]["cases"]:
+        c = orc.c_commitment(bytes.fromhex(case["node_id"]), bytes.fromhex(case["commitment_atx"]))
+        assert c.hex() == case["commitment"], case["name"]
+        diff = bytes.fromhex(case["vrf_difficulty"]) if "vrf_difficulty" in case else None
+        labels, found, idx, l32 = orc.c_labels_range(c, case["N"], case["start"], case["count"], diff, threads=4)
+        assert hashlib.sha256(labels.tobytes()).hexdigest() == case["labels_sha256"], case["name"]
+        if "labels_hex" in case:
+            assert labels.tobytes().hex() == case["labels_hex"], case["name"]
+        if diff is not None:
+            if case["vrf_index"] is None:
+                assert not found
+            else:
+                assert found and idx == case["vrf_index"] and l32.hex() == case["vrf_label32"], case["name"]
+
+
+def test_gather_golden_vectors(orc, golden):
+    items = golden["gather"]["items"]
+    for n in (2, 8192):
+        sel = [it for it in items if it["N"] == n]
+        comms = np.frombuffer(b"".join(bytes.fromhex(it["commitment"]) for it in sel), dtype=np.uint8).reshape(-1, 32)
+        idx = np.array([it["index"] for it in sel], dtype=np.uint64)
+        got = orc.c_labels_gather(comms, idx, n, threads=4)
+        for row, it in zip(got, sel):
+            assert row.tobytes().hex() == it["label32"][:32]
+
+
+def test_threads_do_not_change_results(orc):
+    c = orc.c_commitment(b"\x01" * 32, b"\x02" * 32)
+    d = orc.py_vrf_difficulty(8)
+    a = orc.c_labels_range(c, 16, 7, 301, d, threads=1)
+    b = orc.c_labels_range(c, 16, 7, 301, d, threads=7)
+    assert (a[0] == b[0]).all() and a[1:] == b[1:]
+
+
+def test_vrf_scan_matches_python(orc):
+    c = orc.c_commitment(b"\x07" * 32, b"\x09" * 32)
+    for num_labels in (4, 64, 4096):
+        d = orc.py_vrf_difficulty(num_labels)
+        _, found, idx, l32 = orc.c_labels_range(c, 4, 100, 500, d, threads=3)
+        pidx, pl32 = orc.py_vrf_scan(c, 4, 100, 500, d)
+        assert (idx if found else None) == pidx and (l32 if found else None) == pl32
+
+
+def test_bad_parameters_rejected(orc):
+    c = bytes(32)
+    for n in (0, 1, 3, 12):
+        with pytest.raises(ValueError):
+            orc.c_labels_range(c, n, 0, 4)
+    labels, found, _, _ = orc.c_labels_range(c, 2, 0, 0)
+    assert labels.shape == (0, 16) and not found

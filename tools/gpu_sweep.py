@@ -65,6 +65,7 @@ def sweep(specs, tag):
         try:
             b2.set_option("romix_variant", sp["variant"]); b2.set_option("mulwide_mask", sp["mw"])
             b2.set_option("tpb", sp["tpb"]); b2.set_option("ctas_per_sm", sp["ctas"])
+            b2.set_option("mem_policy", sp.get("policy", 0)); b2.set_option("debug_skip_phase", sp.get("skip", 0))
             slots = prov["sm_count"] * sp["ctas"] * sp["tpb"]
             waves = sp.get("waves", 2)
             b2.labels_range(commitment, n, 0, slots, discard=True)  # warm-up wave: allocates scratch
