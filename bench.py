@@ -255,7 +255,7 @@ def main() -> None:
     wall, dev_ms = timed(step_dev, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     launches = b2.launch_count() - launches0
-    romix_ms, romix_k = b2.romix_time(provider=local_rank, reset=True)
+    romix_ms, romix_k, romix_labels = b2.romix_time(provider=local_rank, reset=True)
 
     # ---- end-to-end arm (host buffers through the reference-facing C-ABI call)
     for w in range(2):
@@ -269,7 +269,7 @@ def main() -> None:
     e2e_value = total_labels / wall_e2e
 
     peak, peak_src = measured_peaks()
-    labels_per_launch = batch * args.steps / max(romix_k, 1)
+    labels_per_launch = romix_labels / max(romix_k, 1)     # label-equivalents per ROMix launch (engine-counted)
     romix_avg_ms = romix_ms / max(romix_k, 1)
     achieved = labels_per_launch * BYTES_PER_LABEL / (romix_avg_ms / 1e3) / 1e9 if romix_avg_ms > 0 else 0.0
     traffic = None

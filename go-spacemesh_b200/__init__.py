@@ -85,7 +85,8 @@ def lib() -> ctypes.CDLL:
     L.b200post_verify_vrf_nonce.argtypes = [u32, u64, u8p, u8p, u32, u64, u64, ctypes.POINTER(ctypes.c_int)]
     L.b200post_benchmark.argtypes = [u32, u64, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
     L.b200post_launch_count.restype = ctypes.c_uint64
-    L.b200post_romix_time.argtypes = [u32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64), ctypes.c_int]
+    L.b200post_romix_time.argtypes = [u32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64),
+                                      ctypes.POINTER(ctypes.c_double), ctypes.c_int]
     L.b200post_last_call_ms.argtypes = [u32]
     L.b200post_last_call_ms.restype = ctypes.c_double
     L.b200post_wave_slots.argtypes = [u32, u64, ctypes.POINTER(u64)]
@@ -214,10 +215,11 @@ def launch_count() -> int:
     return int(lib().b200post_launch_count())
 
 
-def romix_time(provider: int = 0, reset: bool = False) -> tuple[float, int]:
-    ms, k = ctypes.c_double(0), ctypes.c_uint64(0)
-    _check(lib().b200post_romix_time(provider, ctypes.byref(ms), ctypes.byref(k), int(reset)))
-    return ms.value, int(k.value)
+def romix_time(provider: int = 0, reset: bool = False) -> tuple[float, int, float]:
+    """(device ms, launches, label-equivalents) accumulated by the ROMix kernel since the last reset."""
+    ms, k, lab = ctypes.c_double(0), ctypes.c_uint64(0), ctypes.c_double(0)
+    _check(lib().b200post_romix_time(provider, ctypes.byref(ms), ctypes.byref(k), ctypes.byref(lab), int(reset)))
+    return ms.value, int(k.value), lab.value
 
 
 def last_call_ms(provider: int = 0) -> float:

@@ -14,7 +14,9 @@ using namespace b200post;
 
 namespace {
 
-bool valid_n(uint64_t n) { return n >= 2 && n <= (1ull << 31) && (n & (n - 1)) == 0; }
+// N is a power of two in [2, 2^20]: one scratchpad is 128*N bytes (128 MiB at the cap) and a warp's
+// region (N * 4 KiB) must stay within 4 GiB for the kernels' 32-bit in-region addressing.
+bool valid_n(uint64_t n) { return n >= 2 && n <= (1ull << 20) && (n & (n - 1)) == 0; }
 
 void fill_nonce(b200post_vrf_nonce *dst, const VrfResult &r) {
     if (!dst) return;
@@ -26,8 +28,8 @@ void fill_nonce(b200post_vrf_nonce *dst, const VrfResult &r) {
 int range_common(uint32_t provider, const uint8_t *commitment, uint64_t n, uint64_t start, uint64_t count,
                  uint8_t *out_host, uint8_t *out_dev, const uint8_t *vrf_difficulty, b200post_vrf_nonce *nonce,
                  const volatile int *cancel) {
-    if (!commitment || !valid_n(n) || (vrf_difficulty && !nonce) || start + count < start) {
-        set_error("invalid argument (commitment NULL, N not a power of two in [2, 2^31], missing nonce out, or index overflow)");
+    if (!commitment || !valid_n(n) || (vrf_difficulty && !nonce) || (count && start + (count - 1) < start)) {
+        set_error("invalid argument (commitment NULL, N not a power of two in [2, 2^20], missing nonce out, or index overflow)");
         return B200POST_ERR_INVALID_ARGUMENT;
     }
     if (provider == B200POST_CPU_PROVIDER_ID) { engine_for(provider); return B200POST_ERR_UNSUPPORTED; }
@@ -70,13 +72,13 @@ int b200post_set_option(const char *key, int64_t value) {
     if (!key) return B200POST_ERR_INVALID_ARGUMENT;
     Options &o = options();
     const std::string k(key);
-    if (k == "romix_variant" && value >= 0 && value <= 3) { o.romix_variant = value; return B200POST_OK; }
-    if (k == "mulwide_mask" && (value == 0 || value == 5 || value == 15)) { o.mulwide_mask = value; return B200POST_OK; }
-    if (k == "mem_policy" && value >= 0 && value <= 2) { o.mem_policy = value; return B200POST_OK; }
-    if (k == "debug_skip_phase" && value >= 0 && value <= 3) { o.debug_skip_phase = value; return B200POST_OK; }
+    if (k == "romix_variant" && value >= 0 && value <= 4) { o.romix_variant = value; return B200POST_OK; }
+    if (k == "mulwide_mask" && value >= 0 && value <= 0xffff && romix_mask_supported((int)value)) { o.mulwide_mask = value; return B200POST_OK; }
     if (k == "tpb" && (value == 64 || value == 128 || value == 256)) { o.tpb = value; return B200POST_OK; }
+    if (k == "dr_unroll" && (value == 1 || value == 4)) { o.dr_unroll = value; return B200POST_OK; }
     if (k == "ctas_per_sm" && value >= 0 && value <= 32) { o.ctas_per_sm = value; return B200POST_OK; }
     if (k == "max_scratch_mib" && value >= 0) { o.max_scratch_mib = value; return B200POST_OK; }
+    if (k == "debug_skip_phase" && value >= 0 && value <= 3) { o.debug_skip_phase = value; return B200POST_OK; }
     set_error("unknown option or value out of range: " + k);
     return B200POST_ERR_INVALID_ARGUMENT;
 }
@@ -88,10 +90,10 @@ int64_t b200post_get_option(const char *key) {
     if (k == "romix_variant") return o.romix_variant;
     if (k == "mulwide_mask") return o.mulwide_mask;
     if (k == "tpb") return o.tpb;
-    if (k == "mem_policy") return o.mem_policy;
-    if (k == "debug_skip_phase") return o.debug_skip_phase;
+    if (k == "dr_unroll") return o.dr_unroll;
     if (k == "ctas_per_sm") return o.ctas_per_sm;
     if (k == "max_scratch_mib") return o.max_scratch_mib;
+    if (k == "debug_skip_phase") return o.debug_skip_phase;
     return -1;
 }
 
@@ -205,10 +207,10 @@ int b200post_benchmark(uint32_t provider, uint64_t n, double seconds, double *la
 
 uint64_t b200post_launch_count(void) { return g_launches.load(); }
 
-int b200post_romix_time(uint32_t provider, double *ms_total, uint64_t *launches, int reset) {
+int b200post_romix_time(uint32_t provider, double *ms_total, uint64_t *launches, double *labels, int reset) {
     DeviceEngine *e = engine_for(provider);
     if (!e) return B200POST_ERR_NO_DEVICE;
-    e->romix_time(ms_total, launches, reset != 0);
+    e->romix_time(ms_total, launches, labels, reset != 0);
     return B200POST_OK;
 }
 

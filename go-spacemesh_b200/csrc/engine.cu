@@ -1,9 +1,12 @@
-// engine.cu — wave scheduler for the POST label kernels (see engine.h).
+// engine.cu — layer scheduler for the POST label kernels (see engine.h).
 //
 // Mirrors what the reference's initializer does around libpost's `initialize()` (activation/post.go:295:
-// batches of ComputeBatchSize labels, cancellable, progress observable) but sized for a B200: a wave is
-// every scratchpad that fits the SMs (and HBM) at once, waves are queued two deep on one stream, and the
-// 16-byte labels of wave w are copied out while wave w+1 computes.
+// batches of ComputeBatchSize labels, cancellable, progress observable) but sized for a B200.  A *layer*
+// is one label per resident slot (threads x SMs that fit the registers and the HBM scratch).  With the
+// pipelined ROMix kernel the stream carries, for layer m:
+//     K1(m)  ->  K2p{ mix layer m-1 | fill layer m }  ->  K3(m-1) -> D2H(m-1)
+// so every launch keeps half of each thread's work latency-free, and the 16-byte labels of layer m-1
+// leave the device while layer m computes.  Buffers are double-buffered by layer parity.
 #include "engine.h"
 
 #include <algorithm>
@@ -34,9 +37,7 @@ const char *last_error() { return t_error.c_str(); }
 
 static inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
 
-DeviceEngine::DeviceEngine(int device) : dev_(device) {
-    cudaGetDeviceProperties(&prop_, device);
-}
+DeviceEngine::DeviceEngine(int device) : dev_(device) { cudaGetDeviceProperties(&prop_, device); }
 
 DeviceEngine::~DeviceEngine() {
     cudaSetDevice(dev_);
@@ -45,23 +46,20 @@ DeviceEngine::~DeviceEngine() {
 
 void DeviceEngine::release() {
     if (stream_) cudaStreamSynchronize(stream_);
-    cudaFree(V_); V_ = nullptr; v_bytes_ = 0;
-    cudaFree(X_); X_ = nullptr;
+    cudaFree(V_raw_); V_raw_ = nullptr; V_ = nullptr; v_bytes_ = 0; v_align_ = 0;
     for (int b = 0; b < 2; b++) {
+        cudaFree(X_[b]); X_[b] = nullptr;
         cudaFree(d_out_[b]); d_out_[b] = nullptr;
         cudaFreeHost(h_out_[b]); h_out_[b] = nullptr;
-        if (ev_done_[b]) cudaEventDestroy(ev_done_[b]);
-        if (ev_k2a_[b]) cudaEventDestroy(ev_k2a_[b]);
-        if (ev_k2b_[b]) cudaEventDestroy(ev_k2b_[b]);
-        if (ev_call_[b]) cudaEventDestroy(ev_call_[b]);
-        ev_done_[b] = ev_k2a_[b] = ev_k2b_[b] = ev_call_[b] = nullptr;
-        k2_pending_[b] = false;
+        cudaFree(d_commit_[b]); d_commit_[b] = nullptr;
+        cudaFree(d_idx_[b]); d_idx_[b] = nullptr;
+        cudaFreeHost(h_commit_[b]); h_commit_[b] = nullptr;
+        cudaFreeHost(h_idx_[b]); h_idx_[b] = nullptr;
+        cudaFree(d_mid_[b]); d_mid_[b] = nullptr;
+        cudaEvent_t *evs[] = {&ev_done_[b], &ev_in_[b], &ev_k2a_[b], &ev_k2b_[b], &ev_call_[b]};
+        for (cudaEvent_t *e : evs) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
+        k2_pending_[b] = false; in_pending_[b] = false; pend_[b].live = false;
     }
-    cudaFree(d_commit_); d_commit_ = nullptr;
-    cudaFree(d_idx_); d_idx_ = nullptr;
-    cudaFreeHost(h_commit_); h_commit_ = nullptr;
-    cudaFreeHost(h_idx_); h_idx_ = nullptr;
-    cudaFree(d_mid_); d_mid_ = nullptr;
     cudaFree(d_diff_); d_diff_ = nullptr;
     cudaFree(d_cta_cand_); d_cta_cand_ = nullptr;
     cudaFree(d_running_); d_running_ = nullptr;
@@ -72,14 +70,16 @@ void DeviceEngine::release() {
     wave_slots_ = 0;
 }
 
-// Decide the wave size for scrypt-N and make sure scratch for min(wave, want_slots) slots exists.
+// Decide the layer size for scrypt-N and make sure scratch for min(layer, want_slots) slots exists.
 int DeviceEngine::ensure(uint64_t N, uint64_t want_slots) {
     Options &o = options();
     const int variant = (int)o.romix_variant.load(), mw = (int)o.mulwide_mask.load(), tpb = (int)o.tpb.load();
+    const int dr = (int)o.dr_unroll.load();
     if (!stream_) {
         CU_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
         for (int b = 0; b < 2; b++) {
             CU_TRY(cudaEventCreateWithFlags(&ev_done_[b], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&ev_in_[b], cudaEventDisableTiming));
             CU_TRY(cudaEventCreate(&ev_k2a_[b]));
             CU_TRY(cudaEventCreate(&ev_k2b_[b]));
             CU_TRY(cudaEventCreate(&ev_call_[b]));
@@ -88,13 +88,14 @@ int DeviceEngine::ensure(uint64_t N, uint64_t want_slots) {
         CU_TRY(cudaMalloc(&d_running_, sizeof(VrfCandidate)));
         CU_TRY(cudaMallocHost(&h_running_, sizeof(VrfCandidate)));
     }
-    variant_ = variant; mw_ = mw; tpb_ = tpb; policy_ = (int)o.mem_policy.load();
-    int ctas = romix_max_ctas_per_sm(variant, mw, policy_, tpb);
-    if (ctas <= 0) { set_error("romix kernel cannot be resident (bad variant/mask/tpb?)"); return B200POST_ERR_INVALID_ARGUMENT; }
+    variant_ = variant; mw_ = mw; tpb_ = tpb; dr_unroll_ = dr;
+    int ctas = romix_max_ctas_per_sm(variant, mw, tpb, dr);
+    if (ctas <= 0) { set_error("romix kernel cannot be resident (unsupported variant / mask / tpb combination)"); return B200POST_ERR_INVALID_ARGUMENT; }
     const int64_t want_ctas = o.ctas_per_sm.load();
     if (want_ctas > 0) ctas = std::min<int>(ctas, (int)want_ctas);
 
-    const size_t per_slot = 128 * (size_t)N;
+    const size_t pads = variant == ROMIX_PIPELINED ? 2 : 1;   // scratchpads per slot
+    const size_t per_slot = 128 * (size_t)N * pads;
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
     size_t budget = (size_t)((double)(free_b + v_bytes_) * 0.90);
@@ -112,61 +113,160 @@ int DeviceEngine::ensure(uint64_t N, uint64_t want_slots) {
 
     const uint32_t need = (uint32_t)std::min<uint64_t>(wave, round_up((uint32_t)std::min<uint64_t>(want_slots, wave), 32));
     const size_t need_v = per_slot * (size_t)need;
-    if (need_v > v_bytes_) {
+    if (need_v > v_bytes_ || 128 * (size_t)N * 32 > v_align_) {
         CU_TRY(cudaStreamSynchronize(stream_));
-        cudaFree(V_); V_ = nullptr; v_bytes_ = 0;
-        CU_TRY(cudaMalloc(&V_, need_v));
+        cudaFree(V_raw_); V_raw_ = nullptr; V_ = nullptr; v_bytes_ = 0;
+        // align to the largest per-warp region this allocation can be used with (N * 4 KiB, <= 4 GiB) so
+        // that no region straddles a 4 GiB boundary: the kernels do 32-bit address arithmetic inside one
+        const size_t align = std::min<size_t>(128 * (size_t)N * 32, (size_t)1 << 32);
+        CU_TRY(cudaMalloc(&V_raw_, need_v + align));
+        V_ = reinterpret_cast<uint4 *>(((uintptr_t)V_raw_ + align - 1) / align * align);
         v_bytes_ = need_v;
+        v_align_ = align;
     }
     if (need > alloc_slots_) {
         CU_TRY(cudaStreamSynchronize(stream_));
-        cudaFree(X_); cudaFree(d_commit_); cudaFree(d_idx_); cudaFree(d_mid_); cudaFree(d_cta_cand_);
-        cudaFreeHost(h_commit_); cudaFreeHost(h_idx_);
-        X_ = nullptr; d_commit_ = nullptr; d_idx_ = nullptr; d_mid_ = nullptr; d_cta_cand_ = nullptr;
-        h_commit_ = nullptr; h_idx_ = nullptr;
-        for (int b = 0; b < 2; b++) { cudaFree(d_out_[b]); cudaFreeHost(h_out_[b]); d_out_[b] = nullptr; h_out_[b] = nullptr; }
-        alloc_slots_ = 0;
-        CU_TRY(cudaMalloc(&X_, (size_t)need * 128));
-        CU_TRY(cudaMalloc(&d_commit_, (size_t)need * 32));
-        CU_TRY(cudaMalloc(&d_idx_, (size_t)need * 8));
-        CU_TRY(cudaMalloc(&d_mid_, (size_t)need * 64));
-        CU_TRY(cudaMalloc(&d_cta_cand_, (size_t)pbkdf2_final_ctas(need) * sizeof(VrfCandidate)));
-        CU_TRY(cudaMallocHost(&h_commit_, (size_t)need * 32));
-        CU_TRY(cudaMallocHost(&h_idx_, (size_t)need * 8));
         for (int b = 0; b < 2; b++) {
+            cudaFree(X_[b]); cudaFree(d_commit_[b]); cudaFree(d_idx_[b]); cudaFree(d_mid_[b]); cudaFree(d_out_[b]);
+            cudaFreeHost(h_commit_[b]); cudaFreeHost(h_idx_[b]); cudaFreeHost(h_out_[b]);
+            X_[b] = nullptr; d_commit_[b] = nullptr; d_idx_[b] = nullptr; d_mid_[b] = nullptr; d_out_[b] = nullptr;
+            h_commit_[b] = nullptr; h_idx_[b] = nullptr; h_out_[b] = nullptr;
+        }
+        cudaFree(d_cta_cand_); d_cta_cand_ = nullptr;
+        alloc_slots_ = 0;
+        for (int b = 0; b < 2; b++) {
+            CU_TRY(cudaMalloc(&X_[b], (size_t)need * 128));
+            CU_TRY(cudaMalloc(&d_commit_[b], (size_t)need * 32));
+            CU_TRY(cudaMalloc(&d_idx_[b], (size_t)need * 8));
+            CU_TRY(cudaMalloc(&d_mid_[b], (size_t)need * 64));
             CU_TRY(cudaMalloc(&d_out_[b], (size_t)need * 16));
+            CU_TRY(cudaMallocHost(&h_commit_[b], (size_t)need * 32));
+            CU_TRY(cudaMallocHost(&h_idx_[b], (size_t)need * 8));
             CU_TRY(cudaMallocHost(&h_out_[b], (size_t)need * 16));
         }
+        CU_TRY(cudaMalloc(&d_cta_cand_, (size_t)pbkdf2_final_ctas(need) * sizeof(VrfCandidate)));
         alloc_slots_ = need;
     }
     return B200POST_OK;
 }
 
-// collect the ROMix device time of the wave that last used buffer `buf` (its events have completed)
+// collect the ROMix device time recorded under parity `buf` (blocks until that launch has finished)
 void DeviceEngine::harvest(int buf) {
     if (!k2_pending_[buf]) return;
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, ev_k2a_[buf], ev_k2b_[buf]) == cudaSuccess) { romix_ms_ += ms; romix_launches_++; }
+    if (cudaEventSynchronize(ev_k2b_[buf]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, ev_k2a_[buf], ev_k2b_[buf]) == cudaSuccess) {
+        romix_ms_ += ms; romix_launches_++; romix_labels_ += k2_labels_[buf];
+    }
     k2_pending_[buf] = false;
 }
 
-int DeviceEngine::run_wave(const LabelJob &job, uint32_t n_slots, uint64_t N, uint8_t *d_out, const uint32_t *d_diff, int buf) {
-    CU_TRY(launch_pbkdf2_expand(job, X_, alloc_slots_, n_slots, stream_));
-    RomixParams rp;
-    rp.V = V_; rp.X = X_; rp.x_stride = alloc_slots_; rp.N = (uint32_t)N; rp.n_slots = n_slots;
-    rp.flags = (uint32_t)options().debug_skip_phase.load();
-    rp.rc = RotConsts{1u << 7, 1u << 9, 1u << 13, 1u << 18};
-    CU_TRY(cudaEventRecord(ev_k2a_[buf], stream_));
-    CU_TRY(launch_romix(variant_, mw_, policy_, tpb_, rp, stream_));
-    CU_TRY(cudaEventRecord(ev_k2b_[buf], stream_));
-    k2_pending_[buf] = true;
-    CU_TRY(launch_pbkdf2_final(job, X_, alloc_slots_, n_slots, d_out, d_diff, d_cta_cand_, stream_));
-    g_launches += 3;
-    if (d_diff) {
+int DeviceEngine::retire(const Job &job, int b) {
+    if (!pend_[b].live) return B200POST_OK;
+    CU_TRY(cudaEventSynchronize(ev_done_[b]));
+    if (job.out_host) memcpy(job.out_host + pend_[b].off * 16, h_out_[b], (size_t)pend_[b].n * 16);
+    pend_[b].live = false;
+    return B200POST_OK;
+}
+
+int DeviceEngine::stage_layer(const Job &job, uint64_t layer, uint32_t n_valid, LabelJob *lj) {
+    const int b = (int)(layer & 1);
+    const uint64_t off = layer * (uint64_t)std::min<uint64_t>(wave_slots_, alloc_slots_);
+    if (job.gather) {
+        if (in_pending_[b]) { CU_TRY(cudaEventSynchronize(ev_in_[b])); in_pending_[b] = false; }
+        memcpy(h_commit_[b], job.commitments + off * 32, (size_t)n_valid * 32);
+        memcpy(h_idx_[b], job.indices + off, (size_t)n_valid * 8);
+        CU_TRY(cudaMemcpyAsync(d_commit_[b], h_commit_[b], (size_t)n_valid * 32, cudaMemcpyHostToDevice, stream_));
+        CU_TRY(cudaMemcpyAsync(d_idx_[b], h_idx_[b], (size_t)n_valid * 8, cudaMemcpyHostToDevice, stream_));
+        CU_TRY(cudaEventRecord(ev_in_[b], stream_));
+        in_pending_[b] = true;
+        CU_TRY(launch_hmac_midstates(d_commit_[b], n_valid, d_mid_[b], stream_));
+        g_launches += 1;
+        *lj = LabelJob{d_mid_[b], 16, d_idx_[b], 0, n_valid};
+    } else {
+        *lj = LabelJob{d_mid_[0], 0, nullptr, job.start + off, n_valid};
+    }
+    CU_TRY(launch_pbkdf2_expand(*lj, X_[b], alloc_slots_, round_up(n_valid, 32), stream_));
+    g_launches += 1;
+    return B200POST_OK;
+}
+
+int DeviceEngine::finish_layer(const Job &job, uint64_t layer, uint32_t n_valid, const LabelJob &lj) {
+    const int b = (int)(layer & 1);
+    const uint64_t off = layer * (uint64_t)std::min<uint64_t>(wave_slots_, alloc_slots_);
+    const uint32_t n_slots = round_up(n_valid, 32);
+    uint8_t *d_out = job.out_dev ? job.out_dev + off * 16 : d_out_[b];
+    CU_TRY(launch_pbkdf2_final(lj, X_[b], alloc_slots_, n_slots, d_out, job.d_diff, d_cta_cand_, stream_));
+    g_launches += 1;
+    if (job.d_diff) {
         CU_TRY(launch_vrf_merge(d_cta_cand_, pbkdf2_final_ctas(n_slots), d_running_, stream_));
         g_launches += 1;
     }
+    if (job.out_host) CU_TRY(cudaMemcpyAsync(h_out_[b], d_out_[b], (size_t)n_valid * 16, cudaMemcpyDeviceToHost, stream_));
+    CU_TRY(cudaEventRecord(ev_done_[b], stream_));
+    pend_[b] = Pending{off, n_valid, true};
     return B200POST_OK;
+}
+
+int DeviceEngine::run_job(const Job &job) {
+    const uint64_t S = std::min<uint64_t>(wave_slots_, alloc_slots_);
+    const uint64_t M = (job.total + S - 1) / S;
+    const RotConsts rc{1u << 7, 1u << 9, 1u << 13, 1u << 18};
+    int rc_ = B200POST_OK, status = B200POST_OK;
+    auto layer_count = [&](uint64_t m) { return (uint32_t)std::min<uint64_t>(S, job.total - m * S); };
+
+    if (variant_ != ROMIX_PIPELINED) {
+        for (uint64_t m = 0; m < M; m++) {
+            if (job.cancel && *job.cancel) { status = B200POST_ERR_CANCELLED; break; }
+            const int b = (int)(m & 1);
+            if ((rc_ = retire(job, b))) return rc_;
+            harvest(b);
+            const uint32_t n_valid = layer_count(m);
+            LabelJob lj;
+            if ((rc_ = stage_layer(job, m, n_valid, &lj))) return rc_;
+            RomixParams rp;
+            rp.V = V_; rp.X = X_[b]; rp.x_stride = alloc_slots_; rp.N = (uint32_t)job.N; rp.n_slots = round_up(n_valid, 32);
+            rp.flags = (uint32_t)options().debug_skip_phase.load(); rp.rc = rc;
+            CU_TRY(cudaEventRecord(ev_k2a_[b], stream_));
+            CU_TRY(launch_romix(variant_, mw_, tpb_, rp, stream_));
+            CU_TRY(cudaEventRecord(ev_k2b_[b], stream_));
+            k2_pending_[b] = true; k2_labels_[b] = n_valid;
+            g_launches += 1;
+            if ((rc_ = finish_layer(job, m, n_valid, lj))) return rc_;
+        }
+    } else {
+        LabelJob lj[2];
+        uint32_t nv[2] = {0, 0};
+        for (uint64_t m = 0; m <= M; m++) {
+            if (m < M && job.cancel && *job.cancel) { status = B200POST_ERR_CANCELLED; break; }
+            const int b = (int)(m & 1);
+            harvest(b);
+            if (m < M) {
+                if ((rc_ = retire(job, b))) return rc_;   // layer m-2 used this parity's buffers
+                nv[b] = layer_count(m);
+                if ((rc_ = stage_layer(job, m, nv[b], &lj[b]))) return rc_;
+            }
+            PipeParams pp;
+            pp.V = V_; pp.x_stride = alloc_slots_; pp.N = (uint32_t)job.N; pp.rc = rc;
+            pp.Xfill = X_[b]; pp.Xmix = X_[b ^ 1];
+            pp.n_fill = m < M ? round_up(nv[b], 32) : 0;
+            pp.n_mix = m >= 1 ? round_up(nv[b ^ 1], 32) : 0;
+            pp.fill_parity = (uint32_t)b;
+            CU_TRY(cudaEventRecord(ev_k2a_[b], stream_));
+            CU_TRY(launch_romix_pipe(mw_, tpb_, dr_unroll_, pp, stream_));
+            CU_TRY(cudaEventRecord(ev_k2b_[b], stream_));
+            k2_pending_[b] = true;
+            k2_labels_[b] = 0.5 * ((m < M ? nv[b] : 0) + (m >= 1 ? nv[b ^ 1] : 0));
+            g_launches += 1;
+            if (m >= 1 && (rc_ = finish_layer(job, m - 1, nv[b ^ 1], lj[b ^ 1]))) return rc_;
+        }
+    }
+    for (int b = 0; b < 2; b++) {
+        if ((rc_ = retire(job, b))) return rc_;
+        harvest(b);
+        if (in_pending_[b]) { CU_TRY(cudaEventSynchronize(ev_in_[b])); in_pending_[b] = false; }
+    }
+    return status;
 }
 
 int DeviceEngine::labels_range(const uint8_t commitment[32], uint64_t N, uint64_t start, uint64_t count, uint8_t *out_host,
@@ -177,13 +277,14 @@ int DeviceEngine::labels_range(const uint8_t commitment[32], uint64_t N, uint64_
     if (count == 0) return B200POST_OK;
     int rc = ensure(N, count);
     if (rc) return rc;
-
     CU_TRY(cudaEventRecord(ev_call_[0], stream_));
+
     // per-call constants: commitment -> HMAC midstates (K0), VRF threshold, running candidate
-    CU_TRY(cudaMemcpyAsync(d_commit_, commitment, 32, cudaMemcpyHostToDevice, stream_));
-    CU_TRY(launch_hmac_midstates(d_commit_, 1, d_mid_, stream_));
+    CU_TRY(cudaMemcpyAsync(d_commit_[0], commitment, 32, cudaMemcpyHostToDevice, stream_));
+    CU_TRY(launch_hmac_midstates(d_commit_[0], 1, d_mid_[0], stream_));
     g_launches += 1;
-    const uint32_t *d_diff = nullptr;
+    Job job;
+    job.start = start; job.total = count; job.N = N; job.out_host = out_host; job.out_dev = out_dev; job.cancel = cancel;
     if (vrf_difficulty) {
         uint32_t be[8];
         for (int k = 0; k < 8; k++)
@@ -192,38 +293,10 @@ int DeviceEngine::labels_range(const uint8_t commitment[32], uint64_t N, uint64_
         CU_TRY(cudaMemcpyAsync(d_diff_, be, 32, cudaMemcpyHostToDevice, stream_));
         CU_TRY(cudaMemsetAsync(d_running_, 0, sizeof(VrfCandidate), stream_));
         CU_TRY(cudaStreamSynchronize(stream_));   // `be` is a stack buffer
-        d_diff = d_diff_;
+        job.d_diff = d_diff_;
     }
-
-    const uint64_t wave = std::min<uint64_t>(wave_slots_, alloc_slots_);
-    struct Pending { uint64_t off; uint32_t n; bool live; } pend[2] = {{0, 0, false}, {0, 0, false}};
-    int status = B200POST_OK;
-    uint64_t done = 0;
-    int w = 0;
-    auto retire = [&](int b) -> int {
-        if (!pend[b].live) return B200POST_OK;
-        CU_TRY(cudaEventSynchronize(ev_done_[b]));
-        harvest(b);
-        if (out_host) memcpy(out_host + pend[b].off * 16, h_out_[b], (size_t)pend[b].n * 16);
-        pend[b].live = false;
-        return B200POST_OK;
-    };
-    while (done < count) {
-        if (cancel && *cancel) { status = B200POST_ERR_CANCELLED; break; }
-        const int b = w & 1;
-        if ((rc = retire(b))) return rc;   // buffer b (wave w-2) must be drained before reuse
-        const uint32_t n_valid = (uint32_t)std::min<uint64_t>(wave, count - done);
-        const uint32_t n_slots = round_up(n_valid, 32);
-        LabelJob job{d_mid_, 0, nullptr, start + done, n_valid};
-        uint8_t *d_out = out_dev ? out_dev + done * 16 : d_out_[b];
-        if ((rc = run_wave(job, n_slots, N, d_out, d_diff, b))) return rc;
-        if (out_host) CU_TRY(cudaMemcpyAsync(h_out_[b], d_out_[b], (size_t)n_valid * 16, cudaMemcpyDeviceToHost, stream_));
-        CU_TRY(cudaEventRecord(ev_done_[b], stream_));
-        pend[b] = Pending{done, n_valid, true};
-        done += n_valid;
-        w++;
-    }
-    for (int k = 0; k < 2; k++) if ((rc = retire((w + k) & 1))) return rc;
+    const int status = run_job(job);
+    if (status != B200POST_OK && status != B200POST_ERR_CANCELLED) return status;
     if (status == B200POST_OK && vrf_difficulty && vrf) {
         CU_TRY(cudaMemcpyAsync(h_running_, d_running_, sizeof(VrfCandidate), cudaMemcpyDeviceToHost, stream_));
         CU_TRY(cudaStreamSynchronize(stream_));
@@ -251,41 +324,10 @@ int DeviceEngine::labels_gather(size_t n_items, const uint8_t *commitments, cons
     int rc = ensure(N, n_items);
     if (rc) return rc;
     CU_TRY(cudaEventRecord(ev_call_[0], stream_));
-    const uint64_t wave = std::min<uint64_t>(wave_slots_, alloc_slots_);
-    uint64_t done = 0;
-    // single-buffered inputs (they are consumed by K0/K1 at the head of the wave), double-buffered outputs
-    struct Pending { uint64_t off; uint32_t n; bool live; } pend[2] = {{0, 0, false}, {0, 0, false}};
-    auto retire = [&](int b) -> int {
-        if (!pend[b].live) return B200POST_OK;
-        CU_TRY(cudaEventSynchronize(ev_done_[b]));
-        harvest(b);
-        memcpy(out_host + pend[b].off * 16, h_out_[b], (size_t)pend[b].n * 16);
-        pend[b].live = false;
-        return B200POST_OK;
-    };
-    int w = 0;
-    while (done < n_items) {
-        const int b = w & 1;
-        if ((rc = retire(b))) return rc;
-        // the previous wave's H2D of the staging buffers must have been consumed: wave w-1's done event
-        if (w > 0) CU_TRY(cudaEventSynchronize(ev_done_[(w - 1) & 1]));
-        const uint32_t n_valid = (uint32_t)std::min<uint64_t>(wave, n_items - done);
-        const uint32_t n_slots = round_up(n_valid, 32);
-        memcpy(h_commit_, commitments + done * 32, (size_t)n_valid * 32);
-        memcpy(h_idx_, indices + done, (size_t)n_valid * 8);
-        CU_TRY(cudaMemcpyAsync(d_commit_, h_commit_, (size_t)n_valid * 32, cudaMemcpyHostToDevice, stream_));
-        CU_TRY(cudaMemcpyAsync(d_idx_, h_idx_, (size_t)n_valid * 8, cudaMemcpyHostToDevice, stream_));
-        CU_TRY(launch_hmac_midstates(d_commit_, n_valid, d_mid_, stream_));
-        g_launches += 1;
-        LabelJob job{d_mid_, 16, d_idx_, 0, n_valid};
-        if ((rc = run_wave(job, n_slots, N, d_out_[b], nullptr, b))) return rc;
-        CU_TRY(cudaMemcpyAsync(h_out_[b], d_out_[b], (size_t)n_valid * 16, cudaMemcpyDeviceToHost, stream_));
-        CU_TRY(cudaEventRecord(ev_done_[b], stream_));
-        pend[b] = Pending{done, n_valid, true};
-        done += n_valid;
-        w++;
-    }
-    for (int k = 0; k < 2; k++) if ((rc = retire((w + k) & 1))) return rc;
+    Job job;
+    job.gather = true; job.commitments = commitments; job.indices = indices; job.total = n_items; job.N = N;
+    job.out_host = out_host;
+    if ((rc = run_job(job))) return rc;
     CU_TRY(cudaEventRecord(ev_call_[1], stream_));
     CU_TRY(cudaStreamSynchronize(stream_));
     { float ms = 0; if (cudaEventElapsedTime(&ms, ev_call_[0], ev_call_[1]) == cudaSuccess) last_call_ms_ = ms; }
@@ -304,11 +346,12 @@ double DeviceEngine::last_call_ms() {
     return last_call_ms_;
 }
 
-void DeviceEngine::romix_time(double *ms_total, uint64_t *launches, bool reset) {
+void DeviceEngine::romix_time(double *ms_total, uint64_t *launches, double *labels, bool reset) {
     std::lock_guard<std::mutex> lk(mu_);
     if (ms_total) *ms_total = romix_ms_;
     if (launches) *launches = romix_launches_;
-    if (reset) { romix_ms_ = 0; romix_launches_ = 0; }
+    if (labels) *labels = romix_labels_;
+    if (reset) { romix_ms_ = 0; romix_launches_ = 0; romix_labels_ = 0; }
 }
 
 // ------------------------------------------------------------------------------------------------ registry

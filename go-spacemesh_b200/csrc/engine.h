@@ -1,7 +1,7 @@
-// engine.h — host runtime of the B200 POST label engine: per-device scratch, wave scheduling,
-// double-buffered result staging.  C++ because the reference's host side for this path is compiled
-// code (Go: activation/post.go PostSetupManager, activation/post_verifier.go); the Go toolchain is
-// absent in this image (INTEGRATION.md shows the cgo binding that sits on top of the C ABI).
+// engine.h — host runtime of the B200 POST label engine: per-device scratch, layer scheduling,
+// double-buffered staging.  C++ because the reference's host side for this path is compiled code
+// (Go: activation/post.go PostSetupManager, activation/post_verifier.go); the Go toolchain is absent
+// in this image (INTEGRATION.md shows the cgo binding that sits on top of the C ABI).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -16,13 +16,13 @@
 namespace b200post {
 
 struct Options {
-    std::atomic<int64_t> romix_variant{ROMIX_DIRECT};
+    std::atomic<int64_t> romix_variant{ROMIX_PIPELINED};
     std::atomic<int64_t> mulwide_mask{0};
     std::atomic<int64_t> tpb{128};
-    std::atomic<int64_t> mem_policy{0};        // 0 ld.cs/st.cs, 1 default, 2 .cg
-    std::atomic<int64_t> debug_skip_phase{0};  // diagnostics only: bit0 skip fill, bit1 skip mix (labels become garbage)
+    std::atomic<int64_t> dr_unroll{4};         // pipelined kernel: Salsa double-rounds unrolled (4) or rolled (1)
     std::atomic<int64_t> ctas_per_sm{0};       // 0 = occupancy maximum
     std::atomic<int64_t> max_scratch_mib{0};   // 0 = 90 % of free HBM
+    std::atomic<int64_t> debug_skip_phase{0};  // diagnostics only (classic variants): bit0 skip fill, bit1 skip mix
 };
 Options &options();
 
@@ -43,18 +43,31 @@ public:
     int labels_range(const uint8_t commitment[32], uint64_t N, uint64_t start, uint64_t count, uint8_t *out_host,
                      uint8_t *out_dev, const uint8_t *vrf_difficulty, VrfResult *vrf, const volatile int *cancel);
     int labels_gather(size_t n_items, const uint8_t *commitments, const uint64_t *indices, uint64_t N, uint8_t *out_host);
-    void romix_time(double *ms_total, uint64_t *launches, bool reset);
+    // accumulated ROMix kernel device time, launches, and label-equivalents processed by those launches
+    void romix_time(double *ms_total, uint64_t *launches, double *labels, bool reset);
     // device time (CUDA events on the engine's stream) of the last labels_range / labels_gather call
     double last_call_ms();
-    // slots (labels) one wave holds for scrypt-N under the current options; 0 + error text on failure
+    // labels one layer (wave) holds for scrypt-N under the current options; 0 + error text on failure
     uint32_t wave_slots(uint64_t N);
     int device() const { return dev_; }
     const cudaDeviceProp &prop() const { return prop_; }
 
 private:
+    struct Job {
+        bool gather = false;
+        const uint8_t *commitments = nullptr;   // gather: n x 32 (host)
+        const uint64_t *indices = nullptr;      // gather: n (host)
+        uint64_t start = 0, total = 0, N = 0;
+        uint8_t *out_host = nullptr, *out_dev = nullptr;
+        const uint32_t *d_diff = nullptr;
+        const volatile int *cancel = nullptr;
+    };
     int ensure(uint64_t N, uint64_t want_slots);   // (re)allocates scratch; sets wave_slots_
     void release();
-    int run_wave(const LabelJob &job, uint32_t n_slots, uint64_t N, uint8_t *d_out, const uint32_t *d_diff, int buf);
+    int run_job(const Job &job);
+    int stage_layer(const Job &job, uint64_t layer, uint32_t n_valid, LabelJob *lj);          // inputs + K0 + K1
+    int finish_layer(const Job &job, uint64_t layer, uint32_t n_valid, const LabelJob &lj);   // K3 (+K4) + D2H + event
+    int retire(const Job &job, int buf);
     void harvest(int buf);
 
     int dev_;
@@ -62,31 +75,37 @@ private:
     std::mutex mu_;
     cudaStream_t stream_ = nullptr;
     // scratch
-    uint4 *V_ = nullptr;
-    size_t v_bytes_ = 0;
-    uint4 *X_ = nullptr;
+    uint4 *V_ = nullptr;         // aligned view into V_raw_
+    void *V_raw_ = nullptr;
+    size_t v_bytes_ = 0, v_align_ = 0;
     uint32_t alloc_slots_ = 0;   // capacity of the per-slot buffers below
-    uint32_t wave_slots_ = 0;    // slots per wave for the current (N, options)
+    uint32_t wave_slots_ = 0;    // slots per layer for the current (N, options)
+    // per-layer state, double-buffered by layer parity
+    uint4 *X_[2] = {nullptr, nullptr};
     uint8_t *d_out_[2] = {nullptr, nullptr};
-    uint8_t *h_out_[2] = {nullptr, nullptr};   // pinned
-    uint8_t *d_commit_ = nullptr;
-    uint64_t *d_idx_ = nullptr;
-    uint8_t *h_commit_ = nullptr;              // pinned staging for gather inputs
-    uint64_t *h_idx_ = nullptr;
-    uint32_t *d_mid_ = nullptr;
+    uint8_t *h_out_[2] = {nullptr, nullptr};       // pinned
+    uint8_t *d_commit_[2] = {nullptr, nullptr};
+    uint64_t *d_idx_[2] = {nullptr, nullptr};
+    uint8_t *h_commit_[2] = {nullptr, nullptr};    // pinned staging for gather inputs
+    uint64_t *h_idx_[2] = {nullptr, nullptr};
+    uint32_t *d_mid_[2] = {nullptr, nullptr};
     uint32_t *d_diff_ = nullptr;
     VrfCandidate *d_cta_cand_ = nullptr;
     VrfCandidate *d_running_ = nullptr;
-    VrfCandidate *h_running_ = nullptr;        // pinned
-    cudaEvent_t ev_done_[2] = {nullptr, nullptr};
+    VrfCandidate *h_running_ = nullptr;            // pinned
+    cudaEvent_t ev_done_[2] = {nullptr, nullptr};  // layer outputs are in h_out_[b]
+    cudaEvent_t ev_in_[2] = {nullptr, nullptr};    // layer inputs have left h_commit_/h_idx_[b]
+    bool in_pending_[2] = {false, false};
     cudaEvent_t ev_k2a_[2] = {nullptr, nullptr}, ev_k2b_[2] = {nullptr, nullptr};
     bool k2_pending_[2] = {false, false};
+    double k2_labels_[2] = {0, 0};
+    struct Pending { uint64_t off; uint32_t n; bool live; } pend_[2] = {{0, 0, false}, {0, 0, false}};
     cudaEvent_t ev_call_[2] = {nullptr, nullptr};
     double last_call_ms_ = 0;
-    double romix_ms_ = 0;
+    double romix_ms_ = 0, romix_labels_ = 0;
     uint64_t romix_launches_ = 0;
     // current tuning
-    int variant_ = 0, mw_ = 0, tpb_ = 128, policy_ = 0;
+    int variant_ = ROMIX_PIPELINED, mw_ = 0, tpb_ = 128, dr_unroll_ = 4;
 };
 
 // registry: lazily created engine per CUDA ordinal (nullptr + error text if the device is unusable)

@@ -8,22 +8,40 @@ namespace b200post {
 // =================================================================================================
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// Scratchpad access policies (V is written once and read ~once: nothing is worth keeping in cache):
-//   0: ld.cs / st.cs (evict-first streaming)   1: default ld / st   2: ld.cg / st.cg (L2 only)
-template <int POLICY>
-__device__ __forceinline__ uint4 ld_v(const uint4 *p) {
+// Scratchpad accesses are streaming (.cs = evict-first): V is written once and read about once, and a
+// wave's scratch (tens of GiB) never fits the 126 MB L2.  (Default and .cg policies measured the same.)
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
     uint4 v;
-    if (POLICY == 0) asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    else if (POLICY == 1) asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    else asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
-template <int POLICY>
-__device__ __forceinline__ void st_v(uint4 *p, const uint4 &v) {
-    if (POLICY == 0) asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    else if (POLICY == 1) asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    else asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+__device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// Ampere-style async copy global -> shared, 16 B per lane, L2 only (SASS: LDGSTS)
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+// Same with the 64-bit source address given as {lo, hi} + immediate: scratchpad regions never cross a 4 GiB
+// boundary (the engine aligns V to the region size), so per-row address math is one 32-bit IMAD on the
+// fmaheavy pipe instead of 64-bit IADD3/IMAD.WIDE chains on the saturated alu pipe.
+template <int IMM>
+__device__ __forceinline__ void cp_async16_lohi(uint32_t dst_smem, uint32_t lo, uint32_t hi) {
+    asm volatile("{\n\t.reg .b64 a;\n\tmov.b64 a, {%1, %2};\n\tcp.async.cg.shared.global [%0], [a+%3], 16;\n\t}"
+                 ::"r"(dst_smem), "r"(lo), "r"(hi), "n"(IMM) : "memory");
+}
+template <int IMM>
+__device__ __forceinline__ void st_stream_lohi(uint32_t lo, uint32_t hi, const uint4 &v) {
+    asm volatile("{\n\t.reg .b64 a;\n\tmov.b64 a, {%0, %1};\n\tst.global.cs.v4.u32 [a+%2], {%3,%4,%5,%6};\n\t}"
+                 ::"r"(lo), "r"(hi), "n"(IMM), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void sts128(uint32_t a, const uint4 &v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -121,7 +139,7 @@ __global__ void __launch_bounds__(128) pbkdf2_expand_kernel(LabelJob job, uint4 
 // private scratch, so any layout is legal as long as reads undo it; the swizzle makes the dense
 // 32 x 128-B shared-memory tile bank-conflict-free in both the row-wise and the transposed access.
 // =================================================================================================
-template <int VARIANT, int MW, int TPB, int POLICY>
+template <int VARIANT, int MW, int TPB>
 __global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t slot = blockIdx.x * TPB + threadIdx.x;
@@ -143,14 +161,14 @@ __global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
         uint4 *const Vt = Vw + lane * 8;
         for (uint32_t i = 0; i < n1; i++) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) st_v<POLICY>(Vt + (size_t)i * 256 + k, ROW_CHUNK(lo, hi, k));
+            for (int k = 0; k < 8; k++) st_stream(Vt + (size_t)i * 256 + k, ROW_CHUNK(lo, hi, k));
             blockmix_r1<MW>(lo, hi, rc);
         }
         for (uint32_t i = 0; i < n2; i++) {
             const uint32_t j = hi[0] & mask;
             uint32_t vlo[16], vhi[16];
 #pragma unroll
-            for (int k = 0; k < 8; k++) set_chunk(vlo, vhi, k, ld_v<POLICY>(Vt + (size_t)j * 256 + k));
+            for (int k = 0; k < 8; k++) set_chunk(vlo, vhi, k, ld_stream(Vt + (size_t)j * 256 + k));
             blockmix_r1_xor<MW>(lo, hi, vlo, vhi, rc);
         }
     } else if (VARIANT == ROMIX_COALESCED) {
@@ -163,7 +181,7 @@ __global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
             __syncwarp();
             uint4 *const dst = Vw + (size_t)i * 256 + lane;   // + k*32: the warp writes 512 contiguous bytes per k
 #pragma unroll
-            for (int k = 0; k < 8; k++) st_v<POLICY>(dst + k * 32, lds128(tile + (k * 4 + tr_row) * 128 + (tr_c << 4)));
+            for (int k = 0; k < 8; k++) st_stream(dst + k * 32, lds128(tile + (k * 4 + tr_row) * 128 + (tr_c << 4)));
             __syncwarp();
             blockmix_r1<MW>(lo, hi, rc);
         }
@@ -173,7 +191,7 @@ __global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const uint32_t jr = __shfl_sync(0xffffffffu, j, k * 4 + tr_row);
-                t[k] = ld_v<POLICY>(Vw + (size_t)jr * 256 + k * 32 + lane);
+                t[k] = ld_stream(Vw + (size_t)jr * 256 + k * 32 + lane);
             }
 #pragma unroll
             for (int k = 0; k < 8; k++) sts128(tile + (k * 4 + tr_row) * 128 + (tr_c << 4), t[k]);
@@ -230,6 +248,105 @@ __global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) p.X[(size_t)k * p.x_stride + slot] = ROW_CHUNK(lo, hi, k);
+}
+
+// =================================================================================================
+// K2p: pipelined ROMix.  Every thread advances TWO labels per step: the label of layer m is in its fill
+// loop (V[i] <- X; X <- BlockMix(X)) while the label of layer m-1 is in its mix loop
+// (X <- BlockMix(X ^ V[Integerify(X)])).  The mix loop's dependent HBM read (~0.6-1.5 us) is issued
+// with cp.async at the top of the step and lands in shared memory while the fill label's BlockMix
+// keeps the integer pipes busy; the two Salsa streams are interleaved instruction by instruction.
+// Each slot owns two scratchpads (parity = layer & 1).  The mid-state of a filled label travels to the
+// next launch through the layer's X buffer, so consecutive launches form one software pipeline:
+//     launch m:  K1(layer m) -> K2p{mix layer m-1, fill layer m} -> K3(layer m-1)
+// =================================================================================================
+template <int MW, int TPB, int DR_UNROLL>
+__global__ void __launch_bounds__(TPB) romix_pipe_kernel(const PipeParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const uint32_t slot = blockIdx.x * TPB + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
+    const bool do_fill = slot < p.n_fill, do_mix = slot < p.n_mix;   // multiples of 32: warp-uniform
+    if (!do_fill && !do_mix) return;
+    const uint32_t N = p.N, mask = N - 1;
+    const RotConsts rc = p.rc;
+    const uint32_t tile_f = smem_u32(smem_raw) + warp_in_cta * 8192, tile_m = tile_f + 4096;
+    const uint32_t own_f = tile_f + lane * 128, own_m = tile_m + lane * 128;
+    const uint32_t swz = lane & 7, tr_row = lane >> 3, tr_c = lane & 7;
+    const size_t warp = slot >> 5;
+    // this lane's base addresses inside the two scratchpad regions of its warp, as {lo, hi}: a region is
+    // N * 4 KiB, V is aligned to the region size and N <= 2^20, so `hi` is constant within a region
+    const uint64_t vf64 = (uint64_t)(p.V + (warp * 2 + p.fill_parity) * (size_t)N * 256 + lane);         // written
+    const uint64_t vm64 = (uint64_t)(p.V + (warp * 2 + (p.fill_parity ^ 1)) * (size_t)N * 256 + lane);   // read
+    const uint32_t vf_hi = (uint32_t)(vf64 >> 32), vm_lo = (uint32_t)vm64, vm_hi = (uint32_t)(vm64 >> 32);
+    uint32_t vf_cur = (uint32_t)vf64;   // low word of row i's address for this lane; +4096 per step
+
+    uint32_t lo_f[16], hi_f[16], lo_m[16], hi_m[16];
+    if (do_fill) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) set_chunk(lo_f, hi_f, k, p.Xfill[(size_t)k * p.x_stride + slot]);
+    }
+    if (do_mix) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) set_chunk(lo_m, hi_m, k, p.Xmix[(size_t)k * p.x_stride + slot]);
+    }
+    // lane whose j this lane needs for its k-th transposed copy (loop-invariant)
+    uint32_t src_lane[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) src_lane[k] = k * 4 + tr_row;
+    const uint32_t tile_m_tr = tile_m + tr_row * 128 + (tr_c << 4);
+    const uint32_t tile_f_tr = tile_f + tr_row * 128 + (tr_c << 4);
+
+    // issue the mix label's row read: 8 x (4 rows x 128 B) per warp, straight into the shared tile
+#define MIX_PREFETCH_K(k) \
+    cp_async16_lohi<(k) * 512>(tile_m_tr + (k) * 512, mad_u32(__shfl_sync(0xffffffffu, j, src_lane[k]), 4096u, vm_lo), vm_hi);
+    auto mix_prefetch = [&]() {
+        const uint32_t j = hi_m[0] & mask;
+        MIX_PREFETCH_K(0) MIX_PREFETCH_K(1) MIX_PREFETCH_K(2) MIX_PREFETCH_K(3)
+        MIX_PREFETCH_K(4) MIX_PREFETCH_K(5) MIX_PREFETCH_K(6) MIX_PREFETCH_K(7)
+        cp_async_commit();
+    };
+    // write the fill label's row i: own row -> tile (swizzled), tile -> HBM as 8 x 512 contiguous bytes
+#define FILL_STORE_K(k) st_stream_lohi<(k) * 512>(vf_cur, vf_hi, lds128(tile_f_tr + (k) * 512));
+    auto fill_store = [&]() {
+#pragma unroll
+        for (int k = 0; k < 8; k++) sts128(own_f + ((k ^ swz) << 4), ROW_CHUNK(lo_f, hi_f, k));
+        __syncwarp();
+        FILL_STORE_K(0) FILL_STORE_K(1) FILL_STORE_K(2) FILL_STORE_K(3)
+        FILL_STORE_K(4) FILL_STORE_K(5) FILL_STORE_K(6) FILL_STORE_K(7)
+        __syncwarp();
+        vf_cur = mad_u32(1u, 4096u, vf_cur);
+    };
+
+    // One loop serves all three launch shapes (fill+mix in steady state, fill only for the first layer,
+    // mix only for the drain).  The mix label's row for step i is requested at the end of step i-1 and
+    // lands in shared memory while this step's fill BlockMix occupies the integer pipes.
+    if (do_mix) mix_prefetch();
+    for (uint32_t i = 0; i < N; i++) {
+        if (do_fill) {
+            fill_store();
+            blockmix_r1<MW, DR_UNROLL>(lo_f, hi_f, rc);
+        }
+        if (do_mix) {
+            cp_async_wait_all();
+            __syncwarp();
+            uint32_t vlo[16], vhi[16];
+#pragma unroll
+            for (int k = 0; k < 8; k++) set_chunk(vlo, vhi, k, lds128(own_m + ((k ^ swz) << 4)));
+            __syncwarp();
+            blockmix_r1_xor<MW, DR_UNROLL>(lo_m, hi_m, vlo, vhi, rc);
+            if (i + 1 < N) mix_prefetch();
+        }
+    }
+#undef MIX_PREFETCH_K
+#undef FILL_STORE_K
+    if (do_fill) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) p.Xfill[(size_t)k * p.x_stride + slot] = ROW_CHUNK(lo_f, hi_f, k);
+    }
+    if (do_mix) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) p.Xmix[(size_t)k * p.x_stride + slot] = ROW_CHUNK(lo_m, hi_m, k);
+    }
 }
 
 // =================================================================================================
@@ -393,6 +510,7 @@ size_t romix_smem_bytes(int variant, int tpb) {
     const size_t warps = (size_t)tpb / 32;
     if (variant == ROMIX_COALESCED) return warps * 4096;
     if (variant == ROMIX_BULK) return warps * 8192 + warps * 8;
+    if (variant == ROMIX_PIPELINED) return warps * 8192;
     return 0;
 }
 
@@ -402,63 +520,99 @@ const char *romix_variant_name(int variant) {
         case ROMIX_COALESCED: return "coalesced";
         case ROMIX_BULK: return "bulk";
         case ROMIX_NOMEM: return "nomem";
+        case ROMIX_PIPELINED: return "pipelined";
     }
     return "?";
 }
 
 typedef void (*romix_fn)(const RomixParams);
+typedef void (*pipe_fn)(const PipeParams);
 
-template <int VARIANT, int MW, int POLICY>
+// rotate-mix masks compiled in (see salsa20_8): 0 = all funnel shifts (the fastest, measured);
+// 0x8421 / 0xFFFF = 4 / 16 of a half-round's 16 rotates as IMAD.WIDE, kept as the evidence for that finding
+#define B200POST_MW_LIST(X) X(0x0000) X(0x8421) X(0xFFFF)
+
+template <int VARIANT, int MW>
 static romix_fn pick_tpb(int tpb) {
     switch (tpb) {
-        case 64: return romix_kernel<VARIANT, MW, 64, POLICY>;
-        case 128: return romix_kernel<VARIANT, MW, 128, POLICY>;
-        case 256: return romix_kernel<VARIANT, MW, 256, POLICY>;
+        case 128: return romix_kernel<VARIANT, MW, 128>;
+        case 256: return romix_kernel<VARIANT, MW, 256>;
     }
     return nullptr;
-}
-template <int VARIANT, int MW>
-static romix_fn pick_policy(int policy, int tpb) {
-    if (VARIANT == ROMIX_DIRECT || VARIANT == ROMIX_COALESCED) {
-        switch (policy) {
-            case 1: return pick_tpb<VARIANT, MW, 1>(tpb);
-            case 2: return pick_tpb<VARIANT, MW, 2>(tpb);
-        }
-    }
-    return pick_tpb<VARIANT, MW, 0>(tpb);
 }
 template <int VARIANT>
-static romix_fn pick_mw(int mw, int policy, int tpb) {
+static romix_fn pick_mw(int mw, int tpb) {
     switch (mw) {
-        case 0: return pick_policy<VARIANT, 0>(policy, tpb);
-        case 5: return pick_policy<VARIANT, 5>(policy, tpb);
-        case 15: return pick_policy<VARIANT, 15>(policy, tpb);
+#define X(m) case m: return pick_tpb<VARIANT, m>(tpb);
+        B200POST_MW_LIST(X)
+#undef X
     }
     return nullptr;
 }
-static romix_fn pick(int variant, int mw, int policy, int tpb) {
+static romix_fn pick(int variant, int mw, int tpb) {
     switch (variant) {
-        case ROMIX_DIRECT: return pick_mw<ROMIX_DIRECT>(mw, policy, tpb);
-        case ROMIX_COALESCED: return pick_mw<ROMIX_COALESCED>(mw, policy, tpb);
-        case ROMIX_BULK: return pick_mw<ROMIX_BULK>(mw, policy, tpb);
-        case ROMIX_NOMEM: return pick_mw<ROMIX_NOMEM>(mw, policy, tpb);
+        case ROMIX_DIRECT: return pick_mw<ROMIX_DIRECT>(mw, tpb);
+        case ROMIX_COALESCED: return pick_mw<ROMIX_COALESCED>(mw, tpb);
+        case ROMIX_BULK: return pick_mw<ROMIX_BULK>(mw, tpb);
+        case ROMIX_NOMEM: return pick_mw<ROMIX_NOMEM>(mw, tpb);
+    }
+    return nullptr;
+}
+template <int MW>
+static pipe_fn pick_pipe_tpb(int tpb, int dr_unroll) {
+    if (dr_unroll == 4) {
+        switch (tpb) {
+            case 64: return romix_pipe_kernel<MW, 64, 4>;
+            case 128: return romix_pipe_kernel<MW, 128, 4>;
+            case 256: return romix_pipe_kernel<MW, 256, 4>;
+        }
+    } else {
+        switch (tpb) {
+            case 64: return romix_pipe_kernel<MW, 64, 1>;
+            case 128: return romix_pipe_kernel<MW, 128, 1>;
+            case 256: return romix_pipe_kernel<MW, 256, 1>;
+        }
+    }
+    return nullptr;
+}
+static pipe_fn pick_pipe(int mw, int tpb, int dr_unroll) {
+    switch (mw) {
+#define X(m) case m: return pick_pipe_tpb<m>(tpb, dr_unroll);
+        B200POST_MW_LIST(X)
+#undef X
     }
     return nullptr;
 }
 
-int romix_max_ctas_per_sm(int variant, int mulwide_mask, int policy, int tpb) {
-    romix_fn fn = pick(variant, mulwide_mask, policy, tpb);
-    if (!fn) return 0;
+bool romix_mask_supported(int mw) {
+    switch (mw) {
+#define X(m) case m: return true;
+        B200POST_MW_LIST(X)
+#undef X
+    }
+    return false;
+}
+
+int romix_max_ctas_per_sm(int variant, int mulwide_mask, int tpb, int dr_unroll) {
     const size_t smem = romix_smem_bytes(variant, tpb);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int n = 0;
+    if (variant == ROMIX_PIPELINED) {
+        pipe_fn fn = pick_pipe(mulwide_mask, tpb, dr_unroll);
+        if (!fn) return 0;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, tpb, smem) != cudaSuccess) return 0;
+        return n;
+    }
+    romix_fn fn = pick(variant, mulwide_mask, tpb);
+    if (!fn) return 0;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, tpb, smem) != cudaSuccess) return 0;
     return n;
 }
 
-cudaError_t launch_romix(int variant, int mulwide_mask, int policy, int tpb, const RomixParams &p, cudaStream_t s) {
+cudaError_t launch_romix(int variant, int mulwide_mask, int tpb, const RomixParams &p, cudaStream_t s) {
     if (p.n_slots == 0) return cudaSuccess;
-    romix_fn fn = pick(variant, mulwide_mask, policy, tpb);
+    romix_fn fn = pick(variant, mulwide_mask, tpb);
     if (!fn) return cudaErrorInvalidValue;
     const size_t smem = romix_smem_bytes(variant, tpb);
     if (smem > 48 * 1024) {
@@ -466,6 +620,20 @@ cudaError_t launch_romix(int variant, int mulwide_mask, int policy, int tpb, con
         if (e != cudaSuccess) return e;
     }
     fn<<<(p.n_slots + tpb - 1) / tpb, tpb, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_romix_pipe(int mulwide_mask, int tpb, int dr_unroll, const PipeParams &p, cudaStream_t s) {
+    const uint32_t n = p.n_fill > p.n_mix ? p.n_fill : p.n_mix;
+    if (n == 0) return cudaSuccess;
+    pipe_fn fn = pick_pipe(mulwide_mask, tpb, dr_unroll);
+    if (!fn) return cudaErrorInvalidValue;
+    const size_t smem = romix_smem_bytes(ROMIX_PIPELINED, tpb);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    fn<<<(n + tpb - 1) / tpb, tpb, smem, s>>>(p);
     return cudaGetLastError();
 }
 

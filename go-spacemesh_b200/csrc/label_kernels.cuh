@@ -26,6 +26,7 @@ enum RomixVariant : int {
     ROMIX_COALESCED = 1,// rows transposed through shared memory so that a warp moves whole 128-B lines
     ROMIX_BULK = 2,     // rows moved by the TMA unit: cp.async.bulk global<->shared + mbarrier
     ROMIX_NOMEM = 3,    // ALU ceiling probe: no scratchpad traffic (results are NOT labels)
+    ROMIX_PIPELINED = 4,// two labels per thread: layer m fills while layer m-1 mixes (cp.async prefetch)
 };
 
 struct RomixParams {
@@ -35,6 +36,17 @@ struct RomixParams {
     uint32_t N;          // scrypt N (power of two, >= 2)
     uint32_t n_slots;    // active slots this wave (multiple of 32)
     uint32_t flags;      // diagnostics: bit0 skip fill loop, bit1 skip mix loop (0 in production)
+    RotConsts rc;
+};
+
+struct PipeParams {
+    uint4 *V;            // scratch: [warp][parity][row j][lane][8 x uint4]  (two scratchpads per slot)
+    uint4 *Xfill;        // layer being filled (initial state in, mid-state out); unused if n_fill == 0
+    uint4 *Xmix;         // layer being mixed (mid-state in, final state out); unused if n_mix == 0
+    uint32_t x_stride;
+    uint32_t N;
+    uint32_t n_fill, n_mix;   // active slots of each layer (multiples of 32)
+    uint32_t fill_parity;     // which of the slot's two scratchpads the filling layer owns
     RotConsts rc;
 };
 
@@ -54,7 +66,9 @@ struct VrfCandidate {           // 48 bytes
 
 cudaError_t launch_hmac_midstates(const uint8_t *d_commitments, uint32_t n, uint32_t *d_mid, cudaStream_t s);
 cudaError_t launch_pbkdf2_expand(const LabelJob &job, uint4 *X, uint32_t x_stride, uint32_t n_slots, cudaStream_t s);
-cudaError_t launch_romix(int variant, int mulwide_mask, int policy, int tpb, const RomixParams &p, cudaStream_t s);
+cudaError_t launch_romix(int variant, int mulwide_mask, int tpb, const RomixParams &p, cudaStream_t s);
+cudaError_t launch_romix_pipe(int mulwide_mask, int tpb, int dr_unroll, const PipeParams &p, cudaStream_t s);
+bool romix_mask_supported(int mw);
 // out16: n_valid x 16 bytes (device).  vrf_difficulty_be: 8 big-endian words (device) or nullptr.
 // cta_cand: one VrfCandidate per CTA (device), only touched when vrf_difficulty_be != nullptr.
 cudaError_t launch_pbkdf2_final(const LabelJob &job, const uint4 *X, uint32_t x_stride, uint32_t n_slots,
@@ -65,7 +79,7 @@ uint32_t pbkdf2_final_ctas(uint32_t n_slots);
 // bytes of dynamic shared memory the ROMix variant needs per CTA
 size_t romix_smem_bytes(int variant, int tpb);
 // occupancy query helper: max resident CTAs/SM for (variant, mask, tpb)
-int romix_max_ctas_per_sm(int variant, int mulwide_mask, int policy, int tpb);
+int romix_max_ctas_per_sm(int variant, int mulwide_mask, int tpb, int dr_unroll);
 const char *romix_variant_name(int variant);
 
 }  // namespace b200post

@@ -61,50 +61,83 @@ PD_HD void xor_rotl(uint32_t &dst, uint32_t s, int k, uint32_t pow2k) {
 struct RotConsts { uint32_t p7, p9, p13, p18; };
 
 // ------------------------------------------------------------------------------------------------
-// Salsa20/8 (RFC 7914 §3): x <- x + rounds(x).  MW is a 4-bit mask choosing, per rotate amount
-// (bit0: 7, bit1: 9, bit2: 13, bit3: 18), the mul.wide form instead of the funnel shift.
+// Salsa20/8 (RFC 7914 §3): x <- x + rounds(x).
+// MW is a 16-bit mask selecting which of the 16 rotates of a half-round use the mul.wide form
+// (bit 4*q + r: quarter-round q = 0..3 of the half-round, rotate r = 0..3 for 7/9/13/18).  The same
+// mask serves column and row half-rounds.  Measured on B200 (profiles/): SHF and LOP3 issue on the
+// 16-lane alu pipe, IMAD.IADD / IMAD.WIDE on the 16-lane fmaheavy pipe (IMAD.WIDE at half rate), so
+// moving ~1/3 of the rotates to IMAD.WIDE balances the two pipes; all-SHF is alu-bound.
 // ------------------------------------------------------------------------------------------------
-template <int MW>
+#define PD_QR(w, q, a, b, c, d)                                                    \
+    xor_rotl<((MW >> (4 * (q) + 0)) & 1) != 0>(w[b], w[a] + w[d], 7, rc.p7);       \
+    xor_rotl<((MW >> (4 * (q) + 1)) & 1) != 0>(w[c], w[b] + w[a], 9, rc.p9);       \
+    xor_rotl<((MW >> (4 * (q) + 2)) & 1) != 0>(w[d], w[c] + w[b], 13, rc.p13);     \
+    xor_rotl<((MW >> (4 * (q) + 3)) & 1) != 0>(w[a], w[d] + w[c], 18, rc.p18);
+#define PD_DOUBLE_ROUND(w)                                                                               \
+    PD_QR(w, 0, 0, 4, 8, 12) PD_QR(w, 1, 5, 9, 13, 1) PD_QR(w, 2, 10, 14, 2, 6) PD_QR(w, 3, 15, 3, 7, 11) \
+    PD_QR(w, 0, 0, 1, 2, 3) PD_QR(w, 1, 5, 6, 7, 4) PD_QR(w, 2, 10, 11, 8, 9) PD_QR(w, 3, 15, 12, 13, 14)
+
+template <int MW, int DR_UNROLL = 4>
 PD_HD void salsa20_8(uint32_t (&x)[16], const RotConsts &rc) {
     uint32_t w[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) w[i] = x[i];
-#define PD_QR(a, b, c, d)                                             \
-    xor_rotl<(MW & 1) != 0>(w[b], w[a] + w[d], 7, rc.p7);              \
-    xor_rotl<(MW & 2) != 0>(w[c], w[b] + w[a], 9, rc.p9);              \
-    xor_rotl<(MW & 4) != 0>(w[d], w[c] + w[b], 13, rc.p13);            \
-    xor_rotl<(MW & 8) != 0>(w[a], w[d] + w[c], 18, rc.p18);
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        PD_QR(0, 4, 8, 12) PD_QR(5, 9, 13, 1) PD_QR(10, 14, 2, 6) PD_QR(15, 3, 7, 11)   // column round
-        PD_QR(0, 1, 2, 3) PD_QR(5, 6, 7, 4) PD_QR(10, 11, 8, 9) PD_QR(15, 12, 13, 14)   // row round
-    }
-#undef PD_QR
+#pragma unroll DR_UNROLL
+    for (int r = 0; r < 4; r++) { PD_DOUBLE_ROUND(w) }
 #pragma unroll
     for (int i = 0; i < 16; i++) x[i] += w[i];
 }
 
+// Two independent Salsa20/8 cores in one instruction stream (8 independent dependency chains): used by
+// the pipelined ROMix kernel, where every thread advances a filling and a mixing label together.
+template <int MW, int DR_UNROLL>
+PD_HD void salsa20_8_x2(uint32_t (&xa)[16], uint32_t (&xb)[16], const RotConsts &rc) {
+    uint32_t wa[16], wb[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { wa[i] = xa[i]; wb[i] = xb[i]; }
+#pragma unroll DR_UNROLL
+    for (int r = 0; r < 4; r++) { PD_DOUBLE_ROUND(wa) PD_DOUBLE_ROUND(wb) }
+#pragma unroll
+    for (int i = 0; i < 16; i++) { xa[i] += wa[i]; xb[i] += wb[i]; }
+}
+
 // scryptBlockMix for r = 1 (RFC 7914 §4) on X = lo(16) || hi(16):
 //   T = hi ^ lo; Y0 = Salsa(T); Y1 = Salsa(Y0 ^ hi); X = Y0 || Y1.
-template <int MW>
+template <int MW, int DR_UNROLL = 4>
 PD_HD void blockmix_r1(uint32_t (&lo)[16], uint32_t (&hi)[16], const RotConsts &rc) {
 #pragma unroll
     for (int i = 0; i < 16; i++) lo[i] ^= hi[i];
-    salsa20_8<MW>(lo, rc);
+    salsa20_8<MW, DR_UNROLL>(lo, rc);
 #pragma unroll
     for (int i = 0; i < 16; i++) hi[i] ^= lo[i];
-    salsa20_8<MW>(hi, rc);
+    salsa20_8<MW, DR_UNROLL>(hi, rc);
 }
 // Same, fused with the ROMix phase-2 "X ^= V[j]" so that the three-way XOR is one LOP3 per word.
-template <int MW>
+template <int MW, int DR_UNROLL = 4>
 PD_HD void blockmix_r1_xor(uint32_t (&lo)[16], uint32_t (&hi)[16], const uint32_t (&vlo)[16],
                            const uint32_t (&vhi)[16], const RotConsts &rc) {
 #pragma unroll
     for (int i = 0; i < 16; i++) { hi[i] ^= vhi[i]; lo[i] = lo[i] ^ vlo[i] ^ hi[i]; }
-    salsa20_8<MW>(lo, rc);
+    salsa20_8<MW, DR_UNROLL>(lo, rc);
 #pragma unroll
     for (int i = 0; i < 16; i++) hi[i] ^= lo[i];
-    salsa20_8<MW>(hi, rc);
+    salsa20_8<MW, DR_UNROLL>(hi, rc);
+}
+
+// One ROMix step of the pipelined kernel: BlockMix of the filling label (lo_f, hi_f) and
+// BlockMix(X ^ V[j]) of the mixing label (lo_m, hi_m), interleaved.
+template <int MW, int DR_UNROLL>
+PD_HD void blockmix_r1_dual(uint32_t (&lo_f)[16], uint32_t (&hi_f)[16], uint32_t (&lo_m)[16], uint32_t (&hi_m)[16],
+                            const uint32_t (&vlo)[16], const uint32_t (&vhi)[16], const RotConsts &rc) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        lo_f[i] ^= hi_f[i];
+        hi_m[i] ^= vhi[i]; lo_m[i] = lo_m[i] ^ vlo[i] ^ hi_m[i];
+    }
+    salsa20_8_x2<MW, DR_UNROLL>(lo_f, lo_m, rc);
+#pragma unroll
+    for (int i = 0; i < 16; i++) { hi_f[i] ^= lo_f[i]; hi_m[i] ^= lo_m[i]; }
+    salsa20_8_x2<MW, DR_UNROLL>(hi_f, hi_m, rc);
 }
 
 // ------------------------------------------------------------------------------------------------

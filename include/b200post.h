@@ -72,9 +72,11 @@ int b200post_providers(b200post_provider *out, int max);
 /* Thread-local text of the last error returned on this thread ("" if none). */
 const char *b200post_last_error(void);
 
-/* Engine tuning knobs (process-wide; take effect at the next scratch (re)allocation):
- *   "romix_variant" 0 direct | 1 coalesced | 2 bulk(TMA) ; "mulwide_mask" 0|5|10|15 ; "tpb" 64|128|256 ;
- *   "ctas_per_sm" 0 = as many as fit ; "max_scratch_mib" 0 = 90 % of free HBM.
+/* Engine tuning knobs (process-wide; take effect at the next call):
+ *   "romix_variant"  4 pipelined (default) | 0 direct | 1 coalesced | 2 bulk(TMA) | 3 nomem (ALU probe, NOT labels)
+ *   "mulwide_mask"   16-bit mask of Salsa rotates issued as IMAD.WIDE instead of SHF (a compiled-in set)
+ *   "tpb" 64|128|256 (64 only for the pipelined kernel) ; "dr_unroll" 4|1 ; "ctas_per_sm" 0 = as many as fit ;
+ *   "max_scratch_mib" 0 = 90 % of free HBM ; "debug_skip_phase" diagnostics only.
  * Returns B200POST_ERR_INVALID_ARGUMENT for an unknown key or value. */
 int b200post_set_option(const char *key, int64_t value);
 int64_t b200post_get_option(const char *key);
@@ -122,9 +124,11 @@ int b200post_verify_vrf_nonce(uint32_t provider, uint64_t nonce, const uint8_t n
 int b200post_benchmark(uint32_t provider, uint64_t n, double seconds, double *labels_per_sec);
 
 /* Device-side instrumentation for bench.py: kernels launched by this library since load, and the
- * accumulated device time (ms, CUDA events on the launching stream) of the ROMix kernel. */
+ * accumulated device time (ms, CUDA events on the launching stream) of the ROMix kernel, its launch count
+ * and the label-equivalents those launches processed (a pipelined launch that fills S labels and mixes S
+ * labels counts S). */
 uint64_t b200post_launch_count(void);
-int b200post_romix_time(uint32_t provider, double *ms_total, uint64_t *launches, int reset);
+int b200post_romix_time(uint32_t provider, double *ms_total, uint64_t *launches, double *labels, int reset);
 /* Device time in ms (CUDA events recorded on the engine's own stream at the start and end of the call)
  * of the most recent labels_range* / labels_gather call on `provider`; < 0 if the provider is unusable. */
 double b200post_last_call_ms(uint32_t provider);

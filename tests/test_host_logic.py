@@ -68,12 +68,12 @@ def test_no_cpu_fallback(b2):
 
 
 def test_argument_validation(b2):
-    for n in (0, 1, 3, 12, 2**32):
+    for n in (0, 1, 3, 12, 2**21, 2**32):
         with pytest.raises(b2.B200PostError) as e:
             b2.labels_range(bytes(32), n, 0, 8)
         assert e.value.code == b2.ERR_INVALID_ARGUMENT
     with pytest.raises(b2.B200PostError) as e:
-        b2.labels_range(bytes(32), 2, 2**64 - 4, 8)   # index overflow
+        b2.labels_range(bytes(32), 2, 2**64 - 4, 8)   # index overflow: last index would be 2^64 + 3
     assert e.value.code == b2.ERR_INVALID_ARGUMENT
     with pytest.raises(b2.B200PostError):
         b2.set_option("romix_variant", 9)

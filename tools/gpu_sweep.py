@@ -20,7 +20,7 @@ OUT = "gpurun_out"
 os.makedirs(OUT, exist_ok=True)
 
 
-def parity(variant: int, mws=(0, 5, 15)):
+def parity(variant: int, mws=(0, 0x8421, 0xFFFF)):
     res = {"variant": variant, "cases": []}
     rng = np.random.default_rng(7)
     commitment = bytes(rng.integers(0, 256, 32, dtype=np.uint8))
@@ -65,17 +65,19 @@ def sweep(specs, tag):
         try:
             b2.set_option("romix_variant", sp["variant"]); b2.set_option("mulwide_mask", sp["mw"])
             b2.set_option("tpb", sp["tpb"]); b2.set_option("ctas_per_sm", sp["ctas"])
-            b2.set_option("mem_policy", sp.get("policy", 0)); b2.set_option("debug_skip_phase", sp.get("skip", 0))
-            slots = prov["sm_count"] * sp["ctas"] * sp["tpb"]
+            b2.set_option("debug_skip_phase", sp.get("skip", 0)); b2.set_option("dr_unroll", sp.get("dr", 4))
+            slots = b2.wave_slots(n)
             waves = sp.get("waves", 2)
-            b2.labels_range(commitment, n, 0, slots, discard=True)  # warm-up wave: allocates scratch
+            b2.labels_range(commitment, n, 0, slots, discard=True)  # warm-up layer: allocates scratch
             b2.romix_time(reset=True)
             t0 = time.time()
             b2.labels_range(commitment, n, slots, slots * waves, discard=True)
             wall = time.time() - t0
-            ms, k = b2.romix_time(reset=True)
-            lps_k2 = slots * k / (ms / 1e3)
-            r = dict(sp, slots=slots, romix_ms=round(ms / max(k, 1), 3), launches=k, labels_per_s_k2=round(lps_k2), labels_per_s_wall=round(slots * waves / wall),
+            dev_ms = b2.last_call_ms()
+            ms, k, lab = b2.romix_time(reset=True)
+            lps_k2 = lab / (ms / 1e3)
+            r = dict(sp, slots=slots, romix_ms=round(ms / max(k, 1), 3), launches=k, labels_per_s_k2=round(lps_k2),
+                     labels_per_s_call=round(slots * waves / (dev_ms / 1e3)), labels_per_s_wall=round(slots * waves / wall),
                      GBps=round(lps_k2 * (256 * n + 16) / 1e9, 1))
         except Exception as e:  # noqa: BLE001
             r = dict(sp, error=str(e))
