@@ -3,7 +3,8 @@
 
 Workload (BASELINE.json configs[1]): 4-SU init, scrypt N = 8192, r = p = 1, single B200, labels
 discarded ("/dev/null").  One *step* = one batch of `--batch` consecutive labels of the 2^34-label
-index space (default: 4 waves of resident scratchpads), exactly what one `initialize(start, end)`
+index space (default: 16 layers of resident scratchpads ~ 1.2 M labels; the reference's default
+ComputeBatchSize is 2^20), exactly what one `initialize(start, end)`
 call of the reference's initializer does per ComputeBatchSize batch (activation/post.go:295).
 
   value      labels/s with the output resident in HBM (b200post_labels_range_dev), device-timed
@@ -98,13 +99,27 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def best_thread_count(orc, commitment: bytes):
+    """The oracle is DRAM-latency bound (1 MiB scratchpad per thread) and the box may cap CPU time below
+    its visible core count: use the thread count that gives the highest labels/s on a short probe."""
+    avail = orc.default_threads()
+    best = (1, 0.0)
+    t = avail
+    while t >= 1:
+        probe = max(t * 16, 64)
+        rate = probe / orc.c_time_labels(commitment, N_SCRYPT, 0, probe, t)
+        if rate > best[1]:
+            best = (t, rate)
+        if t == 1:
+            break
+        t = max(t // 2, 1)
+    return best
+
+
 def cpu_baseline(orc, seconds_target: float = 12.0) -> dict:
     """Oracle port timed on all host cores on a bounded sample of the same workload."""
-    cores = orc.default_threads()
     commitment = bytes(range(32))
-    probe = max(cores * 8, 64)
-    t = orc.c_time_labels(commitment, N_SCRYPT, 0, probe, cores)
-    rate = probe / t
+    cores, rate = best_thread_count(orc, commitment)
     sample = int(max(cores * 32, min(rate * seconds_target, 1 << 20)))
     t = orc.c_time_labels(commitment, N_SCRYPT, 1 << 20, sample, cores)
     return {"value": sample / t, "unit": "labels/s", "cores": cores, "kind": "port",
@@ -117,8 +132,8 @@ def run_reference(args, rank: int, world: int) -> None:
         return
     from oracle import pyoracle as orc
     orc.build()
-    cores = orc.default_threads()
     commitment = bytes(range(32))
+    cores, _ = best_thread_count(orc, commitment)
     per_step = max(cores * 64, 256)      # bounded sample per step (~0.2 s per 64 labels per core)
     for w in range(args.warmup):
         orc.c_time_labels(commitment, N_SCRYPT, w * per_step, min(per_step, cores * 8), cores)
@@ -144,7 +159,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=0, help="labels per step per GPU (0 = 4 waves)")
+    ap.add_argument("--batch", type=int, default=0, help="labels per step per GPU (0 = 16 layers ~ 2^20, the reference's default ComputeBatchSize)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -178,7 +193,7 @@ def main() -> None:
 
     wave = b2.wave_slots(N_SCRYPT, provider=local_rank)                    # resident scratchpads per wave
     tpb = b2.get_option("tpb")
-    batch = args.batch or 4 * wave
+    batch = args.batch or 16 * wave
     d_out = torch.empty((batch, 16), dtype=torch.uint8, device=dev)        # labels stay in HBM for `value`
     h_out = np.empty((batch, 16), dtype=np.uint8)                          # host sink for `e2e`
 
@@ -186,28 +201,12 @@ def main() -> None:
         # weak scaling: every rank initialises its own contiguous slice of a (4*world)-SU space
         return rank * NUM_LABELS_4SU + step * batch
 
-    cand = torch.zeros((12,), dtype=torch.int64, device=dev)               # 48-byte VRF record + padding
-    gathered = [torch.zeros_like(cand) for _ in range(world)] if world > 1 else None
+    sharding = importlib.import_module("go-spacemesh_b200.sharding")
 
     def exchange(vrf):
-        """The path's only exchange step: min-reduction of the VRF nonce candidate over ranks."""
-        if world == 1:
-            return vrf
-        rec = np.zeros(12, dtype=np.int64)
-        if vrf is not None:
-            rec[0] = 1
-            rec[1] = np.int64(np.uint64(vrf[0]).astype(np.int64))
-            rec[2:6] = np.frombuffer(vrf[1], dtype=">u8").astype(np.uint64).view(np.int64)
-        cand.copy_(torch.from_numpy(rec), non_blocking=False)
-        dist.all_gather(gathered, cand)
-        best = None
-        for g in gathered:
-            r = g.cpu().numpy()
-            if r[0]:
-                key = (tuple(int(x) for x in r[2:6].view(np.uint64)), int(np.uint64(r[1])))
-                if best is None or key < best:
-                    best = key
-        return best
+        """The path's only exchange step: min-reduction of the VRF nonce candidate over ranks
+        (one 48-byte record per rank, NCCL all_gather + local lexicographic min)."""
+        return sharding.allgather_vrf(vrf, device=dev) if world > 1 else vrf
 
     def barrier():
         if world > 1:
@@ -294,7 +293,7 @@ def main() -> None:
                        "value_wall_clock": value_wall},
             "e2e": {"value": e2e_value, "unit": "labels/s", "h2d_bytes_per_step": 32 + 32, "d2h_bytes_per_step": batch * 16 + 48},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "romix_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "romix_pipe_kernel" if b2.get_option("romix_variant") == 4 else "romix_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_label": BYTES_PER_LABEL, "labels_per_launch": labels_per_launch,
                          "avg_launch_ms": romix_avg_ms, "launches_timed": int(romix_k),
