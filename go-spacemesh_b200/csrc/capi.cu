@@ -74,7 +74,7 @@ int b200post_set_option(const char *key, int64_t value) {
     const std::string k(key);
     if (k == "romix_variant" && value >= 0 && value <= 4) { o.romix_variant = value; return B200POST_OK; }
     if (k == "mulwide_mask" && value >= 0 && value <= 0xffff && romix_mask_supported((int)value)) { o.mulwide_mask = value; return B200POST_OK; }
-    if (k == "tpb" && (value == 64 || value == 128 || value == 256)) { o.tpb = value; return B200POST_OK; }
+    if (k == "tpb" && (value == 64 || value == 128 || value == 256 || value == 512)) { o.tpb = value; return B200POST_OK; }
     if (k == "dr_unroll" && (value == 1 || value == 4)) { o.dr_unroll = value; return B200POST_OK; }
     if (k == "ctas_per_sm" && value >= 0 && value <= 32) { o.ctas_per_sm = value; return B200POST_OK; }
     if (k == "max_scratch_mib" && value >= 0) { o.max_scratch_mib = value; return B200POST_OK; }

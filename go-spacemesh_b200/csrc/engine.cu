@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -73,7 +74,9 @@ void DeviceEngine::release() {
 // Decide the layer size for scrypt-N and make sure scratch for min(layer, want_slots) slots exists.
 int DeviceEngine::ensure(uint64_t N, uint64_t want_slots) {
     Options &o = options();
-    const int variant = (int)o.romix_variant.load(), mw = (int)o.mulwide_mask.load(), tpb = (int)o.tpb.load();
+    const int variant = (int)o.romix_variant.load(), mw = (int)o.mulwide_mask.load();
+    int tpb = (int)o.tpb.load();
+    if (variant != ROMIX_PIPELINED && tpb != 128 && tpb != 256) tpb = 128;   // the classic kernels are built for 128/256 only
     const int dr = (int)o.dr_unroll.load();
     if (!stream_) {
         CU_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
@@ -252,12 +255,32 @@ int DeviceEngine::run_job(const Job &job) {
             pp.n_fill = m < M ? round_up(nv[b], 32) : 0;
             pp.n_mix = m >= 1 ? round_up(nv[b ^ 1], 32) : 0;
             pp.fill_parity = (uint32_t)b;
+            pp.cta_trace = nullptr;
+            // diagnostics: B200POST_CTA_TRACE=<file> dumps {start ns, end ns, smid} per CTA of the last steady launch
+            static const char *trace_path = getenv("B200POST_CTA_TRACE");
+            unsigned long long *d_trace = nullptr;
+            const uint32_t n_cta = (std::max(pp.n_fill, pp.n_mix) + tpb_ - 1) / tpb_;
+            if (trace_path && m >= 1 && m + 1 == M) {
+                CU_TRY(cudaMalloc(&d_trace, (size_t)n_cta * 24));
+                CU_TRY(cudaMemsetAsync(d_trace, 0, (size_t)n_cta * 24, stream_));
+                pp.cta_trace = d_trace;
+            }
             CU_TRY(cudaEventRecord(ev_k2a_[b], stream_));
             CU_TRY(launch_romix_pipe(mw_, tpb_, dr_unroll_, pp, stream_));
             CU_TRY(cudaEventRecord(ev_k2b_[b], stream_));
             k2_pending_[b] = true;
             k2_labels_[b] = 0.5 * ((m < M ? nv[b] : 0) + (m >= 1 ? nv[b ^ 1] : 0));
             g_launches += 1;
+            if (d_trace) {
+                std::vector<unsigned long long> h((size_t)n_cta * 3);
+                CU_TRY(cudaMemcpyAsync(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost, stream_));
+                CU_TRY(cudaStreamSynchronize(stream_));
+                cudaFree(d_trace);
+                if (FILE *f = fopen(trace_path, "w")) {
+                    for (uint32_t c = 0; c < n_cta; c++) fprintf(f, "%u,%llu,%llu,%llu\n", c, h[3 * c], h[3 * c + 1], h[3 * c + 2]);
+                    fclose(f);
+                }
+            }
             if (m >= 1 && (rc_ = finish_layer(job, m - 1, nv[b ^ 1], lj[b ^ 1]))) return rc_;
         }
     }

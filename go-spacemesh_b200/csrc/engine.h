@@ -18,7 +18,7 @@ namespace b200post {
 struct Options {
     std::atomic<int64_t> romix_variant{ROMIX_PIPELINED};
     std::atomic<int64_t> mulwide_mask{0};
-    std::atomic<int64_t> tpb{128};
+    std::atomic<int64_t> tpb{512};             // pipelined default: one 16-warp CTA per SM (measured best)
     std::atomic<int64_t> dr_unroll{4};         // pipelined kernel: Salsa double-rounds unrolled (4) or rolled (1)
     std::atomic<int64_t> ctas_per_sm{0};       // 0 = occupancy maximum
     std::atomic<int64_t> max_scratch_mib{0};   // 0 = 90 % of free HBM
@@ -105,7 +105,7 @@ private:
     double romix_ms_ = 0, romix_labels_ = 0;
     uint64_t romix_launches_ = 0;
     // current tuning
-    int variant_ = ROMIX_PIPELINED, mw_ = 0, tpb_ = 128, dr_unroll_ = 4;
+    int variant_ = ROMIX_PIPELINED, mw_ = 0, tpb_ = 512, dr_unroll_ = 4;
 };
 
 // registry: lazily created engine per CUDA ordinal (nullptr + error text if the device is unusable)

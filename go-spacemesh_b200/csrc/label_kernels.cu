@@ -267,6 +267,12 @@ __global__ void __launch_bounds__(TPB) romix_pipe_kernel(const PipeParams p) {
     const uint32_t lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
     const bool do_fill = slot < p.n_fill, do_mix = slot < p.n_mix;   // multiples of 32: warp-uniform
     if (!do_fill && !do_mix) return;
+    if (p.cta_trace && threadIdx.x == 0) {
+        unsigned long long t; uint32_t sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        p.cta_trace[3 * (size_t)blockIdx.x] = t; p.cta_trace[3 * (size_t)blockIdx.x + 2] = sm;
+    }
     const uint32_t N = p.N, mask = N - 1;
     const RotConsts rc = p.rc;
     const uint32_t tile_f = smem_u32(smem_raw) + warp_in_cta * 8192, tile_m = tile_f + 4096;
@@ -346,6 +352,11 @@ __global__ void __launch_bounds__(TPB) romix_pipe_kernel(const PipeParams p) {
     if (do_mix) {
 #pragma unroll
         for (int k = 0; k < 8; k++) p.Xmix[(size_t)k * p.x_stride + slot] = ROW_CHUNK(lo_m, hi_m, k);
+    }
+    if (p.cta_trace && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.cta_trace[3 * (size_t)blockIdx.x + 1] = t;
     }
 }
 
@@ -565,12 +576,14 @@ static pipe_fn pick_pipe_tpb(int tpb, int dr_unroll) {
             case 64: return romix_pipe_kernel<MW, 64, 4>;
             case 128: return romix_pipe_kernel<MW, 128, 4>;
             case 256: return romix_pipe_kernel<MW, 256, 4>;
+            case 512: return romix_pipe_kernel<MW, 512, 4>;
         }
     } else {
         switch (tpb) {
             case 64: return romix_pipe_kernel<MW, 64, 1>;
             case 128: return romix_pipe_kernel<MW, 128, 1>;
             case 256: return romix_pipe_kernel<MW, 256, 1>;
+            case 512: return romix_pipe_kernel<MW, 512, 1>;
         }
     }
     return nullptr;

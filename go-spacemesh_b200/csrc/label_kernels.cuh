@@ -47,6 +47,7 @@ struct PipeParams {
     uint32_t N;
     uint32_t n_fill, n_mix;   // active slots of each layer (multiples of 32)
     uint32_t fill_parity;     // which of the slot's two scratchpads the filling layer owns
+    unsigned long long *cta_trace;   // diagnostics (nullptr in production): per CTA {start ns, end ns, smid}
     RotConsts rc;
 };
 

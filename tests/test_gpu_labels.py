@@ -200,7 +200,7 @@ def test_all_romix_variants_agree(b2, orc):
         ref = None
         for variant in (4, 0, 1, 2):
             for mw in (0, 0x8421, 0xFFFF):
-                for tpb in ((64, 128, 256) if variant == 4 else (128, 256)):
+                for tpb in ((64, 128, 256, 512) if variant == 4 else (128, 256)):
                     b2.set_option("romix_variant", variant); b2.set_option("mulwide_mask", mw); b2.set_option("tpb", tpb)
                     b2.set_option("dr_unroll", 1 if (mw == 0x8421 and variant == 4) else 4)
                     got, _ = b2.labels_range(c, 512, 2**35, 777)
