@@ -1,0 +1,403 @@
+// verifier.cu — batched POST proof verification (include/b200post_verify.h).
+//
+// Host side of the verify path, C++ because the reference's is compiled Go
+// (activation/post_verifier.go:122-390 offloadingPostVerifier + :150-160 postVerifier.Verify).  The GPU does
+// what is expensive and certain — recomputing every requested label with the gather kernels — and this file
+// does the cheap per-proof bookkeeping around it.  All conventions marked ASSUMED follow the published
+// post-rs v0.7.x verifier from memory and are "parity unpinned" (DESIGN.md §2).
+#include <immintrin.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/b200post_verify.h"
+#include "engine.h"
+#include "host_hash.h"
+
+namespace b200post {
+namespace {
+
+// ---------------------------------------------------------------------------------------------- AES-128
+// FIPS-197 with AES-NI (every x86-64 server CPU that hosts a B200 has it); single-block ECB encryption.
+struct Aes128 {
+    __m128i rk[11];
+    template <int RCON>
+    static __m128i expand(__m128i k) {
+        __m128i t = _mm_aeskeygenassist_si128(k, RCON);
+        t = _mm_shuffle_epi32(t, 0xff);
+        k = _mm_xor_si128(k, _mm_slli_si128(k, 4));
+        k = _mm_xor_si128(k, _mm_slli_si128(k, 4));
+        k = _mm_xor_si128(k, _mm_slli_si128(k, 4));
+        return _mm_xor_si128(k, t);
+    }
+    explicit Aes128(const uint8_t key[16]) {
+        rk[0] = _mm_loadu_si128(reinterpret_cast<const __m128i *>(key));
+        rk[1] = expand<0x01>(rk[0]); rk[2] = expand<0x02>(rk[1]); rk[3] = expand<0x04>(rk[2]);
+        rk[4] = expand<0x08>(rk[3]); rk[5] = expand<0x10>(rk[4]); rk[6] = expand<0x20>(rk[5]);
+        rk[7] = expand<0x40>(rk[6]); rk[8] = expand<0x80>(rk[7]); rk[9] = expand<0x1b>(rk[8]);
+        rk[10] = expand<0x36>(rk[9]);
+    }
+    void encrypt(const uint8_t in[16], uint8_t out[16]) const {
+        __m128i s = _mm_xor_si128(_mm_loadu_si128(reinterpret_cast<const __m128i *>(in)), rk[0]);
+        for (int r = 1; r < 10; r++) s = _mm_aesenc_si128(s, rk[r]);
+        s = _mm_aesenclast_si128(s, rk[10]);
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(out), s);
+    }
+};
+
+inline void put_le32(uint8_t *p, uint32_t v) { for (int i = 0; i < 4; i++) p[i] = (uint8_t)(v >> (8 * i)); }
+inline void put_le64(uint8_t *p, uint64_t v) { for (int i = 0; i < 8; i++) p[i] = (uint8_t)(v >> (8 * i)); }
+
+// ASSUMED (post-rs cipher.rs): key = blake3(challenge || LE32(nonce_group) || LE64(pow) [|| LE32(nonce)])[0:16]
+void cipher_key(const uint8_t challenge[32], uint32_t nonce_group, uint64_t pow, const uint32_t *nonce, uint8_t key[16]) {
+    uint8_t buf[48];
+    memcpy(buf, challenge, 32);
+    put_le32(buf + 32, nonce_group);
+    put_le64(buf + 36, pow);
+    size_t len = 44;
+    if (nonce) { put_le32(buf + 44, *nonce); len = 48; }
+    blake3_single_chunk(buf, len, key, 16);
+}
+
+// ASSUMED (post-rs random_values_gen.rs): BLAKE3-XOF driven partial Fisher-Yates over the K2 positions.
+struct Blake3Rng {
+    std::vector<uint8_t> seed;
+    std::vector<uint8_t> buf;
+    size_t pos = 0;
+    bool ok = true;
+    explicit Blake3Rng(std::vector<uint8_t> s) : seed(std::move(s)) { refill(256); }
+    void refill(size_t n) {
+        buf.resize(n);
+        ok = blake3_single_chunk(seed.data(), seed.size(), buf.data(), n);
+    }
+    uint16_t next_u16() {
+        if (pos + 2 > buf.size()) refill(buf.size() * 2);   // XOF output is a prefix-stable stream
+        const uint16_t v = (uint16_t)(buf[pos] | (buf[pos + 1] << 8));
+        pos += 2;
+        return v;
+    }
+};
+
+// 256-bit big-endian value / 32-bit divisor (scale_pow_difficulty: difficulty / num_units) — ASSUMED
+void div256_u32(const uint8_t in[32], uint32_t d, uint8_t out[32]) {
+    uint64_t rem = 0;
+    for (int i = 0; i < 32; i++) {
+        const uint64_t cur = (rem << 8) | in[i];
+        out[i] = (uint8_t)(cur / d);
+        rem = cur % d;
+    }
+}
+
+struct Job {
+    const b200post_proof *proof;
+    const b200post_proof_metadata *meta;
+    const b200post_verify_params *params;
+    b200post_verify_options opt;
+    int status = B200POST_OK;
+    uint64_t bad_index = 0;
+    bool done = false;
+    // filled by prepare()
+    std::vector<uint64_t> check;   // label indices to recompute, in verification order
+    uint8_t commitment[32];
+    uint8_t key[16], lazy_key[16];
+    uint8_t diff_msb = 0;
+    uint64_t diff_lsb = 0;
+    uint32_t out_byte = 0;
+    size_t first_item = 0;
+};
+
+}  // namespace
+}  // namespace b200post
+
+using namespace b200post;
+
+extern "C" {
+
+uint32_t b200post_bits_per_index(uint64_t num_labels) {
+    // ASSUMED: floor(log2(n)) + 1  (post-rs compression::required_bits / Go shared.BinaryRepresentationMinBits)
+    return num_labels == 0 ? 0 : 64 - (uint32_t)__builtin_clzll(num_labels);
+}
+
+uint64_t b200post_proving_difficulty(uint32_t k1, uint64_t num_labels) {
+    // ASSUMED: floor(2^64 * k1 / num_labels), saturating
+    if (num_labels == 0) return 0;
+    const unsigned __int128 v = ((unsigned __int128)k1 << 64) / num_labels;
+    return v > (unsigned __int128)~0ull ? ~0ull : (uint64_t)v;
+}
+
+size_t b200post_pack_indices(const uint64_t *indices, size_t count, uint32_t bits, uint8_t *out, size_t out_cap) {
+    const size_t need = (count * (size_t)bits + 7) / 8;
+    if (!out || out_cap < need || bits == 0 || bits > 64) return 0;
+    memset(out, 0, need);
+    size_t bitpos = 0;
+    for (size_t i = 0; i < count; i++)
+        for (uint32_t j = 0; j < bits; j++, bitpos++)
+            if ((indices[i] >> j) & 1) out[bitpos >> 3] |= (uint8_t)(1u << (bitpos & 7));
+    return need;
+}
+
+size_t b200post_unpack_indices(const uint8_t *packed, size_t packed_len, uint32_t bits, uint64_t *out, size_t out_cap) {
+    if (!packed || !out || bits == 0 || bits > 64) return 0;
+    const size_t n = std::min(out_cap, packed_len * 8 / bits);
+    size_t bitpos = 0;
+    for (size_t i = 0; i < n; i++) {
+        uint64_t v = 0;
+        for (uint32_t j = 0; j < bits; j++, bitpos++) v |= (uint64_t)((packed[bitpos >> 3] >> (bitpos & 7)) & 1) << j;
+        out[i] = v;
+    }
+    return n;
+}
+
+}  // extern "C"
+
+namespace b200post {
+namespace {
+
+// Per-proof checks that need no labels; fills job.check with the label indices to recompute.
+void prepare(Job &j, const b200post_verifier_opts &vo) {
+    const b200post_proof &p = *j.proof;
+    const b200post_proof_metadata &m = *j.meta;
+    const b200post_verify_params &q = *j.params;
+    j.status = B200POST_OK;
+    if (!p.indices || p.indices_len == 0) { j.status = B200POST_ERR_EMPTY_PROOF; return; }   // "proof indices are empty"
+    const unsigned __int128 nl = (unsigned __int128)m.num_units * m.labels_per_unit;
+    if (nl == 0 || nl > ~0ull || q.k2 == 0 || q.k1 == 0 || m.num_units == 0) { j.status = B200POST_ERR_INVALID_ARGUMENT; return; }
+    const uint64_t num_labels = (uint64_t)nl;
+    const uint32_t bits = b200post_bits_per_index(num_labels);
+    const size_t expect_len = ((size_t)q.k2 * bits + 7) / 8;
+    if (p.indices_len != expect_len) { j.status = B200POST_ERR_INVALID_ARGUMENT; return; }   // wrong number of indices
+    const uint32_t nonce_group = p.nonce / 16;
+    if (vo.pow_verify) {
+        if (nonce_group > 255) { j.status = B200POST_ERR_INVALID_ARGUMENT; return; }
+        uint8_t scaled[32];
+        div256_u32(q.pow_difficulty, m.num_units, scaled);
+        if (vo.pow_verify(vo.pow_ctx, p.pow, (uint8_t)nonce_group, m.challenge, scaled, m.node_id) != 0) {
+            j.status = B200POST_ERR_INVALID_PROOF;
+            j.bad_index = ~0ull;   // the pow, not a label, is invalid
+            return;
+        }
+    }
+    std::vector<uint64_t> all(q.k2);
+    if (b200post_unpack_indices(p.indices, p.indices_len, bits, all.data(), all.size()) != q.k2) { j.status = B200POST_ERR_INVALID_ARGUMENT; return; }
+    switch (j.opt.mode) {
+        case B200POST_VERIFY_ALL: j.check = std::move(all); break;
+        case B200POST_VERIFY_SELECTED_INDEX:
+            if (j.opt.selected_index >= q.k2) { j.status = B200POST_ERR_INVALID_ARGUMENT; return; }
+            j.check.assign(1, all[j.opt.selected_index]);
+            break;
+        case B200POST_VERIFY_SUBSET: {
+            const uint32_t k3 = std::min(j.opt.k3, q.k2);
+            if (k3 == 0) { j.status = B200POST_ERR_INVALID_ARGUMENT; return; }
+            // seed = caller seed || LE32(nonce) || indices || LE64(pow)   — ASSUMED
+            std::vector<uint8_t> seed;
+            if (j.opt.seed && j.opt.seed_len) seed.assign(j.opt.seed, j.opt.seed + j.opt.seed_len);
+            uint8_t tmp[8];
+            put_le32(tmp, p.nonce); seed.insert(seed.end(), tmp, tmp + 4);
+            seed.insert(seed.end(), p.indices, p.indices + p.indices_len);
+            put_le64(tmp, p.pow); seed.insert(seed.end(), tmp, tmp + 8);
+            if (seed.size() > 1024) { j.status = B200POST_ERR_INVALID_ARGUMENT; return; }
+            Blake3Rng rng(std::move(seed));
+            size_t idx = 0;
+            while (j.check.size() < k3 && idx < all.size()) {
+                const uint16_t remaining = (uint16_t)(all.size() - idx);
+                const uint16_t max_allowed = (uint16_t)(0xffffu - 0xffffu % remaining);
+                uint16_t r;
+                do { r = rng.next_u16(); } while (r >= max_allowed && rng.ok);
+                if (!rng.ok) { j.status = B200POST_ERR_INVALID_ARGUMENT; return; }
+                std::swap(all[idx], all[idx + r % remaining]);
+                j.check.push_back(all[idx++]);
+            }
+            break;
+        }
+        default: j.status = B200POST_ERR_INVALID_ARGUMENT; return;
+    }
+    for (uint64_t v : j.check)
+        if (v >= num_labels && false) { /* post-rs does not range-check: the label is simply recomputed */ }
+    commitment_bytes(m.node_id, m.commitment_atx_id, j.commitment);
+    cipher_key(m.challenge, nonce_group, p.pow, nullptr, j.key);
+    cipher_key(m.challenge, nonce_group, p.pow, &p.nonce, j.lazy_key);
+    const uint64_t diff = b200post_proving_difficulty(q.k1, num_labels);
+    j.diff_msb = (uint8_t)(diff >> 56);
+    j.diff_lsb = diff & 0x00ffffffffffffffull;
+    j.out_byte = p.nonce % 16;
+}
+
+// Label-dependent verdict for one proof (ASSUMED post-rs 8/56 split compare).
+void judge(Job &j, const uint8_t *labels16) {
+    const Aes128 aes(j.key);
+    for (size_t k = 0; k < j.check.size(); k++) {
+        uint8_t out[16];
+        aes.encrypt(labels16 + 16 * k, out);
+        const uint8_t msb = out[j.out_byte];
+        if (msb < j.diff_msb) continue;
+        if (msb > j.diff_msb) { j.status = B200POST_ERR_INVALID_PROOF; j.bad_index = j.check[k]; return; }
+        const Aes128 lazy(j.lazy_key);
+        lazy.encrypt(labels16 + 16 * k, out);
+        uint64_t lsb = 0;
+        for (int b = 0; b < 8; b++) lsb |= (uint64_t)out[b] << (8 * b);
+        lsb &= 0x00ffffffffffffffull;
+        if (lsb >= j.diff_lsb) { j.status = B200POST_ERR_INVALID_PROOF; j.bad_index = j.check[k]; return; }
+    }
+}
+
+// One GPU batch: jobs may use different scrypt N; group by N (in practice a single value).
+int process(uint32_t provider, std::vector<Job *> &jobs, const b200post_verifier_opts &vo) {
+    for (Job *j : jobs) prepare(*j, vo);
+    std::vector<uint64_t> ns;
+    for (Job *j : jobs)
+        if (j->status == B200POST_OK && std::find(ns.begin(), ns.end(), j->params->scrypt_n) == ns.end()) ns.push_back(j->params->scrypt_n);
+    for (uint64_t n : ns) {
+        std::vector<uint8_t> commitments;
+        std::vector<uint64_t> indices;
+        for (Job *j : jobs) {
+            if (j->status != B200POST_OK || j->params->scrypt_n != n) continue;
+            j->first_item = indices.size();
+            for (uint64_t idx : j->check) {
+                commitments.insert(commitments.end(), j->commitment, j->commitment + 32);
+                indices.push_back(idx);
+            }
+        }
+        std::vector<uint8_t> labels(indices.size() * 16);
+        int rc = B200POST_ERR_INVALID_ARGUMENT;
+        if (n >= 2 && n <= (1ull << 20) && (n & (n - 1)) == 0) {
+            DeviceEngine *e = engine_for(provider);
+            rc = e ? e->labels_gather(indices.size(), commitments.data(), indices.data(), n, labels.data()) : B200POST_ERR_NO_DEVICE;
+        }
+        for (Job *j : jobs) {
+            if (j->status != B200POST_OK || j->params->scrypt_n != n) continue;
+            if (rc != B200POST_OK) j->status = rc; else judge(*j, labels.data() + 16 * j->first_item);
+        }
+    }
+    return B200POST_OK;
+}
+
+}  // namespace
+}  // namespace b200post
+
+struct b200post_verifier {
+    uint32_t provider = 0;
+    b200post_verifier_opts opts{};
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::deque<Job *> prioritized, normal;
+    bool closed = false;
+    uint64_t batches = 0, proofs = 0;
+    std::thread worker;
+
+    void run() {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv_work.wait(lk, [&] { return closed || !prioritized.empty() || !normal.empty(); });
+            if (closed) {
+                for (auto *q : {&prioritized, &normal}) {
+                    for (Job *j : *q) { j->status = B200POST_ERR_CLOSED; j->done = true; }
+                    q->clear();
+                }
+                cv_done.notify_all();
+                return;
+            }
+            // drain everything queued (prioritised first): while the GPU works on this batch the next one fills
+            std::vector<Job *> batch;
+            const size_t cap = opts.max_batch_proofs ? opts.max_batch_proofs : 16384;
+            while (batch.size() < cap && !prioritized.empty()) { batch.push_back(prioritized.front()); prioritized.pop_front(); }
+            while (batch.size() < cap && !normal.empty()) { batch.push_back(normal.front()); normal.pop_front(); }
+            lk.unlock();
+            process(provider, batch, opts);
+            lk.lock();
+            batches++; proofs += batch.size();
+            for (Job *j : batch) j->done = true;
+            cv_done.notify_all();
+        }
+    }
+};
+
+extern "C" {
+
+int b200post_verifier_new(uint32_t provider, const b200post_verifier_opts *opts, b200post_verifier **out) {
+    if (!out) { set_error("invalid argument"); return B200POST_ERR_INVALID_ARGUMENT; }
+    *out = nullptr;
+    if (!engine_for(provider)) return provider == B200POST_CPU_PROVIDER_ID ? B200POST_ERR_UNSUPPORTED : B200POST_ERR_NO_DEVICE;
+    b200post_verifier *v = new b200post_verifier;
+    v->provider = provider;
+    if (opts) v->opts = *opts;
+    v->worker = std::thread([v] { v->run(); });
+    *out = v;
+    return B200POST_OK;
+}
+
+int b200post_verifier_verify(b200post_verifier *v, const b200post_proof *proof, const b200post_proof_metadata *meta,
+                             const b200post_verify_params *params, const b200post_verify_options *options,
+                             uint64_t *invalid_index) {
+    if (!v || !proof || !meta || !params) { set_error("invalid argument"); return B200POST_ERR_INVALID_ARGUMENT; }
+    Job j;
+    j.proof = proof; j.meta = meta; j.params = params;
+    if (options) j.opt = *options; else memset(&j.opt, 0, sizeof j.opt);
+    {
+        std::unique_lock<std::mutex> lk(v->mu);
+        if (v->closed) { set_error("verifier is closed"); return B200POST_ERR_CLOSED; }
+        (j.opt.prioritized ? v->prioritized : v->normal).push_back(&j);
+        v->cv_work.notify_one();
+        v->cv_done.wait(lk, [&] { return j.done; });
+    }
+    if (j.status == B200POST_ERR_CLOSED) set_error("verifier is closed");
+    else if (j.status == B200POST_ERR_EMPTY_PROOF) set_error("proof indices are empty");
+    else if (j.status == B200POST_ERR_INVALID_PROOF) set_error(j.bad_index == ~0ull ? "invalid k2pow" : "invalid index");
+    else if (j.status == B200POST_ERR_INVALID_ARGUMENT) set_error("malformed proof, metadata or options");
+    if (invalid_index) *invalid_index = j.bad_index;
+    return j.status;
+}
+
+int b200post_verifier_close(b200post_verifier *v) {
+    if (!v) return B200POST_ERR_INVALID_ARGUMENT;
+    {
+        std::lock_guard<std::mutex> lk(v->mu);
+        if (v->closed) return B200POST_OK;
+        v->closed = true;
+    }
+    v->cv_work.notify_all();
+    if (v->worker.joinable()) v->worker.join();
+    return B200POST_OK;
+}
+
+void b200post_verifier_free(b200post_verifier *v) {
+    if (!v) return;
+    b200post_verifier_close(v);
+    delete v;
+}
+
+int b200post_verifier_stats(b200post_verifier *v, uint64_t *batches, uint64_t *proofs) {
+    if (!v) return B200POST_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(v->mu);
+    if (batches) *batches = v->batches;
+    if (proofs) *proofs = v->proofs;
+    return B200POST_OK;
+}
+
+int b200post_verify_batch(uint32_t provider, size_t n, const b200post_proof *proofs, const b200post_proof_metadata *metas,
+                          const b200post_verify_params *params, const b200post_verify_options *options,
+                          const b200post_verifier_opts *opts, int *statuses, uint64_t *invalid_indices) {
+    if (n && (!proofs || !metas || !params || !statuses)) { set_error("invalid argument"); return B200POST_ERR_INVALID_ARGUMENT; }
+    if (!engine_for(provider)) return provider == B200POST_CPU_PROVIDER_ID ? B200POST_ERR_UNSUPPORTED : B200POST_ERR_NO_DEVICE;
+    b200post_verifier_opts vo{};
+    if (opts) vo = *opts;
+    std::vector<Job> jobs(n);
+    std::vector<Job *> ptrs(n);
+    for (size_t i = 0; i < n; i++) {
+        jobs[i].proof = &proofs[i]; jobs[i].meta = &metas[i]; jobs[i].params = params;
+        if (options) jobs[i].opt = options[i]; else memset(&jobs[i].opt, 0, sizeof jobs[i].opt);
+        ptrs[i] = &jobs[i];
+    }
+    process(provider, ptrs, vo);
+    for (size_t i = 0; i < n; i++) {
+        statuses[i] = jobs[i].status;
+        if (invalid_indices) invalid_indices[i] = jobs[i].bad_index;
+    }
+    return B200POST_OK;
+}
+
+}  // extern "C"

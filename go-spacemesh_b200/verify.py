@@ -1,0 +1,223 @@
+"""PostVerifier over libb200post.so — host-side mirror of activation.PostVerifier
+(activation/interface.go:26-29, activation/post_verifier.go) for tests and bench.py.
+
+`Verify` is blocking and safe for concurrent use; concurrent calls are coalesced into one GPU batch by the
+library's dispatcher.  Errors keep the reference's meaning: `ErrInvalidIndex` (verifying.ErrInvalidIndex,
+activation/handler_v1.go:228), "verifier is closed" (post_verifier_test.go:61), "proof indices are empty"
+(e2e/validation_test.go:102).  Conventions outside label recomputation are ASSUMED (include/b200post_verify.h).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+
+from . import B200PostError, ERR_CLOSED, ERR_EMPTY_PROOF, ERR_INVALID_PROOF, OK, lib
+
+MODE_ALL, MODE_SUBSET, MODE_SELECTED_INDEX = 0, 1, 2
+
+
+class _Proof(ctypes.Structure):
+    _fields_ = [("nonce", ctypes.c_uint32), ("indices", ctypes.c_char_p), ("indices_len", ctypes.c_size_t),
+                ("pow", ctypes.c_uint64)]
+
+
+class _Meta(ctypes.Structure):
+    _fields_ = [("node_id", ctypes.c_uint8 * 32), ("commitment_atx_id", ctypes.c_uint8 * 32),
+                ("challenge", ctypes.c_uint8 * 32), ("num_units", ctypes.c_uint32), ("labels_per_unit", ctypes.c_uint64)]
+
+
+class _Params(ctypes.Structure):
+    _fields_ = [("k1", ctypes.c_uint32), ("k2", ctypes.c_uint32), ("pow_difficulty", ctypes.c_uint8 * 32),
+                ("scrypt_n", ctypes.c_uint64)]
+
+
+class _Options(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_uint32), ("k3", ctypes.c_uint32), ("seed", ctypes.c_char_p),
+                ("seed_len", ctypes.c_size_t), ("selected_index", ctypes.c_uint32), ("prioritized", ctypes.c_uint32)]
+
+
+POW_VERIFY_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint8,
+                                 ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_uint8),
+                                 ctypes.POINTER(ctypes.c_uint8))
+
+
+class _VerifierOpts(ctypes.Structure):
+    _fields_ = [("pow_verify", POW_VERIFY_FN), ("pow_ctx", ctypes.c_void_p), ("max_batch_proofs", ctypes.c_uint32)]
+
+
+class ErrInvalidIndex(Exception):
+    """verifying.ErrInvalidIndex{Index}."""
+    def __init__(self, index: int):
+        super().__init__(f"invalid index: {index}")
+        self.index = index
+
+
+class ErrVerifierClosed(Exception):
+    def __init__(self):
+        super().__init__("verifier is closed")
+
+
+class ErrEmptyProof(Exception):
+    def __init__(self):
+        super().__init__("proof indices are empty")
+
+
+@dataclass
+class Proof:                 # shared.Proof
+    nonce: int
+    indices: bytes
+    pow: int = 0
+
+
+@dataclass
+class ProofMetadata:         # shared.ProofMetadata (activation/validation.go:193-199)
+    node_id: bytes
+    commitment_atx_id: bytes
+    challenge: bytes
+    num_units: int
+    labels_per_unit: int
+
+
+@dataclass
+class VerifyParams:          # PostConfig.ToConfig() + Scrypt (activation/post.go:40-49,59)
+    k1: int
+    k2: int
+    scrypt_n: int = 8192
+    pow_difficulty: bytes = field(default_factory=lambda: b"\xff" * 32)
+
+
+def _bind():
+    L = lib()
+    if getattr(L, "_verify_bound", False):
+        return L
+    vp = ctypes.c_void_p
+    L.b200post_verifier_new.argtypes = [ctypes.c_uint32, ctypes.POINTER(_VerifierOpts), ctypes.POINTER(vp)]
+    L.b200post_verifier_verify.argtypes = [vp, ctypes.POINTER(_Proof), ctypes.POINTER(_Meta), ctypes.POINTER(_Params),
+                                           ctypes.POINTER(_Options), ctypes.POINTER(ctypes.c_uint64)]
+    L.b200post_verifier_close.argtypes = [vp]
+    L.b200post_verifier_free.argtypes = [vp]
+    L.b200post_verifier_free.restype = None
+    L.b200post_verifier_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+    L.b200post_verify_batch.argtypes = [ctypes.c_uint32, ctypes.c_size_t, ctypes.POINTER(_Proof), ctypes.POINTER(_Meta),
+                                        ctypes.POINTER(_Params), ctypes.POINTER(_Options), ctypes.POINTER(_VerifierOpts),
+                                        ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_uint64)]
+    L.b200post_bits_per_index.argtypes = [ctypes.c_uint64]
+    L.b200post_bits_per_index.restype = ctypes.c_uint32
+    L.b200post_proving_difficulty.argtypes = [ctypes.c_uint32, ctypes.c_uint64]
+    L.b200post_proving_difficulty.restype = ctypes.c_uint64
+    L.b200post_pack_indices.argtypes = [ctypes.POINTER(ctypes.c_uint64), ctypes.c_size_t, ctypes.c_uint32, vp, ctypes.c_size_t]
+    L.b200post_pack_indices.restype = ctypes.c_size_t
+    L.b200post_unpack_indices.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint64), ctypes.c_size_t]
+    L.b200post_unpack_indices.restype = ctypes.c_size_t
+    L._verify_bound = True
+    return L
+
+
+def bits_per_index(num_labels: int) -> int:
+    return int(_bind().b200post_bits_per_index(num_labels))
+
+
+def proving_difficulty(k1: int, num_labels: int) -> int:
+    return int(_bind().b200post_proving_difficulty(k1, num_labels))
+
+
+def pack_indices(indices, bits: int) -> bytes:
+    arr = (ctypes.c_uint64 * len(indices))(*[int(v) for v in indices])
+    out = ctypes.create_string_buffer((len(indices) * bits + 7) // 8 or 1)
+    n = _bind().b200post_pack_indices(arr, len(indices), bits, out, len(out))
+    return out.raw[:n]
+
+
+def unpack_indices(packed: bytes, bits: int, count: int) -> list[int]:
+    arr = (ctypes.c_uint64 * max(count, 1))()
+    n = _bind().b200post_unpack_indices(packed, len(packed), bits, arr, count)
+    return [int(v) for v in arr[:n]]
+
+
+def _c_proof(p: Proof) -> _Proof:
+    return _Proof(p.nonce, p.indices if p.indices else None, len(p.indices), p.pow)
+
+
+def _c_meta(m: ProofMetadata) -> _Meta:
+    c = _Meta()
+    ctypes.memmove(c.node_id, m.node_id, 32)
+    ctypes.memmove(c.commitment_atx_id, m.commitment_atx_id, 32)
+    ctypes.memmove(c.challenge, m.challenge, 32)
+    c.num_units, c.labels_per_unit = m.num_units, m.labels_per_unit
+    return c
+
+
+def _c_params(q: VerifyParams) -> _Params:
+    c = _Params(k1=q.k1, k2=q.k2, scrypt_n=q.scrypt_n)
+    ctypes.memmove(c.pow_difficulty, q.pow_difficulty, 32)
+    return c
+
+
+def _c_options(mode=MODE_ALL, k3=0, seed=b"", selected_index=0, prioritized=False) -> _Options:
+    return _Options(mode, k3, seed if seed else None, len(seed), selected_index, int(prioritized))
+
+
+def _raise(rc: int, bad: int):
+    if rc == OK:
+        return
+    if rc == ERR_INVALID_PROOF:
+        raise ErrInvalidIndex(bad)
+    if rc == ERR_CLOSED:
+        raise ErrVerifierClosed()
+    if rc == ERR_EMPTY_PROOF:
+        raise ErrEmptyProof()
+    raise B200PostError(rc, lib().b200post_last_error().decode(errors="replace"))
+
+
+class PostVerifier:
+    """activation.PostVerifier: Verify(ctx, proof, metadata, opts...) error; Close() error."""
+
+    def __init__(self, provider: int = 0, pow_verify=None, max_batch_proofs: int = 0):
+        L = _bind()
+        self._cb = POW_VERIFY_FN(pow_verify) if pow_verify else ctypes.cast(None, POW_VERIFY_FN)
+        opts = _VerifierOpts(self._cb, None, max_batch_proofs)
+        self._h = ctypes.c_void_p()
+        rc = L.b200post_verifier_new(provider, ctypes.byref(opts), ctypes.byref(self._h))
+        if rc != OK:
+            raise B200PostError(rc, L.b200post_last_error().decode(errors="replace"))
+
+    def verify(self, proof: Proof, meta: ProofMetadata, params: VerifyParams, *, mode=MODE_ALL, k3=0, seed=b"",
+               selected_index=0, prioritized=False) -> None:
+        cp, cm, cq = _c_proof(proof), _c_meta(meta), _c_params(params)
+        co = _c_options(mode, k3, seed, selected_index, prioritized)
+        bad = ctypes.c_uint64(0)
+        rc = _bind().b200post_verifier_verify(self._h, ctypes.byref(cp), ctypes.byref(cm), ctypes.byref(cq),
+                                              ctypes.byref(co), ctypes.byref(bad))
+        _raise(rc, bad.value)
+
+    def stats(self) -> tuple[int, int]:
+        b, p = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        _bind().b200post_verifier_stats(self._h, ctypes.byref(b), ctypes.byref(p))
+        return int(b.value), int(p.value)
+
+    def close(self) -> None:
+        _bind().b200post_verifier_close(self._h)
+
+    def __del__(self):
+        try:
+            if self._h:
+                _bind().b200post_verifier_free(self._h)
+                self._h = None
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def verify_batch(proofs: list[Proof], metas: list[ProofMetadata], params: VerifyParams, *, provider: int = 0,
+                 options: list[dict] | None = None):
+    """One synchronous GPU batch (BASELINE.json configs[2]).  Returns (statuses, invalid_indices)."""
+    n = len(proofs)
+    cps = (_Proof * max(n, 1))(*[_c_proof(p) for p in proofs])
+    cms = (_Meta * max(n, 1))(*[_c_meta(m) for m in metas])
+    cq = _c_params(params)
+    cos = (_Options * n)(*[_c_options(**o) for o in options]) if options else None
+    st = (ctypes.c_int * max(n, 1))()
+    bad = (ctypes.c_uint64 * max(n, 1))()
+    rc = _bind().b200post_verify_batch(provider, n, cps, cms, ctypes.byref(cq), cos, None, st, bad)
+    if rc != OK:
+        raise B200PostError(rc, lib().b200post_last_error().decode(errors="replace"))
+    return list(st[:n]), list(bad[:n])

@@ -197,3 +197,109 @@ def c_labels_gather(commitments: np.ndarray, indices: np.ndarray, n: int, thread
 def c_time_labels(commitment: bytes, n: int, start: int, count: int, threads: int) -> float:
     out = np.empty((count, 16), dtype=np.uint8)
     return float(lib().oracle_time_labels(commitment, n, start, count, threads, out.ctypes.data))
+
+
+# ----------------------------------------------------------------------------- verify-path restatement
+# Python restatement of the post-rs v0.7.x proof verifier (ASSUMED conventions, "parity unpinned"): used by
+# the tests as the checker of go-spacemesh_b200's batched verifier, and to build synthetic valid proofs.
+def py_bits_per_index(num_labels: int) -> int:
+    return 0 if num_labels == 0 else int(num_labels).bit_length()          # floor(log2(n)) + 1
+
+
+def py_proving_difficulty(k1: int, num_labels: int) -> int:
+    return min((k1 << 64) // num_labels, (1 << 64) - 1)
+
+
+def py_pack_indices(indices, bits: int) -> bytes:
+    acc = 0
+    for i, v in enumerate(indices):
+        acc |= (int(v) & ((1 << bits) - 1)) << (i * bits)
+    return acc.to_bytes((len(indices) * bits + 7) // 8, "little")
+
+
+def py_unpack_indices(packed: bytes, bits: int, count: int):
+    acc = int.from_bytes(packed, "little")
+    return [(acc >> (i * bits)) & ((1 << bits) - 1) for i in range(count)]
+
+
+def py_cipher_key(challenge: bytes, nonce_group: int, pow_: int, nonce: int | None = None) -> bytes:
+    import blake3
+    msg = challenge + nonce_group.to_bytes(4, "little") + pow_.to_bytes(8, "little")
+    if nonce is not None:
+        msg += nonce.to_bytes(4, "little")
+    return blake3.blake3(msg).digest()[:16]
+
+
+def py_aes128(key: bytes, block: bytes) -> bytes:
+    from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
+    return Cipher(algorithms.AES(key), modes.ECB()).encryptor().update(block)
+
+
+def py_label_passes(label16: bytes, challenge: bytes, nonce: int, pow_: int, difficulty: int) -> bool:
+    ng = nonce // 16
+    out = py_aes128(py_cipher_key(challenge, ng, pow_), label16)
+    msb, dmsb = out[nonce % 16], difficulty >> 56
+    if msb != dmsb:
+        return msb < dmsb
+    out = py_aes128(py_cipher_key(challenge, ng, pow_, nonce), label16)
+    return (int.from_bytes(out[:8], "little") & ((1 << 56) - 1)) < (difficulty & ((1 << 56) - 1))
+
+
+def py_subset_positions(values, seed: bytes, nonce: int, packed: bytes, pow_: int, k3: int):
+    """RandomValuesIterator: BLAKE3-XOF driven partial Fisher-Yates; returns the first k3 selected values."""
+    import blake3
+    stream = blake3.blake3(seed + nonce.to_bytes(4, "little") + packed + pow_.to_bytes(8, "little")).digest(8192)
+    vals, pos, out, idx = list(values), 0, [], 0
+    while len(out) < min(k3, len(vals)):
+        remaining = len(vals) - idx
+        max_allowed = 0xFFFF - 0xFFFF % remaining
+        while True:
+            r = int.from_bytes(stream[pos:pos + 2], "little")
+            pos += 2
+            if r < max_allowed:
+                break
+        vals[idx], vals[idx + r % remaining] = vals[idx + r % remaining], vals[idx]
+        out.append(vals[idx])
+        idx += 1
+    return out
+
+
+def py_verify(nonce: int, packed: bytes, pow_: int, node_id: bytes, atx: bytes, challenge: bytes, num_units: int,
+              labels_per_unit: int, k1: int, k2: int, n: int, mode: str = "all", k3: int = 0, seed: bytes = b"",
+              selected: int = 0):
+    """Returns (ok, failing_label_index or None).  Labels come from the C oracle."""
+    if not packed:
+        raise ValueError("proof indices are empty")
+    num_labels = num_units * labels_per_unit
+    bits = py_bits_per_index(num_labels)
+    if len(packed) != (k2 * bits + 7) // 8:
+        raise ValueError("wrong indices length")
+    idx = py_unpack_indices(packed, bits, k2)
+    if mode == "subset":
+        idx = py_subset_positions(idx, seed, nonce, packed, pow_, k3)
+    elif mode == "selected":
+        idx = [idx[selected]]
+    c = py_commitment(node_id, atx)
+    comms = np.tile(np.frombuffer(c, dtype=np.uint8), (len(idx), 1))
+    labels = c_labels_gather(comms, np.array(idx, dtype=np.uint64), n, threads=4)
+    diff = py_proving_difficulty(k1, num_labels)
+    for i, lab in zip(idx, labels):
+        if not py_label_passes(lab.tobytes(), challenge, nonce, pow_, diff):
+            return False, i
+    return True, None
+
+
+def py_prove(node_id: bytes, atx: bytes, challenge: bytes, num_units: int, labels_per_unit: int, k1: int, k2: int,
+             n: int, nonce: int = 0, pow_: int = 0):
+    """Scan all labels (small spaces only) and return the packed first-K2 passing indices, or None."""
+    num_labels = num_units * labels_per_unit
+    c = py_commitment(node_id, atx)
+    labels, _, _, _ = c_labels_range(c, n, 0, num_labels, threads=4)
+    diff = py_proving_difficulty(k1, num_labels)
+    hits = []
+    for i in range(num_labels):
+        if py_label_passes(labels[i].tobytes(), challenge, nonce, pow_, diff):
+            hits.append(i)
+            if len(hits) == k2:
+                return py_pack_indices(hits, py_bits_per_index(num_labels)), hits
+    return None, hits

@@ -36,6 +36,7 @@ def test_library_exports_every_declared_symbol(b2):
         if not p.exists():
             continue
         text = re.sub(r"/\*.*?\*/", "", p.read_text(), flags=re.S)
+        text = re.sub(r"typedef[^;{]*\(\s*\*[^;]*;", "", text)        # function-pointer typedefs are not symbols
         declared |= set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", text))
     declared -= {"defined"}
     assert {"b200post_labels_range", "b200post_labels_gather", "initialize", "new_initializer"} <= declared
@@ -89,3 +90,32 @@ def test_product_does_not_reference_the_oracle():
             continue
         text = p.read_text()
         assert "post_oracle" not in text and "pyoracle" not in text and "from oracle" not in text, p
+
+
+def test_verify_helpers_match_oracle(b2, orc):
+    """Index packing / difficulty helpers of the verify path (pure host code) against the Python restatement."""
+    import importlib
+    vf = importlib.import_module("go-spacemesh_b200.verify")
+    rng = np.random.default_rng(23)
+    for n in (1, 2, 3, 1000, 1024, 2**34, 2**34 + 1, 2**64 - 1):
+        assert vf.bits_per_index(n) == orc.py_bits_per_index(n)
+        for k1 in (1, 26, 2**31):
+            assert vf.proving_difficulty(k1, n) == orc.py_proving_difficulty(k1, n)
+    assert vf.bits_per_index(0) == 0
+    for bits in (1, 7, 8, 11, 34, 35, 63, 64):
+        idx = [int(x) for x in rng.integers(0, 2**min(bits, 63), 37)]
+        packed = vf.pack_indices(idx, bits)
+        assert packed == orc.py_pack_indices(idx, bits)
+        assert vf.unpack_indices(packed, bits, 37) == idx
+    # wire cap: 37 x 35-bit indices of a 4-SU space fit the 800-byte Indices cap (activation/wire/wire_v1.go:43)
+    assert len(vf.pack_indices([0] * 37, vf.bits_per_index(2**34))) == 162
+
+
+def test_verifier_needs_a_device(b2):
+    import importlib
+    vf = importlib.import_module("go-spacemesh_b200.verify")
+    if b2.providers():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(b2.B200PostError) as e:
+        vf.PostVerifier()
+    assert e.value.code == b2.ERR_NO_DEVICE
