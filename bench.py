@@ -126,6 +126,35 @@ def cpu_baseline(orc, seconds_target: float = 12.0) -> dict:
             "sample": f"{sample} labels of the N=8192 init (oracle/post_oracle.c, {cores} pthreads, {t:.1f} s)"}
 
 
+def bench_verify(b2, provider: int, n_proofs: int = 10000, k2: int = 37) -> dict:
+    """BASELINE.json configs[2]: PostVerifier batch, 10 000 proofs x K2 = 37 indices, N = 8192, one B200.
+    Synthetic proofs (seed 3): distinct identities, indices uniform in a 4-SU space (so verdicts are mostly
+    "invalid"); every requested label is recomputed on the GPU regardless of the verdict.  Timed end to end through b200post_verify_batch with host
+    buffers: index unpack + key derivation (host), H2D, gather kernels, D2H, AES compare (host)."""
+    import numpy as np
+    vf = importlib.import_module("go-spacemesh_b200.verify")
+    rng = np.random.default_rng(3)
+    num_labels = NUM_LABELS_4SU
+    bits = vf.bits_per_index(num_labels)
+    ids = rng.integers(0, 256, (n_proofs, 96), dtype=np.uint8)
+    idx = rng.integers(0, num_labels, (n_proofs, k2), dtype=np.uint64)
+    proofs = [vf.Proof(int(i % 288), vf.pack_indices(idx[i].tolist(), bits), int(i)) for i in range(n_proofs)]
+    metas = [vf.ProofMetadata(ids[i, :32].tobytes(), ids[i, 32:64].tobytes(), ids[i, 64:].tobytes(), 4, 2**32)
+             for i in range(n_proofs)]
+    params = vf.VerifyParams(k1=2**32 - 1, k2=k2, scrypt_n=N_SCRYPT)   # difficulty ~2^62: ~25 % of labels pass
+    vf.verify_batch(proofs[:256], metas[:256], params, provider=provider)              # warm-up
+    launches0 = b2.launch_count()
+    t0 = time.perf_counter()
+    st, _ = vf.verify_batch(proofs, metas, params, provider=provider)
+    wall = time.perf_counter() - t0
+    return {"workload": f"{n_proofs} proofs x K2={k2}, N=8192, 4-SU index space, synthetic (seed 3)",
+            "proofs": n_proofs, "k2": k2, "labels_recomputed": n_proofs * k2, "seconds": wall,
+            "proofs_per_s": n_proofs / wall, "labels_per_s": n_proofs * k2 / wall,
+            "gpu_device_ms": b2.last_call_ms(provider), "gpu_launches": int(b2.launch_count() - launches0),
+            "invalid": int(sum(1 for x in st if x != 0)),
+            "note": "k2pow (RandomX) check not included; verdict conventions unpinned (DESIGN.md §2)"}
+
+
 def run_reference(args, rank: int, world: int) -> None:
     """--impl reference: the CPU oracle (port) on rank 0; other ranks exit 0 without work."""
     if rank != 0:
@@ -161,6 +190,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="labels per step per GPU (0 = 16 layers ~ 2^20, the reference's default ComputeBatchSize)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the configs[2] verify-batch measurement")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -279,6 +309,10 @@ def main() -> None:
         except Exception:  # noqa: BLE001
             traffic = None
 
+    verify_extra = None
+    if world == 1 and not args.no_verify:
+        verify_extra = bench_verify(b2, local_rank)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "labels/s", "n_gpus": world, "steps": args.steps,
@@ -300,10 +334,15 @@ def main() -> None:
                          "kernel_share_of_step": (romix_ms / dev_ms) if dev_ms else None},
             "clocks": clocks,
         }
+        if verify_extra:
+            line["verify"] = verify_extra
         if not args.no_cpu_baseline:
             from oracle import pyoracle as orc
             orc.build()
             line["cpu_baseline"] = cpu_baseline(orc)
+            if verify_extra:
+                # the reference verifies one proof per worker call: K2 label recomputations on host cores
+                line["verify"]["cpu_baseline_proofs_per_s"] = line["cpu_baseline"]["value"] / verify_extra["k2"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
