@@ -244,25 +244,37 @@ def main() -> None:
         torch.cuda.synchronize(dev)
 
     def timed(fn, steps: int, first_step: int):
-        """K steps bracketed by barrier + synchronize; returns (wall seconds max over ranks, device ms sum)."""
+        """EXACTLY K steps bracketed by barrier + synchronize on both sides.  Returns, max over ranks:
+        (wall seconds, ms between two CUDA events recorded on the engine's launching stream around the K
+        steps — gaps between calls included, ms summed over the calls alone)."""
         barrier()
+        b2.timer_mark(0, local_rank)
         t0 = time.perf_counter()
-        dev_ms = 0.0
+        calls_ms = 0.0
         for s in range(steps):
             fn(first_step + s)
-            dev_ms += b2.last_call_ms(local_rank)
+            calls_ms += b2.last_call_ms(local_rank)
+        b2.timer_mark(1, local_rank)
         barrier()
         el = time.perf_counter() - t0
+        bracket_ms = b2.timer_elapsed_ms(local_rank)
         if world > 1:
-            t = torch.tensor([el, dev_ms], dtype=torch.float64, device=dev)
+            t = torch.tensor([el, bracket_ms, calls_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            el, dev_ms = float(t[0]), float(t[1])
-        return el, dev_ms
+            el, bracket_ms, calls_ms = float(t[0]), float(t[1]), float(t[2])
+        return el, bracket_ms, calls_ms
+
+    debug = bool(os.environ.get("B200POST_BENCH_DEBUG"))
 
     def step_dev(s: int):
+        t_a = time.perf_counter()
         vrf = b2.labels_range_dev(commitment, N_SCRYPT, shard_start(s), batch, d_out.data_ptr(), provider=local_rank,
                                   vrf_difficulty_=diff)
+        t_b = time.perf_counter()
         exchange(vrf)
+        if debug:
+            print(f"[rank {rank}] step {s}: call {1e3 * (t_b - t_a):.1f} ms (device {b2.last_call_ms(local_rank):.1f}), "
+                  f"exchange {1e3 * (time.perf_counter() - t_b):.1f} ms", file=sys.stderr, flush=True)
 
     def step_e2e(s: int):
         nonce = b2.VrfNonce()
@@ -281,7 +293,7 @@ def main() -> None:
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    wall, dev_ms = timed(step_dev, args.steps, args.warmup)
+    wall, dev_ms, calls_ms = timed(step_dev, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     launches = b2.launch_count() - launches0
     romix_ms, romix_k, romix_labels = b2.romix_time(provider=local_rank, reset=True)
@@ -289,7 +301,7 @@ def main() -> None:
     # ---- end-to-end arm (host buffers through the reference-facing C-ABI call)
     for w in range(2):
         step_e2e(args.warmup + args.steps + w)
-    wall_e2e, _ = timed(step_e2e, args.steps, 2 * args.warmup + args.steps + 2)
+    wall_e2e, dev_ms_e2e, _ = timed(step_e2e, args.steps, 2 * args.warmup + args.steps + 2)
 
     total_labels = batch * args.steps * world
     # device-event time is the clock for `value` (max over ranks); wall clock is the cross-check
@@ -323,7 +335,8 @@ def main() -> None:
                        "romix_variant": b2.get_option("romix_variant"), "mulwide_mask": b2.get_option("mulwide_mask"),
                        "tpb": tpb, "l2": "working set = wave_slots x 1 MiB scratch >> 126 MB L2; every step uses fresh indices",
                        "parallelism": f"index-range shards x{world}, NCCL all-gather of one 48-B VRF record per step" if world > 1 else "single GPU",
-                       "timer": "CUDA events on the engine stream, summed over steps, max over ranks",
+                       "timer": "two CUDA events on the engine's launching stream bracketing the K steps (barrier + synchronize on both sides), max over ranks",
+                       "value_from_call_times_only": total_labels / (calls_ms / 1e3) if calls_ms > 0 else None,
                        "value_wall_clock": value_wall},
             "e2e": {"value": e2e_value, "unit": "labels/s", "h2d_bytes_per_step": 32 + 32, "d2h_bytes_per_step": batch * 16 + 48},
             "gpu_launches": int(launches),
@@ -331,7 +344,7 @@ def main() -> None:
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_label": BYTES_PER_LABEL, "labels_per_launch": labels_per_launch,
                          "avg_launch_ms": romix_avg_ms, "launches_timed": int(romix_k),
-                         "kernel_share_of_step": (romix_ms / dev_ms) if dev_ms else None},
+                         "kernel_share_of_step": (romix_ms / calls_ms) if calls_ms else None},
             "clocks": clocks,
         }
         if verify_extra:

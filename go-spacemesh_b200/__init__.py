@@ -90,6 +90,9 @@ def lib() -> ctypes.CDLL:
     L.b200post_last_call_ms.argtypes = [u32]
     L.b200post_last_call_ms.restype = ctypes.c_double
     L.b200post_wave_slots.argtypes = [u32, u64, ctypes.POINTER(u64)]
+    L.b200post_timer_mark.argtypes = [u32, ctypes.c_int]
+    L.b200post_timer_elapsed_ms.argtypes = [u32]
+    L.b200post_timer_elapsed_ms.restype = ctypes.c_double
     L.b200post_shutdown.restype = None
     _lib = L
     return L
@@ -225,6 +228,15 @@ def romix_time(provider: int = 0, reset: bool = False) -> tuple[float, int, floa
 def last_call_ms(provider: int = 0) -> float:
     """Device time (CUDA events on the engine's stream) of the last labels_* call on `provider`."""
     return float(lib().b200post_last_call_ms(provider))
+
+
+def timer_mark(which: int, provider: int = 0) -> None:
+    """Record a CUDA event on the engine's launching stream (0 = start, 1 = stop)."""
+    _check(lib().b200post_timer_mark(provider, which))
+
+
+def timer_elapsed_ms(provider: int = 0) -> float:
+    return float(lib().b200post_timer_elapsed_ms(provider))
 
 
 def wave_slots(n: int = 8192, provider: int = 0) -> int:

@@ -222,6 +222,16 @@ int b200post_wave_slots(uint32_t provider, uint64_t n, uint64_t *slots) {
     return *slots ? B200POST_OK : B200POST_ERR_CUDA;
 }
 
+int b200post_timer_mark(uint32_t provider, int which) {
+    DeviceEngine *e = engine_for(provider);
+    return e ? e->timer_mark(which) : B200POST_ERR_NO_DEVICE;
+}
+
+double b200post_timer_elapsed_ms(uint32_t provider) {
+    DeviceEngine *e = engine_for(provider);
+    return e ? e->timer_elapsed_ms() : -1.0;
+}
+
 double b200post_last_call_ms(uint32_t provider) {
     DeviceEngine *e = engine_for(provider);
     return e ? e->last_call_ms() : -1.0;

@@ -61,6 +61,7 @@ void DeviceEngine::release() {
         for (cudaEvent_t *e : evs) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
         k2_pending_[b] = false; in_pending_[b] = false; pend_[b].live = false;
     }
+    for (int b = 0; b < 2; b++) { if (ev_timer_[b]) cudaEventDestroy(ev_timer_[b]); ev_timer_[b] = nullptr; }
     cudaFree(d_diff_); d_diff_ = nullptr;
     cudaFree(d_cta_cand_); d_cta_cand_ = nullptr;
     cudaFree(d_running_); d_running_ = nullptr;
@@ -362,6 +363,24 @@ uint32_t DeviceEngine::wave_slots(uint64_t N) {
     if (cudaSetDevice(dev_) != cudaSuccess) return 0;
     if (ensure(N, 32) != B200POST_OK) return 0;
     return wave_slots_;
+}
+
+int DeviceEngine::timer_mark(int which) {
+    std::lock_guard<std::mutex> lk(mu_);
+    CU_TRY(cudaSetDevice(dev_));
+    if (which < 0 || which > 1) return B200POST_ERR_INVALID_ARGUMENT;
+    if (!stream_) { int rc = ensure(2, 32); if (rc) return rc; }
+    if (!ev_timer_[which]) CU_TRY(cudaEventCreate(&ev_timer_[which]));
+    CU_TRY(cudaEventRecord(ev_timer_[which], stream_));
+    return B200POST_OK;
+}
+
+double DeviceEngine::timer_elapsed_ms() {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (!ev_timer_[0] || !ev_timer_[1] || cudaSetDevice(dev_) != cudaSuccess) return -1.0;
+    float ms = 0;
+    if (cudaEventSynchronize(ev_timer_[1]) != cudaSuccess || cudaEventElapsedTime(&ms, ev_timer_[0], ev_timer_[1]) != cudaSuccess) return -1.0;
+    return ms;
 }
 
 double DeviceEngine::last_call_ms() {

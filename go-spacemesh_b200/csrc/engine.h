@@ -47,6 +47,9 @@ public:
     void romix_time(double *ms_total, uint64_t *launches, double *labels, bool reset);
     // device time (CUDA events on the engine's stream) of the last labels_range / labels_gather call
     double last_call_ms();
+    // stopwatch on the engine's own stream: mark(0) ... mark(1), then elapsed (CUDA events; includes gaps between calls)
+    int timer_mark(int which);
+    double timer_elapsed_ms();
     // labels one layer (wave) holds for scrypt-N under the current options; 0 + error text on failure
     uint32_t wave_slots(uint64_t N);
     int device() const { return dev_; }
@@ -102,6 +105,7 @@ private:
     struct Pending { uint64_t off; uint32_t n; bool live; } pend_[2] = {{0, 0, false}, {0, 0, false}};
     cudaEvent_t ev_call_[2] = {nullptr, nullptr};
     double last_call_ms_ = 0;
+    cudaEvent_t ev_timer_[2] = {nullptr, nullptr};
     double romix_ms_ = 0, romix_labels_ = 0;
     uint64_t romix_launches_ = 0;
     // current tuning

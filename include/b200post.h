@@ -132,6 +132,11 @@ int b200post_romix_time(uint32_t provider, double *ms_total, uint64_t *launches,
 /* Device time in ms (CUDA events recorded on the engine's own stream at the start and end of the call)
  * of the most recent labels_range* / labels_gather call on `provider`; < 0 if the provider is unusable. */
 double b200post_last_call_ms(uint32_t provider);
+/* Stopwatch for benchmarks: records a CUDA event on the engine's own (launching) stream; which = 0 start,
+ * 1 stop.  b200post_timer_elapsed_ms waits for the stop event and returns the device time between them,
+ * gaps between calls included. */
+int b200post_timer_mark(uint32_t provider, int which);
+double b200post_timer_elapsed_ms(uint32_t provider);
 /* Labels one wave holds for scrypt-N on `provider` under the current options (= resident scratchpads). */
 int b200post_wave_slots(uint32_t provider, uint64_t n, uint64_t *slots);
 
