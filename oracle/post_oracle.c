@@ -390,6 +390,76 @@ void oracle_aes128_encrypt(const uint8_t key[16], const uint8_t in[16], uint8_t 
     memcpy(out, s, 16);
 }
 
+/* ======================================================================== SSE2 ROMix (r = 1) */
+/* A second, vectorised restatement of ROMix used for the timed CPU baseline (the reference's CPU provider,
+ * scrypt-jane inside libpost, is SIMD code too).  Salsa20/8 on four 128-bit rows in "diagonal" word order:
+ * SIMD word i of a 64-byte block holds original word (5*i mod 16), so a column round works on whole
+ * vectors and the row round needs three lane rotations.  V is kept in that order, which is legal because
+ * Integerify reads word 0, which the permutation fixes.  Cross-checked against the scalar path in tests. */
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#define ORACLE_HAVE_SSE2 1
+static inline void salsa20_8_sse(__m128i B[4]) {
+    __m128i X0 = B[0], X1 = B[1], X2 = B[2], X3 = B[3], T;
+#define ROTX(dst, k) dst = _mm_xor_si128(dst, _mm_slli_epi32(T, k)); dst = _mm_xor_si128(dst, _mm_srli_epi32(T, 32 - (k)));
+    for (int i = 0; i < 8; i += 2) {
+        T = _mm_add_epi32(X0, X3); ROTX(X1, 7)
+        T = _mm_add_epi32(X1, X0); ROTX(X2, 9)
+        T = _mm_add_epi32(X2, X1); ROTX(X3, 13)
+        T = _mm_add_epi32(X3, X2); ROTX(X0, 18)
+        X1 = _mm_shuffle_epi32(X1, 0x93); X2 = _mm_shuffle_epi32(X2, 0x4E); X3 = _mm_shuffle_epi32(X3, 0x39);
+        T = _mm_add_epi32(X0, X1); ROTX(X3, 7)
+        T = _mm_add_epi32(X3, X0); ROTX(X2, 9)
+        T = _mm_add_epi32(X2, X3); ROTX(X1, 13)
+        T = _mm_add_epi32(X1, X2); ROTX(X0, 18)
+        X1 = _mm_shuffle_epi32(X1, 0x39); X2 = _mm_shuffle_epi32(X2, 0x4E); X3 = _mm_shuffle_epi32(X3, 0x93);
+    }
+#undef ROTX
+    B[0] = _mm_add_epi32(B[0], X0); B[1] = _mm_add_epi32(B[1], X1);
+    B[2] = _mm_add_epi32(B[2], X2); B[3] = _mm_add_epi32(B[3], X3);
+}
+/* BlockMix for r = 1 on X = (lo, hi), 8 vectors, in place */
+static inline void blockmix_r1_sse(__m128i X[8]) {
+    __m128i T[4];
+    for (int k = 0; k < 4; k++) T[k] = _mm_xor_si128(X[k], X[4 + k]);
+    salsa20_8_sse(T);
+    for (int k = 0; k < 4; k++) { X[k] = T[k]; T[k] = _mm_xor_si128(T[k], X[4 + k]); }
+    salsa20_8_sse(T);
+    for (int k = 0; k < 4; k++) X[4 + k] = T[k];
+}
+static void romix_r1_sse(uint32_t x[32], void *vmem, uint64_t N) {
+    __m128i X[8];
+    __m128i *V = (__m128i *)vmem;
+    uint32_t p[32];
+    for (int b = 0; b < 2; b++)
+        for (int i = 0; i < 16; i++) p[b * 16 + i] = x[b * 16 + (i * 5 % 16)];
+    for (int k = 0; k < 8; k++) X[k] = _mm_loadu_si128((const __m128i *)(p + 4 * k));
+    for (uint64_t i = 0; i < N; i++) {
+        for (int k = 0; k < 8; k++) _mm_storeu_si128(V + 8 * i + k, X[k]);
+        blockmix_r1_sse(X);
+    }
+    for (uint64_t i = 0; i < N; i++) {
+        const uint64_t j = (uint32_t)_mm_cvtsi128_si32(X[4]) & (N - 1);
+        for (int k = 0; k < 8; k++) X[k] = _mm_xor_si128(X[k], _mm_loadu_si128(V + 8 * j + k));
+        blockmix_r1_sse(X);
+    }
+    for (int k = 0; k < 8; k++) _mm_storeu_si128((__m128i *)(p + 4 * k), X[k]);
+    for (int b = 0; b < 2; b++)
+        for (int i = 0; i < 16; i++) x[b * 16 + (i * 5 % 16)] = p[b * 16 + i];
+}
+#else
+#define ORACLE_HAVE_SSE2 0
+#endif
+
+static int g_oracle_impl = ORACLE_HAVE_SSE2;   /* 0 = scalar restatement, 1 = SSE2 */
+int oracle_set_impl(int impl) {
+    if (impl == 1 && !ORACLE_HAVE_SSE2) return -1;
+    if (impl != 0 && impl != 1) return -1;
+    g_oracle_impl = impl;
+    return 0;
+}
+int oracle_get_impl(void) { return g_oracle_impl; }
+
 /* ======================================================================== label path */
 void oracle_commitment(const uint8_t node_id[32], const uint8_t commitment_atx[32], uint8_t out[32]) {
     uint8_t buf[64];
@@ -405,6 +475,9 @@ static void label32_r1(const uint8_t commitment[32], uint64_t index, uint64_t N,
     for (int i = 0; i < 8; i++) salt[i] = (uint8_t)(index >> (8 * i)); /* LE64(index) — ASSUMED */
     oracle_pbkdf2_sha256(commitment, 32, salt, 8, 1, B, 128);
     for (int k = 0; k < 32; k++) x[k] = le32(B + 4 * k);
+#if ORACLE_HAVE_SSE2
+    if (g_oracle_impl == 1) romix_r1_sse(x, v, N); else
+#endif
     romix(x, v, y, N, 1);
     for (int k = 0; k < 32; k++) put_le32(B + 4 * k, x[k]);
     oracle_pbkdf2_sha256(commitment, 32, B, 128, 1, out, 32);

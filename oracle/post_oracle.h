@@ -70,6 +70,11 @@ void oracle_vrf_difficulty(uint64_t num_labels, uint8_t out[32]);
 
 /* Salsa20/8 + scrypt ROMix timing helper for bench.py's cpu_baseline: computes `count`
  * labels starting at `start` on `threads` threads, returns elapsed seconds. */
+/* ROMix implementation used by the label functions: 0 = scalar restatement, 1 = SSE2 (default where
+ * available; cross-checked against 0 in tests/).  Returns 0, or -1 if unsupported. */
+int oracle_set_impl(int impl);
+int oracle_get_impl(void);
+
 double oracle_time_labels(const uint8_t commitment[32], uint64_t N, uint64_t start, uint64_t count,
                           int threads, uint8_t *out16);
 

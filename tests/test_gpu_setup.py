@@ -177,3 +177,21 @@ def test_all_providers_extension(su, orc, tmp_path):
     mgr.start_session()
     c = orc.py_commitment(NODE, ATX)
     assert _read_all(o.data_dir) == orc.c_labels_range(c, 2, 0, 1024)[0].tobytes()
+
+
+def test_postcli_compatible_cli(b2, orc, tmp_path):
+    """systest/cluster/nodes.go:990-999 flag set, with a B200 provider instead of the CPU one."""
+    import subprocess
+    cli = Path(b2.LIB_PATH).parent / "b200postcli"
+    if not cli.exists():
+        pytest.skip("b200postcli not built")
+    d = tmp_path / "data"
+    args = [str(cli), "-id", NODE.hex(), "-commitmentAtxId", ATX.hex(), "-datadir", str(d), "-numUnits", "3",
+            "-labelsPerUnit", "256", "-scryptN", "2", "-provider", "0", "-yes", "-maxFileSize", "8192"]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    c = orc.py_commitment(NODE, ATX)
+    assert _read_all(str(d)) == orc.c_labels_range(c, 2, 0, 768)[0].tobytes()
+    assert "VRF nonce" in r.stdout
+    r = subprocess.run(args[:-4] + ["-provider", "4294967295"], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "CPU" in r.stderr

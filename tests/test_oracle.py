@@ -117,3 +117,22 @@ def test_bad_parameters_rejected(orc):
             orc.c_labels_range(c, n, 0, 4)
     labels, found, _, _ = orc.c_labels_range(c, 2, 0, 0)
     assert labels.shape == (0, 16) and not found
+
+
+def test_sse2_and_scalar_romix_agree(orc):
+    """The vectorised ROMix used for the timed CPU baseline is the same function as the scalar restatement."""
+    L = orc.lib()
+    if L.oracle_set_impl(1) != 0:
+        pytest.skip("no SSE2")
+    try:
+        rng = np.random.default_rng(31)
+        for n in (2, 4, 64, 1024, 8192):
+            c = bytes(rng.integers(0, 256, 32, dtype=np.uint8))
+            d = orc.py_vrf_difficulty(8)
+            L.oracle_set_impl(0)
+            a = orc.c_labels_range(c, n, 2**32 - 3, 24, d, threads=2)
+            L.oracle_set_impl(1)
+            b = orc.c_labels_range(c, n, 2**32 - 3, 24, d, threads=2)
+            assert (a[0] == b[0]).all() and a[1:] == b[1:], n
+    finally:
+        L.oracle_set_impl(1)

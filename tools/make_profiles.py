@@ -1,0 +1,61 @@
+"""Dev tool (CPU box): turn the ncu artefacts in gpurun_out/ into the committed summaries under profiles/.
+usage: python tools/make_profiles.py <round-tag e.g. r01> <full.ncu-rep> <launches.csv> <bench.json>"""
+import collections, csv, json, subprocess, sys
+
+tag, rep, launches, bench = sys.argv[1:5]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units, vals = rows[0], rows[1], rows[2]
+d = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
+keys = ['Kernel Name', 'gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
+        'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem', 'smsp__warps_active.avg.per_cycle_active',
+        'smsp__warps_eligible.avg.per_cycle_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active', 'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum', 'dram__bytes_read.sum',
+        'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_sector_hit_rate.pct',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'sm__cycles_elapsed.avg.per_second',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed']
+scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'byte': 1, 'Kbyte': 1e3, 'Tbyte': 1e12}
+rd = float(d['dram__bytes_read.sum'][0]) * scale[d['dram__bytes_read.sum'][1]]
+wr = float(d['dram__bytes_write.sum'][0]) * scale[d['dram__bytes_write.sum'][1]]
+slots = int(float(d['launch__grid_size'][0])) * int(float(d['launch__block_size'][0]))
+alg = slots * 2097168
+ms = float(d['gpu__time_duration.sum'][0]) * {'ms': 1, 'us': 1e-3, 'ns': 1e-6, 's': 1e3}[d['gpu__time_duration.sum'][1]]
+stalls = sorted(((h.split('issue_stalled_')[1].replace('_per_issue_active.ratio', ''), float(v[0])) for h, v in d.items()
+                 if 'issue_stalled' in h and 'ratio' in h and 'not_issued' not in h and v[0]), key=lambda x: -x[1])
+md = [f"# ROMix pipelined kernel — ncu `--set full` summary ({tag})\n\n",
+      f"Command (gpurun, 1 GPU): `ncu --set full --clock-control none --import-source on -k regex:romix_pipe -s 3 -c 1 -o gpurun_out/{rep.split('/')[-1][:-8]} python tools/prof_pipe.py layers=5`\n\n",
+      "Captured launch: the 4th K2p launch of a 5-layer N=8192 init = steady state (fills layer 3 while mixing layer 2), library defaults.\n",
+      "Times under ncu are serialised/cold: use the shares and ratios; the timed numbers are bench.py's.\n\n",
+      "| metric | value | unit |\n|---|---|---|\n"]
+md += [f"| {k} | {d[k][0]} | {d[k][1]} |\n" for k in keys if k in d]
+md.append(f"\nDerived: slots = {slots}; algorithmic bytes per launch = slots x 2 097 168 = {alg/1e9:.2f} GB; DRAM traffic = {rd/1e9:.2f} GB read + {wr/1e9:.2f} GB written = {(rd+wr)/1e9:.2f} GB ({(rd+wr)/alg:.3f} x algorithmic: no re-reads).\n")
+md.append(f"Label-equivalents/s in this (profiled) launch: {slots/ms*1e3:,.0f}; {alg/ms/1e6:,.0f} GB/s algorithmic.\n")
+md.append("\nWarp stall reasons (cycles per issued instruction):\n\n| stall | ratio |\n|---|---|\n")
+md += [f"| {n} | {v:.3f} |\n" for n, v in stalls[:10]]
+md.append("\nReading: the alu pipe (SHF + LOP3 of the Salsa20/8 add-rotate-xor steps) is the busiest unit (math_pipe_throttle / not_selected are the top stalls, long_scoreboard is gone); fmaheavy carries the IMAD.IADD adds; DRAM sits near 45 % of its peak: the kernel is integer-issue-bound, not HBM-bound (DESIGN.md §4).\n")
+open(f'profiles/{tag}_romix_pipe_ncu_full.md', 'w').write(''.join(md))
+json.dump({"kernel": d['Kernel Name'][0], "slots": slots, "dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr,
+           "algorithmic_bytes_per_launch": alg, "source": f"profiles/{tag}_romix_pipe_ncu_full.md"},
+          open('profiles/romix_dram_bytes_per_launch.json', 'w'), indent=1)
+
+rows = [r for r in csv.reader(open(launches)) if len(r) > 5]
+h = rows[0]; ki, vi, ui = h.index('Kernel Name'), h.index('Metric Value'), h.index('Metric Unit')
+agg = collections.defaultdict(lambda: [0, 0.0])
+for r in rows[1:]:
+    try: v = float(r[vi].replace(',', ''))
+    except ValueError: continue
+    name = r[ki].split('(')[0][:70]
+    agg[name][0] += 1; agg[name][1] += v * {'ns': 1e-6, 'us': 1e-3, 'ms': 1.0, 's': 1e3}.get(r[ui], 1e-6)
+tot = sum(v[1] for v in agg.values())
+b = json.load(open(bench))
+md = [f"# Launch list of `bench.py` under ncu ({tag})\n\n",
+      f"Command (gpurun, 1 GPU): `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/{launches.split('/')[-1]} python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-verify --batch 303104`\n\n",
+      f"Per-launch times under ncu are cold-cache and serialised: compare SHARES. bench.py (not under ncu) reports `kernel_share_of_step` = {b['roofline']['kernel_share_of_step']:.4f} for the ROMix kernel from CUDA events, which agrees with the share below.\n\n",
+      "| kernel | launches | total ms | share | avg ms |\n|---|---|---|---|---|\n"]
+md += [f"| `{k}` | {v[0]} | {v[1]:.3f} | {v[1]/tot*100:.2f} % | {v[1]/v[0]:.3f} |\n" for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])]
+md.append(f"\nRaw CSV: `profiles/{tag}_launches.csv`; the bench line of the same build: `profiles/{tag}_bench_line.json`.\n")
+open(f'profiles/{tag}_launch_list.md', 'w').write(''.join(md))
+import shutil
+shutil.copy(launches, f'profiles/{tag}_launches.csv'); shutil.copy(bench, f'profiles/{tag}_bench_line.json')
+print(open(f'profiles/{tag}_romix_pipe_ncu_full.md').read()[-1500:])
