@@ -245,15 +245,30 @@ void judge(Job &j, const uint8_t *labels16) {
     }
 }
 
+// run fn(i) for i in [0, n) on up to 16 host threads (the per-proof prologue/epilogue is independent work)
+template <typename F>
+void parallel_for(size_t n, F fn) {
+    const size_t nt = std::min<size_t>({(size_t)16, std::max<size_t>(1, std::thread::hardware_concurrency()), (n + 255) / 256});
+    if (nt <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++)
+        th.emplace_back([=] { for (size_t i = t; i < n; i += nt) fn(i); });
+    for (auto &x : th) x.join();
+}
+
 // One GPU batch: jobs may use different scrypt N; group by N (in practice a single value).
 int process(uint32_t provider, std::vector<Job *> &jobs, const b200post_verifier_opts &vo) {
-    for (Job *j : jobs) prepare(*j, vo);
+    if (vo.pow_verify) { for (Job *j : jobs) prepare(*j, vo); }   // the callback's thread-safety is the caller's business
+    else parallel_for(jobs.size(), [&](size_t i) { prepare(*jobs[i], vo); });
     std::vector<uint64_t> ns;
     for (Job *j : jobs)
         if (j->status == B200POST_OK && std::find(ns.begin(), ns.end(), j->params->scrypt_n) == ns.end()) ns.push_back(j->params->scrypt_n);
     for (uint64_t n : ns) {
         std::vector<uint8_t> commitments;
         std::vector<uint64_t> indices;
+        size_t total = 0;
+        for (Job *j : jobs) if (j->status == B200POST_OK && j->params->scrypt_n == n) total += j->check.size();
+        commitments.reserve(total * 32); indices.reserve(total);
         for (Job *j : jobs) {
             if (j->status != B200POST_OK || j->params->scrypt_n != n) continue;
             j->first_item = indices.size();
@@ -268,10 +283,11 @@ int process(uint32_t provider, std::vector<Job *> &jobs, const b200post_verifier
             DeviceEngine *e = engine_for(provider);
             rc = e ? e->labels_gather(indices.size(), commitments.data(), indices.data(), n, labels.data()) : B200POST_ERR_NO_DEVICE;
         }
-        for (Job *j : jobs) {
-            if (j->status != B200POST_OK || j->params->scrypt_n != n) continue;
+        parallel_for(jobs.size(), [&](size_t i) {
+            Job *j = jobs[i];
+            if (j->status != B200POST_OK || j->params->scrypt_n != n) return;
             if (rc != B200POST_OK) j->status = rc; else judge(*j, labels.data() + 16 * j->first_item);
-        }
+        });
     }
     return B200POST_OK;
 }

@@ -207,17 +207,28 @@ class PostVerifier:
             pass
 
 
+class PreparedBatch:
+    """The C structs of a batch, marshalled once (what a Go/C caller holds natively)."""
+
+    def __init__(self, proofs: list[Proof], metas: list[ProofMetadata], params: VerifyParams, options: list[dict] | None = None):
+        n = self.n = len(proofs)
+        self._keep = proofs                      # the packed index bytes are referenced, not copied
+        self.cps = (_Proof * max(n, 1))(*[_c_proof(p) for p in proofs])
+        self.cms = (_Meta * max(n, 1))(*[_c_meta(m) for m in metas])
+        self.cq = _c_params(params)
+        self.cos = (_Options * n)(*[_c_options(**o) for o in options]) if options else None
+        self.st = (ctypes.c_int * max(n, 1))()
+        self.bad = (ctypes.c_uint64 * max(n, 1))()
+
+    def run(self, provider: int = 0):
+        rc = _bind().b200post_verify_batch(provider, self.n, self.cps, self.cms, ctypes.byref(self.cq), self.cos, None,
+                                           self.st, self.bad)
+        if rc != OK:
+            raise B200PostError(rc, lib().b200post_last_error().decode(errors="replace"))
+        return list(self.st[:self.n]), list(self.bad[:self.n])
+
+
 def verify_batch(proofs: list[Proof], metas: list[ProofMetadata], params: VerifyParams, *, provider: int = 0,
                  options: list[dict] | None = None):
     """One synchronous GPU batch (BASELINE.json configs[2]).  Returns (statuses, invalid_indices)."""
-    n = len(proofs)
-    cps = (_Proof * max(n, 1))(*[_c_proof(p) for p in proofs])
-    cms = (_Meta * max(n, 1))(*[_c_meta(m) for m in metas])
-    cq = _c_params(params)
-    cos = (_Options * n)(*[_c_options(**o) for o in options]) if options else None
-    st = (ctypes.c_int * max(n, 1))()
-    bad = (ctypes.c_uint64 * max(n, 1))()
-    rc = _bind().b200post_verify_batch(provider, n, cps, cms, ctypes.byref(cq), cos, None, st, bad)
-    if rc != OK:
-        raise B200PostError(rc, lib().b200post_last_error().decode(errors="replace"))
-    return list(st[:n]), list(bad[:n])
+    return PreparedBatch(proofs, metas, params, options).run(provider)

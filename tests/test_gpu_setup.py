@@ -193,5 +193,5 @@ def test_postcli_compatible_cli(b2, orc, tmp_path):
     c = orc.py_commitment(NODE, ATX)
     assert _read_all(str(d)) == orc.c_labels_range(c, 2, 0, 768)[0].tobytes()
     assert "VRF nonce" in r.stdout
-    r = subprocess.run(args[:-4] + ["-provider", "4294967295"], capture_output=True, text=True, timeout=60)
+    r = subprocess.run(args[:-5] + ["-provider", "4294967295", "-yes"], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0 and "CPU" in r.stderr
