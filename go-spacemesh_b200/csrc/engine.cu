@@ -341,7 +341,8 @@ int DeviceEngine::labels_range(const uint8_t commitment[32], uint64_t N, uint64_
     return status;
 }
 
-int DeviceEngine::labels_gather(size_t n_items, const uint8_t *commitments, const uint64_t *indices, uint64_t N, uint8_t *out_host) {
+int DeviceEngine::labels_gather(size_t n_items, const uint8_t *commitments, const uint64_t *indices, uint64_t N, uint8_t *out_host,
+                                uint8_t *out_dev) {
     std::lock_guard<std::mutex> lk(mu_);
     CU_TRY(cudaSetDevice(dev_));
     if (n_items == 0) return B200POST_OK;
@@ -350,7 +351,7 @@ int DeviceEngine::labels_gather(size_t n_items, const uint8_t *commitments, cons
     CU_TRY(cudaEventRecord(ev_call_[0], stream_));
     Job job;
     job.gather = true; job.commitments = commitments; job.indices = indices; job.total = n_items; job.N = N;
-    job.out_host = out_host;
+    job.out_host = out_host; job.out_dev = out_dev;
     if ((rc = run_job(job))) return rc;
     CU_TRY(cudaEventRecord(ev_call_[1], stream_));
     CU_TRY(cudaStreamSynchronize(stream_));

@@ -42,7 +42,9 @@ public:
     // out_host / out_dev: at most one non-null (both null = discard).  Returns a B200POST_* code.
     int labels_range(const uint8_t commitment[32], uint64_t N, uint64_t start, uint64_t count, uint8_t *out_host,
                      uint8_t *out_dev, const uint8_t *vrf_difficulty, VrfResult *vrf, const volatile int *cancel);
-    int labels_gather(size_t n_items, const uint8_t *commitments, const uint64_t *indices, uint64_t N, uint8_t *out_host);
+    // out_dev (optional): device buffer of n_items*16 bytes on this device; the labels then never leave HBM
+    int labels_gather(size_t n_items, const uint8_t *commitments, const uint64_t *indices, uint64_t N, uint8_t *out_host,
+                      uint8_t *out_dev = nullptr);
     // accumulated ROMix kernel device time, launches, and label-equivalents processed by those launches
     void romix_time(double *ms_total, uint64_t *launches, double *labels, bool reset);
     // device time (CUDA events on the engine's stream) of the last labels_range / labels_gather call

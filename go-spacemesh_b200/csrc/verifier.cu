@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/b200post_verify.h"
+#include "aes_device.cuh"
 #include "engine.h"
 #include "host_hash.h"
 
@@ -227,22 +228,38 @@ void prepare(Job &j, const b200post_verifier_opts &vo) {
     j.out_byte = p.nonce % 16;
 }
 
-// Label-dependent verdict for one proof (ASSUMED post-rs 8/56 split compare).
-void judge(Job &j, const uint8_t *labels16) {
-    const Aes128 aes(j.key);
-    for (size_t k = 0; k < j.check.size(); k++) {
-        uint8_t out[16];
-        aes.encrypt(labels16 + 16 * k, out);
-        const uint8_t msb = out[j.out_byte];
-        if (msb < j.diff_msb) continue;
-        if (msb > j.diff_msb) { j.status = B200POST_ERR_INVALID_PROOF; j.bad_index = j.check[k]; return; }
-        const Aes128 lazy(j.lazy_key);
-        lazy.encrypt(labels16 + 16 * k, out);
-        uint64_t lsb = 0;
-        for (int b = 0; b < 8; b++) lsb |= (uint64_t)out[b] << (8 * b);
-        lsb &= 0x00ffffffffffffffull;
-        if (lsb >= j.diff_lsb) { j.status = B200POST_ERR_INVALID_PROOF; j.bad_index = j.check[k]; return; }
+// ---------------------------------------------------------------------------------------------- device epilogue
+// K5 verify_judge_kernel: the label-dependent verdict, on the device, straight from the labels K3 left in
+// HBM (no label D2H, no host AES).  One thread per recomputed label: AES-128 under the proof's key, compare
+// ciphertext byte (nonce mod 16) with the top 8 bits of the proving difficulty; on equality the lazy cipher
+// decides with the low 56 bits.  The first failing position per proof is kept with atomicMin.
+struct DevJob {            // 384 bytes
+    uint4 rk[11];
+    uint4 lazy_rk[11];
+    uint32_t first_item, n_items, out_byte, diff_msb;
+    uint64_t diff_lsb;
+    uint32_t pad[2];
+};
+
+__global__ void __launch_bounds__(256) verify_judge_kernel(const uint4 *__restrict__ labels, const uint32_t *__restrict__ item_job,
+                                                           const DevJob *__restrict__ jobs, uint32_t n_items,
+                                                           const AesTables *__restrict__ tables, uint32_t *__restrict__ first_bad) {
+    __shared__ AesSmem sm;
+    aes_load_smem(sm, tables);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const uint32_t jb = item_job[i];
+    const DevJob &j = jobs[jb];
+    const uint4 label = labels[i];
+    uint4 out = aes128_encrypt(sm, j.rk, label);
+    const uint32_t msb = uint4_byte(out, j.out_byte);
+    bool bad = msb > j.diff_msb;
+    if (msb == j.diff_msb) {
+        out = aes128_encrypt(sm, j.lazy_rk, label);
+        const uint64_t lsb = ((uint64_t)out.x | ((uint64_t)out.y << 32)) & 0x00ffffffffffffffull;
+        bad = lsb >= j.diff_lsb;
     }
+    if (bad) atomicMin(&first_bad[jb], i - j.first_item);
 }
 
 // run fn(i) for i in [0, n) on up to 16 host threads (the per-proof prologue/epilogue is independent work)
@@ -254,6 +271,66 @@ void parallel_for(size_t n, F fn) {
     for (size_t t = 0; t < nt; t++)
         th.emplace_back([=] { for (size_t i = t; i < n; i += nt) fn(i); });
     for (auto &x : th) x.join();
+}
+
+#define V_TRY(expr)                                                                   \
+    do {                                                                              \
+        cudaError_t e__ = (expr);                                                     \
+        if (e__ != cudaSuccess) {                                                     \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(e__));           \
+            rc = e__ == cudaErrorMemoryAllocation ? B200POST_ERR_OUT_OF_MEMORY : B200POST_ERR_CUDA; \
+            goto done;                                                                \
+        }                                                                             \
+    } while (0)
+
+// Recompute the labels of all OK jobs with scrypt-N `n` (gather kernels, labels stay in HBM) and run the
+// device epilogue.  first_bad[k] = position of the first failing label of the k-th such job, or 0xffffffff.
+int gather_and_judge(uint32_t provider, std::vector<Job *> &jobs, uint64_t n, const std::vector<uint8_t> &commitments,
+                     const std::vector<uint64_t> &indices, std::vector<uint32_t> &first_bad) {
+    DeviceEngine *e = engine_for(provider);
+    if (!e) return B200POST_ERR_NO_DEVICE;
+    std::vector<DevJob> dj;
+    std::vector<uint32_t> item_job(indices.size());
+    for (Job *j : jobs) {
+        if (j->status != B200POST_OK || j->params->scrypt_n != n) continue;
+        DevJob d;
+        memset(&d, 0, sizeof d);
+        const Aes128 a(j->key), l(j->lazy_key);
+        memcpy(d.rk, a.rk, sizeof d.rk);
+        memcpy(d.lazy_rk, l.rk, sizeof d.lazy_rk);
+        d.first_item = (uint32_t)j->first_item; d.n_items = (uint32_t)j->check.size();
+        d.out_byte = j->out_byte; d.diff_msb = j->diff_msb; d.diff_lsb = j->diff_lsb;
+        for (size_t k = 0; k < j->check.size(); k++) item_job[j->first_item + k] = (uint32_t)dj.size();
+        dj.push_back(d);
+    }
+    first_bad.assign(dj.size(), 0xffffffffu);
+    if (indices.empty()) return B200POST_OK;
+    static AesTables host_tables;
+    static std::once_flag once;
+    std::call_once(once, [] { aes_build_tables(host_tables); });
+
+    int rc = B200POST_OK;
+    uint4 *d_labels = nullptr; uint32_t *d_item_job = nullptr, *d_first_bad = nullptr; DevJob *d_jobs = nullptr; AesTables *d_tables = nullptr;
+    const uint32_t n_items = (uint32_t)indices.size();
+    V_TRY(cudaSetDevice(e->device()));
+    V_TRY(cudaMalloc(&d_labels, (size_t)n_items * 16));
+    V_TRY(cudaMalloc(&d_item_job, (size_t)n_items * 4));
+    V_TRY(cudaMalloc(&d_jobs, dj.size() * sizeof(DevJob)));
+    V_TRY(cudaMalloc(&d_first_bad, dj.size() * 4));
+    V_TRY(cudaMalloc(&d_tables, sizeof(AesTables)));
+    V_TRY(cudaMemcpy(d_item_job, item_job.data(), (size_t)n_items * 4, cudaMemcpyHostToDevice));
+    V_TRY(cudaMemcpy(d_jobs, dj.data(), dj.size() * sizeof(DevJob), cudaMemcpyHostToDevice));
+    V_TRY(cudaMemcpy(d_tables, &host_tables, sizeof(AesTables), cudaMemcpyHostToDevice));
+    V_TRY(cudaMemset(d_first_bad, 0xff, dj.size() * 4));
+    rc = e->labels_gather(indices.size(), commitments.data(), indices.data(), n, nullptr, reinterpret_cast<uint8_t *>(d_labels));
+    if (rc != B200POST_OK) goto done;
+    verify_judge_kernel<<<(n_items + 255) / 256, 256>>>(d_labels, d_item_job, d_jobs, n_items, d_tables, d_first_bad);
+    g_launches += 1;
+    V_TRY(cudaGetLastError());
+    V_TRY(cudaMemcpy(first_bad.data(), d_first_bad, dj.size() * 4, cudaMemcpyDeviceToHost));
+done:
+    cudaFree(d_labels); cudaFree(d_item_job); cudaFree(d_jobs); cudaFree(d_first_bad); cudaFree(d_tables);
+    return rc;
 }
 
 // One GPU batch: jobs may use different scrypt N; group by N (in practice a single value).
@@ -277,17 +354,16 @@ int process(uint32_t provider, std::vector<Job *> &jobs, const b200post_verifier
                 indices.push_back(idx);
             }
         }
-        std::vector<uint8_t> labels(indices.size() * 16);
         int rc = B200POST_ERR_INVALID_ARGUMENT;
-        if (n >= 2 && n <= (1ull << 20) && (n & (n - 1)) == 0) {
-            DeviceEngine *e = engine_for(provider);
-            rc = e ? e->labels_gather(indices.size(), commitments.data(), indices.data(), n, labels.data()) : B200POST_ERR_NO_DEVICE;
+        std::vector<uint32_t> first_bad;
+        if (n >= 2 && n <= (1ull << 20) && (n & (n - 1)) == 0) rc = gather_and_judge(provider, jobs, n, commitments, indices, first_bad);
+        size_t k = 0;
+        for (Job *j : jobs) {
+            if (j->status != B200POST_OK || j->params->scrypt_n != n) continue;
+            if (rc != B200POST_OK) j->status = rc;
+            else if (first_bad[k] != 0xffffffffu) { j->status = B200POST_ERR_INVALID_PROOF; j->bad_index = j->check[first_bad[k]]; }
+            k++;
         }
-        parallel_for(jobs.size(), [&](size_t i) {
-            Job *j = jobs[i];
-            if (j->status != B200POST_OK || j->params->scrypt_n != n) return;
-            if (rc != B200POST_OK) j->status = rc; else judge(*j, labels.data() + 16 * j->first_item);
-        });
     }
     return B200POST_OK;
 }

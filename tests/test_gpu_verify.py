@@ -216,3 +216,26 @@ def test_batch_at_mainnet_shape(vf, orc, b2):
         kw = dict(mode="subset", k3=4, seed=b"p") if i % 3 == 0 else {}
         ok, idx = _oracle_verdict(orc, proofs[i], metas[i], params, **kw)
         assert (st[i] == b2.OK) == ok and (ok or bad[i] == idx), i
+
+
+def test_device_epilogue_against_oracle_densely(vf, orc, b2):
+    """The on-device AES epilogue (incl. the rare 'MSB equal -> lazy cipher' branch, ~1/256 labels) must give the
+    oracle's verdict for every proof of a large random batch (N = 2 keeps the oracle side cheap)."""
+    rng = np.random.default_rng(77)
+    n_proofs, k2, num_units, lpu = 1500, 8, 4, 256
+    bits = vf.bits_per_index(num_units * lpu)
+    params = vf.VerifyParams(k1=900, k2=k2, scrypt_n=2)          # difficulty msb ~0xe0: most labels pass, verdicts mixed
+    node_id, atx = (bytes(rng.integers(0, 256, 32, dtype=np.uint8)) for _ in range(2))
+    proofs, metas = [], []
+    for i in range(n_proofs):
+        ch = bytes(rng.integers(0, 256, 32, dtype=np.uint8))
+        ix = [int(x) for x in rng.integers(0, num_units * lpu, k2)]
+        proofs.append(vf.Proof(int(rng.integers(0, 320)), vf.pack_indices(ix, bits), int(rng.integers(0, 2**60))))
+        metas.append(vf.ProofMetadata(node_id, atx, ch, num_units, lpu))
+    st, bad = vf.verify_batch(proofs, metas, params)
+    n_ok = 0
+    for i in range(n_proofs):
+        ok, idx = _oracle_verdict(orc, proofs[i], metas[i], params)
+        assert (st[i] == b2.OK) == ok and (ok or bad[i] == idx), i
+        n_ok += ok
+    assert 0 < n_ok < n_proofs
