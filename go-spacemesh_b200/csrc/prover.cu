@@ -1,0 +1,291 @@
+// prover.cu — POST proof generation scan (include/b200post_prove.h).
+//
+// K6 prove_scan_kernel streams 16-byte labels (H2D from the postdata files, double-buffered) through one
+// AES-128 cipher per nonce group and appends (nonce, index) hits to a small list; the host keeps the per-nonce
+// hit lists and stops when a nonce owns K2 of them.  Bandwidth view: 16 B in per label, ~nothing out; the
+// kernel is far faster than PCIe/NVMe can feed it, so the design goal is simply to keep copies and compute
+// overlapped.  Conventions: post-rs Prover8_56 from memory (ASSUMED, unpinned).
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200post_prove.h"
+#include "aes_device.cuh"
+#include "engine.h"
+#include "proof_common.h"
+
+namespace b200post {
+namespace {
+
+struct Hit { uint32_t nonce; uint32_t pad; uint64_t index; };
+
+// rk: per nonce group 11 round keys; lazy_rk: per nonce 11 round keys
+__global__ void __launch_bounds__(256) prove_scan_kernel(const uint4 *__restrict__ labels, uint64_t first_index, uint32_t count,
+                                                         const uint4 *__restrict__ rk, const uint4 *__restrict__ lazy_rk,
+                                                         uint32_t n_groups, uint32_t diff_msb, uint64_t diff_lsb,
+                                                         const AesTables *__restrict__ tables, Hit *__restrict__ hits,
+                                                         uint32_t hit_cap, uint32_t *__restrict__ n_hits) {
+    __shared__ AesSmem sm;
+    aes_load_smem(sm, tables);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint4 label = labels[i];
+        for (uint32_t g = 0; g < n_groups; g++) {
+            const uint4 out = aes128_encrypt(sm, rk + 11 * g, label);
+#pragma unroll 1
+            for (uint32_t b = 0; b < 16; b++) {
+                const uint32_t msb = uint4_byte(out, b);
+                if (msb > diff_msb) continue;
+                const uint32_t nonce = g * 16 + b;
+                if (msb == diff_msb) {
+                    const uint4 lz = aes128_encrypt(sm, lazy_rk + 11 * nonce, label);
+                    const uint64_t lsb = ((uint64_t)lz.x | ((uint64_t)lz.y << 32)) & 0x00ffffffffffffffull;
+                    if (lsb >= diff_lsb) continue;
+                }
+                const uint32_t pos = atomicAdd(n_hits, 1u);
+                if (pos < hit_cap) hits[pos] = Hit{nonce, 0, first_index + i};
+            }
+        }
+    }
+}
+
+#define P_TRY(expr)                                                                                                   \
+    do {                                                                                                              \
+        cudaError_t e__ = (expr);                                                                                     \
+        if (e__ != cudaSuccess) {                                                                                     \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(e__));                                           \
+            return e__ == cudaErrorMemoryAllocation ? B200POST_ERR_OUT_OF_MEMORY : B200POST_ERR_CUDA;                 \
+        }                                                                                                             \
+    } while (0)
+
+// Streaming scan state: device buffers, keys, per-nonce hit lists.
+class Scanner {
+public:
+    ~Scanner() {
+        if (dev_ >= 0) cudaSetDevice(dev_);
+        for (int b = 0; b < 2; b++) { cudaFree(d_labels_[b]); cudaFreeHost(h_labels_[b]); if (ev_[b]) cudaEventDestroy(ev_[b]); if (st_[b]) cudaStreamDestroy(st_[b]); cudaFree(d_hits_[b]); cudaFree(d_nhits_[b]); cudaFreeHost(h_hits_[b]); cudaFreeHost(h_nhits_[b]); }
+        cudaFree(d_rk_); cudaFree(d_lazy_); cudaFree(d_tables_);
+    }
+    int init(uint32_t provider, const uint8_t challenge[32], uint32_t nonces, const uint64_t *pows, uint32_t k1, uint32_t k2,
+             uint64_t num_labels, uint64_t chunk) {
+        DeviceEngine *e = engine_for(provider);
+        if (!e) return provider == B200POST_CPU_PROVIDER_ID ? B200POST_ERR_UNSUPPORTED : B200POST_ERR_NO_DEVICE;
+        if (nonces == 0 || nonces % 16 || nonces > 4096 || k1 == 0 || k2 == 0 || num_labels == 0 || chunk == 0 || chunk > (1u << 28)) {
+            set_error("invalid proving parameters (nonces must be a positive multiple of 16, <= 4096)");
+            return B200POST_ERR_INVALID_ARGUMENT;
+        }
+        dev_ = e->device(); nonces_ = nonces; k2_ = k2; chunk_ = chunk;
+        const uint64_t diff = b200post_proving_difficulty(k1, num_labels);
+        msb_ = (uint32_t)(diff >> 56); lsb_ = diff & 0x00ffffffffffffffull;
+        // hits per chunk are ~ chunk * nonces * K1/numLabels; leave generous slack, cap the buffer at 64 MiB
+        const double expect = (double)chunk * nonces * ((double)k1 / (double)num_labels);
+        hit_cap_ = (uint32_t)std::min<double>(std::max<double>(4.0 * expect + 65536.0, 65536.0), 4.0 * 1024 * 1024);
+        P_TRY(cudaSetDevice(dev_));
+        std::vector<uint8_t> rk((size_t)(nonces / 16) * 176), lazy((size_t)nonces * 176);
+        for (uint32_t g = 0; g < nonces / 16; g++) {
+            uint8_t key[16];
+            cipher_key(challenge, g, pows[g], nullptr, key);
+            const Aes128 a(key);
+            memcpy(rk.data() + (size_t)g * 176, a.rk, 176);
+        }
+        for (uint32_t n = 0; n < nonces; n++) {
+            uint8_t key[16];
+            cipher_key(challenge, n / 16, pows[n / 16], &n, key);
+            const Aes128 a(key);
+            memcpy(lazy.data() + (size_t)n * 176, a.rk, 176);
+        }
+        static AesTables host_tables;
+        static std::once_flag once;
+        std::call_once(once, [] { aes_build_tables(host_tables); });
+        P_TRY(cudaMalloc(&d_rk_, rk.size()));
+        P_TRY(cudaMalloc(&d_lazy_, lazy.size()));
+        P_TRY(cudaMalloc(&d_tables_, sizeof(AesTables)));
+        P_TRY(cudaMemcpy(d_rk_, rk.data(), rk.size(), cudaMemcpyHostToDevice));
+        P_TRY(cudaMemcpy(d_lazy_, lazy.data(), lazy.size(), cudaMemcpyHostToDevice));
+        P_TRY(cudaMemcpy(d_tables_, &host_tables, sizeof(AesTables), cudaMemcpyHostToDevice));
+        for (int b = 0; b < 2; b++) {
+            P_TRY(cudaStreamCreateWithFlags(&st_[b], cudaStreamNonBlocking));
+            P_TRY(cudaEventCreateWithFlags(&ev_[b], cudaEventDisableTiming));
+            P_TRY(cudaMalloc(&d_labels_[b], chunk * 16));
+            P_TRY(cudaMallocHost(&h_labels_[b], chunk * 16));
+            P_TRY(cudaMalloc(&d_hits_[b], (size_t)hit_cap_ * sizeof(Hit)));
+            P_TRY(cudaMalloc(&d_nhits_[b], 4));
+            P_TRY(cudaMallocHost(&h_hits_[b], (size_t)hit_cap_ * sizeof(Hit)));
+            P_TRY(cudaMallocHost(&h_nhits_[b], 4));
+        }
+        cudaDeviceProp p;
+        P_TRY(cudaGetDeviceProperties(&p, dev_));
+        grid_ = (uint32_t)p.multiProcessorCount * 8;
+        return B200POST_OK;
+    }
+    uint8_t *staging(int b) { return h_labels_[b]; }
+    // enqueue chunk in staging(b): labels [first, first+count)
+    int submit(int b, uint64_t first, uint32_t count) {
+        P_TRY(cudaMemcpyAsync(d_labels_[b], h_labels_[b], (size_t)count * 16, cudaMemcpyHostToDevice, st_[b]));
+        P_TRY(cudaMemsetAsync(d_nhits_[b], 0, 4, st_[b]));
+        prove_scan_kernel<<<grid_, 256, 0, st_[b]>>>(reinterpret_cast<const uint4 *>(d_labels_[b]), first, count,
+                                                     reinterpret_cast<const uint4 *>(d_rk_), reinterpret_cast<const uint4 *>(d_lazy_),
+                                                     nonces_ / 16, msb_, lsb_, d_tables_, d_hits_[b], hit_cap_, d_nhits_[b]);
+        g_launches += 1;
+        P_TRY(cudaGetLastError());
+        P_TRY(cudaMemcpyAsync(h_nhits_[b], d_nhits_[b], 4, cudaMemcpyDeviceToHost, st_[b]));
+        P_TRY(cudaMemcpyAsync(h_hits_[b], d_hits_[b], (size_t)hit_cap_ * sizeof(Hit), cudaMemcpyDeviceToHost, st_[b]));
+        P_TRY(cudaEventRecord(ev_[b], st_[b]));
+        pending_[b] = true; end_[b] = first + count;
+        return B200POST_OK;
+    }
+    // wait for chunk b and fold its hits in; *found set when some nonce has K2 hits
+    int collect(int b, bool *found) {
+        if (!pending_[b]) return B200POST_OK;
+        P_TRY(cudaEventSynchronize(ev_[b]));
+        pending_[b] = false;
+        const uint32_t n = *h_nhits_[b];
+        if (n > hit_cap_) { set_error("hit buffer overflow: K1 too large for this chunk size"); return B200POST_ERR_OUT_OF_MEMORY; }
+        std::vector<Hit> v(h_hits_[b], h_hits_[b] + n);
+        std::sort(v.begin(), v.end(), [](const Hit &x, const Hit &y) { return x.index != y.index ? x.index < y.index : x.nonce < y.nonce; });
+        for (const Hit &h : v) {
+            std::vector<uint64_t> &l = lists_[h.nonce];
+            if (l.size() < k2_) l.push_back(h.index);
+        }
+        scanned_ = std::max(scanned_, end_[b]);
+        for (auto &kv : lists_) if (kv.second.size() >= k2_) *found = true;
+        return B200POST_OK;
+    }
+    // the winning nonce: lowest K2-th hit index, ties to the lower nonce
+    bool winner(uint32_t *nonce, std::vector<uint64_t> *indices) const {
+        bool have = false;
+        for (const auto &kv : lists_) {
+            if (kv.second.size() < k2_) continue;
+            if (!have || kv.second[k2_ - 1] < (*indices)[k2_ - 1]) { *nonce = kv.first; *indices = kv.second; have = true; }
+        }
+        return have;
+    }
+    uint64_t scanned() const { return scanned_; }
+
+private:
+    int dev_ = -1;
+    uint32_t nonces_ = 0, k2_ = 0, msb_ = 0, hit_cap_ = 0, grid_ = 0;
+    uint64_t lsb_ = 0, chunk_ = 0, scanned_ = 0;
+    uint8_t *d_rk_ = nullptr, *d_lazy_ = nullptr;
+    AesTables *d_tables_ = nullptr;
+    cudaStream_t st_[2] = {nullptr, nullptr};
+    cudaEvent_t ev_[2] = {nullptr, nullptr};
+    uint8_t *d_labels_[2] = {nullptr, nullptr}, *h_labels_[2] = {nullptr, nullptr};
+    Hit *d_hits_[2] = {nullptr, nullptr}, *h_hits_[2] = {nullptr, nullptr};
+    uint32_t *d_nhits_[2] = {nullptr, nullptr}, *h_nhits_[2] = {nullptr, nullptr};
+    bool pending_[2] = {false, false};
+    uint64_t end_[2] = {0, 0};
+    std::map<uint32_t, std::vector<uint64_t>> lists_;   // ordered: ties resolve to the lower nonce
+};
+
+int finish(const Scanner &sc, uint32_t nonces, const uint64_t *pows, uint64_t num_labels, b200post_proof_out *out) {
+    uint32_t nonce = 0;
+    std::vector<uint64_t> idx;
+    if (!sc.winner(&nonce, &idx)) { set_error("no proof found: no nonce reached K2 qualifying labels"); return B200POST_ERR_INVALID_PROOF; }
+    (void)nonces;
+    memset(out, 0, sizeof *out);
+    out->nonce = nonce; out->pow = pows[nonce / 16]; out->labels_scanned = sc.scanned();
+    out->indices_len = b200post_pack_indices(idx.data(), idx.size(), b200post_bits_per_index(num_labels), out->indices, sizeof out->indices);
+    if (out->indices_len == 0) { set_error("packed indices exceed the 800-byte wire cap"); return B200POST_ERR_INVALID_ARGUMENT; }
+    return B200POST_OK;
+}
+
+}  // namespace
+}  // namespace b200post
+
+using namespace b200post;
+
+extern "C" {
+
+int b200post_prove_scan(uint32_t provider, const uint8_t *labels16, uint64_t first_index, uint64_t count, const uint8_t challenge[32],
+                        uint32_t nonces, const uint64_t *pows, uint32_t k1, uint32_t k2, uint64_t num_labels, b200post_proof_out *out) {
+    if (!labels16 || !challenge || !pows || !out) { set_error("invalid argument"); return B200POST_ERR_INVALID_ARGUMENT; }
+    Scanner sc;
+    const uint64_t chunk = std::min<uint64_t>(std::max<uint64_t>(count, 1), 1u << 22);
+    int rc = sc.init(provider, challenge, nonces, pows, k1, k2, num_labels, chunk);
+    if (rc) return rc;
+    bool found = false;
+    int b = 0;
+    for (uint64_t off = 0; off < count && !found; off += chunk, b ^= 1) {
+        if ((rc = sc.collect(b, &found))) return rc;
+        if (found) break;
+        const uint32_t n = (uint32_t)std::min<uint64_t>(chunk, count - off);
+        memcpy(sc.staging(b), labels16 + off * 16, (size_t)n * 16);
+        if ((rc = sc.submit(b, first_index + off, n))) return rc;
+    }
+    for (int k = 0; k < 2; k++) if ((rc = sc.collect(b ^ k, &found))) return rc;   // older chunk first
+    return finish(sc, nonces, pows, num_labels, out);
+}
+
+int b200post_generate_proof(const char *data_dir, const uint8_t challenge[32], const b200post_post_config *cfg,
+                            const b200post_prove_opts *opts, b200post_proof_out *out, b200post_proof_metadata *meta_out,
+                            const volatile int *cancel) {
+    if (!data_dir || !challenge || !cfg || !out) { set_error("invalid argument"); return B200POST_ERR_INVALID_ARGUMENT; }
+    b200post_prove_opts o{};
+    if (opts) o = *opts;
+    if (o.nonces == 0) o.nonces = 16;
+    if (o.chunk_labels == 0) o.chunk_labels = 1ull << 22;
+    b200post_post_metadata md;
+    int rc = b200post_load_metadata(data_dir, &md);
+    if (rc) return rc;
+    const uint64_t num_labels = (uint64_t)md.num_units * md.labels_per_unit;
+    if (num_labels == 0 || o.nonces % 16 || o.nonces > 4096) { set_error("invalid metadata or nonce count"); return B200POST_ERR_INVALID_ARGUMENT; }
+    // k2pow per nonce group (RandomX upstream) through the caller's hook
+    std::vector<uint64_t> pows(o.nonces / 16, 0);
+    if (o.pow_prove) {
+        uint8_t scaled[32];
+        div256_u32(cfg->pow_difficulty, md.num_units, scaled);
+        for (uint32_t g = 0; g < o.nonces / 16; g++)
+            if (o.pow_prove(o.pow_ctx, (uint8_t)g, challenge, scaled, md.node_id, &pows[g]) != 0) { set_error("k2pow hook failed"); return B200POST_ERR_INVALID_ARGUMENT; }
+    }
+    Scanner sc;
+    const uint64_t chunk = std::min<uint64_t>(o.chunk_labels, num_labels);
+    if ((rc = sc.init(o.provider, challenge, o.nonces, pows.data(), cfg->k1, cfg->k2, num_labels, chunk))) return rc;
+
+    const uint64_t per_file = md.max_file_size / 16;
+    if (per_file == 0) { set_error("corrupt metadata: MaxFileSize"); return B200POST_ERR_IO; }
+    bool found = false;
+    int b = 0, fd = -1;
+    uint64_t open_file = ~0ull;
+    for (uint64_t pos = 0; pos < num_labels && !found; b ^= 1) {
+        if (cancel && *cancel) { if (fd >= 0) close(fd); set_error("cancelled"); return B200POST_ERR_CANCELLED; }
+        if ((rc = sc.collect(b, &found))) { if (fd >= 0) close(fd); return rc; }
+        if (found) break;
+        // fill the staging buffer from the files (a chunk may span files)
+        uint64_t n = 0;
+        const uint64_t want = std::min<uint64_t>(chunk, num_labels - pos);
+        while (n < want) {
+            const uint64_t file = (pos + n) / per_file, in_file = (pos + n) % per_file;
+            if (file != open_file) {
+                if (fd >= 0) close(fd);
+                const std::string path = std::string(data_dir) + "/postdata_" + std::to_string(file) + ".bin";
+                fd = open(path.c_str(), O_RDONLY);
+                if (fd < 0) { set_error("open " + path + ": " + strerror(errno)); return B200POST_ERR_IO; }
+                open_file = file;
+            }
+            const uint64_t take = std::min<uint64_t>(want - n, per_file - in_file);
+            const ssize_t r = pread(fd, sc.staging(b) + n * 16, (size_t)take * 16, (off_t)(in_file * 16));
+            if (r != (ssize_t)(take * 16)) { close(fd); set_error("POST data is incomplete (short read): initialisation not finished?"); return B200POST_ERR_IO; }
+            n += take;
+        }
+        if ((rc = sc.submit(b, pos, (uint32_t)n))) { close(fd); return rc; }
+        pos += n;
+    }
+    if (fd >= 0) close(fd);
+    for (int k = 0; k < 2; k++) if ((rc = sc.collect(b ^ k, &found))) return rc;   // older chunk first
+    if ((rc = finish(sc, o.nonces, pows.data(), num_labels, out))) return rc;
+    if (meta_out) {
+        memcpy(meta_out->node_id, md.node_id, 32);
+        memcpy(meta_out->commitment_atx_id, md.commitment_atx_id, 32);
+        memcpy(meta_out->challenge, challenge, 32);
+        meta_out->num_units = md.num_units; meta_out->labels_per_unit = md.labels_per_unit;
+    }
+    return B200POST_OK;
+}
+
+}  // extern "C"

@@ -5,8 +5,6 @@
 // what is expensive and certain — recomputing every requested label with the gather kernels — and this file
 // does the cheap per-proof bookkeeping around it.  All conventions marked ASSUMED follow the published
 // post-rs v0.7.x verifier from memory and are "parity unpinned" (DESIGN.md §2).
-#include <immintrin.h>
-
 #include <algorithm>
 #include <condition_variable>
 #include <cstring>
@@ -19,51 +17,10 @@
 #include "aes_device.cuh"
 #include "engine.h"
 #include "host_hash.h"
+#include "proof_common.h"
 
 namespace b200post {
 namespace {
-
-// ---------------------------------------------------------------------------------------------- AES-128
-// FIPS-197 with AES-NI (every x86-64 server CPU that hosts a B200 has it); single-block ECB encryption.
-struct Aes128 {
-    __m128i rk[11];
-    template <int RCON>
-    static __m128i expand(__m128i k) {
-        __m128i t = _mm_aeskeygenassist_si128(k, RCON);
-        t = _mm_shuffle_epi32(t, 0xff);
-        k = _mm_xor_si128(k, _mm_slli_si128(k, 4));
-        k = _mm_xor_si128(k, _mm_slli_si128(k, 4));
-        k = _mm_xor_si128(k, _mm_slli_si128(k, 4));
-        return _mm_xor_si128(k, t);
-    }
-    explicit Aes128(const uint8_t key[16]) {
-        rk[0] = _mm_loadu_si128(reinterpret_cast<const __m128i *>(key));
-        rk[1] = expand<0x01>(rk[0]); rk[2] = expand<0x02>(rk[1]); rk[3] = expand<0x04>(rk[2]);
-        rk[4] = expand<0x08>(rk[3]); rk[5] = expand<0x10>(rk[4]); rk[6] = expand<0x20>(rk[5]);
-        rk[7] = expand<0x40>(rk[6]); rk[8] = expand<0x80>(rk[7]); rk[9] = expand<0x1b>(rk[8]);
-        rk[10] = expand<0x36>(rk[9]);
-    }
-    void encrypt(const uint8_t in[16], uint8_t out[16]) const {
-        __m128i s = _mm_xor_si128(_mm_loadu_si128(reinterpret_cast<const __m128i *>(in)), rk[0]);
-        for (int r = 1; r < 10; r++) s = _mm_aesenc_si128(s, rk[r]);
-        s = _mm_aesenclast_si128(s, rk[10]);
-        _mm_storeu_si128(reinterpret_cast<__m128i *>(out), s);
-    }
-};
-
-inline void put_le32(uint8_t *p, uint32_t v) { for (int i = 0; i < 4; i++) p[i] = (uint8_t)(v >> (8 * i)); }
-inline void put_le64(uint8_t *p, uint64_t v) { for (int i = 0; i < 8; i++) p[i] = (uint8_t)(v >> (8 * i)); }
-
-// ASSUMED (post-rs cipher.rs): key = blake3(challenge || LE32(nonce_group) || LE64(pow) [|| LE32(nonce)])[0:16]
-void cipher_key(const uint8_t challenge[32], uint32_t nonce_group, uint64_t pow, const uint32_t *nonce, uint8_t key[16]) {
-    uint8_t buf[48];
-    memcpy(buf, challenge, 32);
-    put_le32(buf + 32, nonce_group);
-    put_le64(buf + 36, pow);
-    size_t len = 44;
-    if (nonce) { put_le32(buf + 44, *nonce); len = 48; }
-    blake3_single_chunk(buf, len, key, 16);
-}
 
 // ASSUMED (post-rs random_values_gen.rs): BLAKE3-XOF driven partial Fisher-Yates over the K2 positions.
 struct Blake3Rng {
@@ -83,16 +40,6 @@ struct Blake3Rng {
         return v;
     }
 };
-
-// 256-bit big-endian value / 32-bit divisor (scale_pow_difficulty: difficulty / num_units) — ASSUMED
-void div256_u32(const uint8_t in[32], uint32_t d, uint8_t out[32]) {
-    uint64_t rem = 0;
-    for (int i = 0; i < 32; i++) {
-        const uint64_t cur = (rem << 8) | in[i];
-        out[i] = (uint8_t)(cur / d);
-        rem = cur % d;
-    }
-}
 
 struct Job {
     const b200post_proof *proof;

@@ -303,3 +303,22 @@ def py_prove(node_id: bytes, atx: bytes, challenge: bytes, num_units: int, label
             if len(hits) == k2:
                 return py_pack_indices(hits, py_bits_per_index(num_labels)), hits
     return None, hits
+
+
+def py_prove_multi(labels: np.ndarray, challenge: bytes, nonces: int, pows, k1: int, k2: int, num_labels: int):
+    """Multi-nonce scan over `labels` (uint8[n,16], label indices 0..n-1) with the product's deterministic
+    selection rule: among nonces reaching K2 hits, lowest K2-th hit index wins, ties to the lower nonce.
+    Returns (nonce, hits) or (None, None)."""
+    diff = py_proving_difficulty(k1, num_labels)
+    best = None
+    for nonce in range(nonces):
+        pow_ = pows[nonce // 16]
+        hits = []
+        for i in range(len(labels)):
+            if py_label_passes(labels[i].tobytes(), challenge, nonce, pow_, diff):
+                hits.append(i)
+                if len(hits) == k2:
+                    break
+        if len(hits) == k2 and (best is None or hits[-1] < best[1][-1]):
+            best = (nonce, hits)
+    return best if best else (None, None)

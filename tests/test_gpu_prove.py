@@ -1,0 +1,87 @@
+"""GPU tier: init -> prove -> verify, the reference's e2e shape (activation/e2e/nipost_test.go:151-231: setup
+session, PostClient.Proof, real verifier) run entirely on the B200 engine, plus parity of the proving scan with
+the oracle's restatement."""
+import importlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+NODE, ATX = bytes(range(50, 82)), bytes(range(150, 182))
+
+
+@pytest.fixture(scope="module")
+def mods(b2, gpu_ready):
+    return (importlib.import_module("go-spacemesh_b200.setup"), importlib.import_module("go-spacemesh_b200.prove"),
+            importlib.import_module("go-spacemesh_b200.verify"))
+
+
+def _init(su, tmp_path, cfg, n, num_units, max_file_size):
+    mgr = su.PostSetupManager(cfg)
+    o = su.PostSetupOpts(data_dir=str(tmp_path / "post"), num_units=num_units, max_file_size=max_file_size, provider_id=0,
+                         scrypt_n=n, compute_batch_size=1 << 12)
+    mgr.prepare_initializer(o, NODE, ATX)
+    mgr.start_session()
+    assert mgr.status().state == su.STATE_COMPLETE
+    return o
+
+
+def test_scan_matches_oracle_rule(mods, orc):
+    """Multi-nonce scan over labels in memory: same (nonce, indices) as the oracle's restatement."""
+    su, pr, vf = mods
+    c = orc.py_commitment(NODE, ATX)
+    num_labels, k1, k2 = 4096, 180, 6
+    labels, _, _, _ = orc.c_labels_range(c, 2, 0, num_labels)
+    rng = np.random.default_rng(8)
+    for nonces, pows in ((16, [5]), (48, [1, 2**40, 77])):
+        challenge = bytes(rng.integers(0, 256, 32, dtype=np.uint8))
+        nonce, packed, pow_, scanned = pr.prove_scan(labels, challenge, nonces, pows, k1, k2, num_labels)
+        exp_nonce, exp_hits = orc.py_prove_multi(labels[:scanned + 64], challenge, nonces, pows, k1, k2, num_labels)
+        assert exp_nonce is not None
+        assert (nonce, vf.unpack_indices(packed, vf.bits_per_index(num_labels), k2)) == (exp_nonce, exp_hits)
+        assert pow_ == pows[nonce // 16]
+
+
+@pytest.mark.parametrize("n,lpu,units,k1,k2,nonces", [(2, 512, 4, 120, 8, 16), (2, 2048, 2, 300, 12, 64), (8192, 1024, 2, 200, 10, 16)])
+def test_init_prove_verify_roundtrip(mods, tmp_path, orc, n, lpu, units, k1, k2, nonces):
+    su, pr, vf = mods
+    cfg = su.PostConfig(labels_per_unit=lpu, k1=k1, k2=k2, k3=k2, max_num_units=8)
+    o = _init(su, tmp_path, cfg, n, units, max_file_size=lpu * 16 // 2)        # data spans several files
+    challenge = bytes(range(200, 232))
+    pows_seen = []
+
+    def k2pow(ctx, nonce_group, challenge8, difficulty, node_id, pow_out):
+        pows_seen.append(nonce_group)
+        pow_out[0] = 1000 + nonce_group
+        return 0
+
+    proof, meta, scanned = pr.generate_proof(o.data_dir, challenge, cfg, nonces=nonces, chunk_labels=700, pow_prove=k2pow)
+    assert pows_seen == list(range(nonces // 16)) and proof.pow == 1000 + proof.nonce // 16
+    assert meta.node_id == NODE and meta.commitment_atx_id == ATX and meta.challenge == challenge
+    assert (meta.num_units, meta.labels_per_unit) == (units, lpu) and 0 < scanned <= units * lpu
+    params = vf.VerifyParams(k1=k1, k2=k2, scrypt_n=n)
+    # the oracle's verifier accepts it ...
+    assert orc.py_verify(proof.nonce, proof.indices, proof.pow, NODE, ATX, challenge, units, lpu, k1, k2, n) == (True, None)
+    # ... and so does the batched GPU verifier, in every mode
+    v = vf.PostVerifier()
+    try:
+        v.verify(proof, meta, params)
+        v.verify(proof, meta, params, mode=vf.MODE_SUBSET, k3=3, seed=b"peer")
+        idx = vf.unpack_indices(proof.indices, vf.bits_per_index(units * lpu), k2)
+        assert idx == sorted(idx) and len(set(idx)) == k2
+        # a proof for another challenge must not verify (activation/e2e/validation_test.go:23-137 spirit)
+        other = vf.ProofMetadata(NODE, ATX, bytes(32), units, lpu)
+        with pytest.raises(vf.ErrInvalidIndex):
+            v.verify(proof, other, params)
+    finally:
+        v.close()
+
+
+def test_no_proof_in_a_space_that_is_too_hard(mods, tmp_path, b2):
+    su, pr, vf = mods
+    cfg = su.PostConfig(labels_per_unit=256, k1=1, k2=30, k3=30)
+    o = _init(su, tmp_path, cfg, 2, 2, max_file_size=4096)
+    with pytest.raises(b2.B200PostError) as e:
+        pr.generate_proof(o.data_dir, bytes(32), cfg)
+    assert e.value.code == b2.ERR_INVALID_PROOF and "no proof found" in str(e.value)
