@@ -25,32 +25,84 @@ namespace {
 
 struct Hit { uint32_t nonce; uint32_t pad; uint64_t index; };
 
-// rk: per nonce group 11 round keys; lazy_rk: per nonce 11 round keys
+// K6a: rk = per nonce group 11 round keys.  Every (label, group) costs one AES; ciphertext bytes below the
+// difficulty MSB are hits, bytes EQUAL to it (1 in 256) need the nonce's "lazy" cipher: those are queued as
+// (label offset, nonce) candidates and resolved densely by K6b — evaluating them in place would run a whole
+// AES with one or two active lanes for most warps.
 __global__ void __launch_bounds__(256) prove_scan_kernel(const uint4 *__restrict__ labels, uint64_t first_index, uint32_t count,
-                                                         const uint4 *__restrict__ rk, const uint4 *__restrict__ lazy_rk,
-                                                         uint32_t n_groups, uint32_t diff_msb, uint64_t diff_lsb,
+                                                         const uint4 *__restrict__ rk, uint32_t n_groups, uint32_t diff_msb,
                                                          const AesTables *__restrict__ tables, Hit *__restrict__ hits,
-                                                         uint32_t hit_cap, uint32_t *__restrict__ n_hits) {
-    __shared__ AesSmem sm;
-    aes_load_smem(sm, tables);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        const uint4 label = labels[i];
+                                                         uint32_t hit_cap, uint32_t *__restrict__ n_hits,
+                                                         uint2 *__restrict__ cands, uint32_t cand_cap, uint32_t *__restrict__ n_cands) {
+    extern __shared__ uint32_t aes_sm[];
+    aes_load_smem(aes_sm, tables);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t *tl = aes_sm + lane;
+    const uint32_t msb4 = diff_msb * 0x01010101u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    // whole warps stay in the loop together (the candidate compaction below is warp-collective)
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < count; base += stride) {
+        const uint32_t i = base + lane;
+        const bool live = i < count;
+        const uint4 label = live ? labels[i] : make_uint4(0, 0, 0, 0);
         for (uint32_t g = 0; g < n_groups; g++) {
-            const uint4 out = aes128_encrypt(sm, rk + 11 * g, label);
+            const uint4 out = aes128_encrypt(tl, rk + 11 * g, label);
+            // per byte: 0xff where ciphertext byte <= MSB / == MSB
+            const uint32_t le[4] = {__vcmpleu4(out.x, msb4), __vcmpleu4(out.y, msb4), __vcmpleu4(out.z, msb4), __vcmpleu4(out.w, msb4)};
+            const uint32_t eq[4] = {__vcmpeq4(out.x, msb4), __vcmpeq4(out.y, msb4), __vcmpeq4(out.z, msb4), __vcmpeq4(out.w, msb4)};
+            const bool any_le = live && (le[0] | le[1] | le[2] | le[3]);
+            if (!__any_sync(0xffffffffu, any_le)) continue;
+            uint32_t n_eq = 0;
+            if (any_le) {
+#pragma unroll
+                for (int w = 0; w < 4; w++) n_eq += __popc(eq[w]) >> 3;
+            }
+            // warp-aggregated reservation of candidate slots
+            uint32_t incl = n_eq;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += t; }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t slot = 0;
+            if (total) {
+                if (lane == 31) slot = atomicAdd(n_cands, total);
+                slot = __shfl_sync(0xffffffffu, slot, 31) + incl - n_eq;
+            }
+            if (any_le) {
 #pragma unroll 1
-            for (uint32_t b = 0; b < 16; b++) {
-                const uint32_t msb = uint4_byte(out, b);
-                if (msb > diff_msb) continue;
-                const uint32_t nonce = g * 16 + b;
-                if (msb == diff_msb) {
-                    const uint4 lz = aes128_encrypt(sm, lazy_rk + 11 * nonce, label);
-                    const uint64_t lsb = ((uint64_t)lz.x | ((uint64_t)lz.y << 32)) & 0x00ffffffffffffffull;
-                    if (lsb >= diff_lsb) continue;
+                for (uint32_t b = 0; b < 16; b++) {
+                    const uint32_t bit = 0xffu << (8 * (b & 3));
+                    if (!(le[b >> 2] & bit)) continue;
+                    const uint32_t nonce = g * 16 + b;
+                    if (eq[b >> 2] & bit) {
+                        if (slot < cand_cap) cands[slot] = make_uint2(i, nonce);
+                        slot++;
+                    } else {
+                        const uint32_t pos = atomicAdd(n_hits, 1u);
+                        if (pos < hit_cap) hits[pos] = Hit{nonce, 0, first_index + i};
+                    }
                 }
-                const uint32_t pos = atomicAdd(n_hits, 1u);
-                if (pos < hit_cap) hits[pos] = Hit{nonce, 0, first_index + i};
             }
         }
+    }
+}
+
+// K6b: one thread per candidate: the nonce's lazy cipher decides with the low 56 bits.
+__global__ void __launch_bounds__(256) prove_lazy_kernel(const uint4 *__restrict__ labels, uint64_t first_index,
+                                                         const uint2 *__restrict__ cands, const uint32_t *__restrict__ n_cands,
+                                                         uint32_t cand_cap, const uint4 *__restrict__ lazy_rk, uint64_t diff_lsb,
+                                                         const AesTables *__restrict__ tables, Hit *__restrict__ hits,
+                                                         uint32_t hit_cap, uint32_t *__restrict__ n_hits) {
+    extern __shared__ uint32_t aes_sm[];
+    aes_load_smem(aes_sm, tables);
+    const uint32_t *tl = aes_sm + (threadIdx.x & 31);
+    const uint32_t n = min(*n_cands, cand_cap);
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        const uint2 cd = cands[c];
+        const uint4 lz = aes128_encrypt(tl, lazy_rk + 11 * cd.y, labels[cd.x]);
+        const uint64_t lsb = ((uint64_t)lz.x | ((uint64_t)lz.y << 32)) & 0x00ffffffffffffffull;
+        if (lsb >= diff_lsb) continue;
+        const uint32_t pos = atomicAdd(n_hits, 1u);
+        if (pos < hit_cap) hits[pos] = Hit{cd.y, 0, first_index + cd.x};
     }
 }
 
@@ -68,7 +120,8 @@ class Scanner {
 public:
     ~Scanner() {
         if (dev_ >= 0) cudaSetDevice(dev_);
-        for (int b = 0; b < 2; b++) { cudaFree(d_labels_[b]); cudaFreeHost(h_labels_[b]); if (ev_[b]) cudaEventDestroy(ev_[b]); if (st_[b]) cudaStreamDestroy(st_[b]); cudaFree(d_hits_[b]); cudaFree(d_nhits_[b]); cudaFreeHost(h_hits_[b]); cudaFreeHost(h_nhits_[b]); }
+        cudaFree(d_cands_); cudaFree(d_ncands_);
+        for (int b = 0; b < 2; b++) { cudaFree(d_labels_[b]); cudaFreeHost(h_labels_[b]); if (ev_[b]) cudaEventDestroy(ev_[b]); if (st_[b]) cudaStreamDestroy(st_[b]); cudaFree(d_hits_[b]); cudaFree(d_nhits_[b]); cudaFreeHost(h_hits_[b]); cudaFreeHost(h_nhits_[b]); cudaFreeHost(h_ncands_[b]); }
         cudaFree(d_rk_); cudaFree(d_lazy_); cudaFree(d_tables_);
     }
     int init(uint32_t provider, const uint8_t challenge[32], uint32_t nonces, const uint64_t *pows, uint32_t k1, uint32_t k2,
@@ -117,10 +170,16 @@ public:
             P_TRY(cudaMalloc(&d_nhits_[b], 4));
             P_TRY(cudaMallocHost(&h_hits_[b], (size_t)hit_cap_ * sizeof(Hit)));
             P_TRY(cudaMallocHost(&h_nhits_[b], 4));
+            P_TRY(cudaMallocHost(&h_ncands_[b], 4));
         }
+        // lazy-cipher candidates: one ciphertext byte in 256 equals the MSB; 2x slack, shared by both buffers
+        // (chunks are processed in stream order on alternating streams, so the queue is fenced by events below)
+        cand_cap_ = (uint32_t)std::min<uint64_t>((chunk * nonces) / 128 + 65536, 1u << 27);
+        P_TRY(cudaMalloc(&d_cands_, (size_t)cand_cap_ * sizeof(uint2)));
+        P_TRY(cudaMalloc(&d_ncands_, 8));
         cudaDeviceProp p;
         P_TRY(cudaGetDeviceProperties(&p, dev_));
-        grid_ = (uint32_t)p.multiProcessorCount * 8;
+        grid_ = (uint32_t)p.multiProcessorCount * 6;   // 6 CTAs x 32 KiB of lane-replicated AES table per SM
         return B200POST_OK;
     }
     uint8_t *staging(int b) { return h_labels_[b]; }
@@ -128,11 +187,18 @@ public:
     int submit(int b, uint64_t first, uint32_t count) {
         P_TRY(cudaMemcpyAsync(d_labels_[b], h_labels_[b], (size_t)count * 16, cudaMemcpyHostToDevice, st_[b]));
         P_TRY(cudaMemsetAsync(d_nhits_[b], 0, 4, st_[b]));
-        prove_scan_kernel<<<grid_, 256, 0, st_[b]>>>(reinterpret_cast<const uint4 *>(d_labels_[b]), first, count,
-                                                     reinterpret_cast<const uint4 *>(d_rk_), reinterpret_cast<const uint4 *>(d_lazy_),
-                                                     nonces_ / 16, msb_, lsb_, d_tables_, d_hits_[b], hit_cap_, d_nhits_[b]);
-        g_launches += 1;
+        // the single candidate queue is reused by consecutive chunks: wait for the other stream's lazy pass
+        if (pending_[b ^ 1]) P_TRY(cudaStreamWaitEvent(st_[b], ev_[b ^ 1], 0));
+        P_TRY(cudaMemsetAsync(d_ncands_, 0, 8, st_[b]));
+        prove_scan_kernel<<<grid_, 256, AES_SMEM_BYTES, st_[b]>>>(reinterpret_cast<const uint4 *>(d_labels_[b]), first, count,
+                                                                reinterpret_cast<const uint4 *>(d_rk_), nonces_ / 16, msb_, d_tables_,
+                                                                d_hits_[b], hit_cap_, d_nhits_[b], d_cands_, cand_cap_, d_ncands_);
+        prove_lazy_kernel<<<grid_, 256, AES_SMEM_BYTES, st_[b]>>>(reinterpret_cast<const uint4 *>(d_labels_[b]), first, d_cands_, d_ncands_,
+                                                                cand_cap_, reinterpret_cast<const uint4 *>(d_lazy_), lsb_, d_tables_,
+                                                                d_hits_[b], hit_cap_, d_nhits_[b]);
+        g_launches += 2;
         P_TRY(cudaGetLastError());
+        P_TRY(cudaMemcpyAsync(h_ncands_[b], d_ncands_, 4, cudaMemcpyDeviceToHost, st_[b]));
         P_TRY(cudaMemcpyAsync(h_nhits_[b], d_nhits_[b], 4, cudaMemcpyDeviceToHost, st_[b]));
         P_TRY(cudaMemcpyAsync(h_hits_[b], d_hits_[b], (size_t)hit_cap_ * sizeof(Hit), cudaMemcpyDeviceToHost, st_[b]));
         P_TRY(cudaEventRecord(ev_[b], st_[b]));
@@ -145,7 +211,7 @@ public:
         P_TRY(cudaEventSynchronize(ev_[b]));
         pending_[b] = false;
         const uint32_t n = *h_nhits_[b];
-        if (n > hit_cap_) { set_error("hit buffer overflow: K1 too large for this chunk size"); return B200POST_ERR_OUT_OF_MEMORY; }
+        if (n > hit_cap_ || *h_ncands_[b] > cand_cap_) { set_error("hit buffer overflow: K1 too large for this chunk size"); return B200POST_ERR_OUT_OF_MEMORY; }
         std::vector<Hit> v(h_hits_[b], h_hits_[b] + n);
         std::sort(v.begin(), v.end(), [](const Hit &x, const Hit &y) { return x.index != y.index ? x.index < y.index : x.nonce < y.nonce; });
         for (const Hit &h : v) {
@@ -177,7 +243,10 @@ private:
     cudaEvent_t ev_[2] = {nullptr, nullptr};
     uint8_t *d_labels_[2] = {nullptr, nullptr}, *h_labels_[2] = {nullptr, nullptr};
     Hit *d_hits_[2] = {nullptr, nullptr}, *h_hits_[2] = {nullptr, nullptr};
-    uint32_t *d_nhits_[2] = {nullptr, nullptr}, *h_nhits_[2] = {nullptr, nullptr};
+    uint32_t *d_nhits_[2] = {nullptr, nullptr}, *h_nhits_[2] = {nullptr, nullptr}, *h_ncands_[2] = {nullptr, nullptr};
+    uint2 *d_cands_ = nullptr;
+    uint32_t *d_ncands_ = nullptr;
+    uint32_t cand_cap_ = 0;
     bool pending_[2] = {false, false};
     uint64_t end_[2] = {0, 0};
     std::map<uint32_t, std::vector<uint64_t>> lists_;   // ordered: ties resolve to the lower nonce

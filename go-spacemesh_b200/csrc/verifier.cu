@@ -191,18 +191,19 @@ struct DevJob {            // 384 bytes
 __global__ void __launch_bounds__(256) verify_judge_kernel(const uint4 *__restrict__ labels, const uint32_t *__restrict__ item_job,
                                                            const DevJob *__restrict__ jobs, uint32_t n_items,
                                                            const AesTables *__restrict__ tables, uint32_t *__restrict__ first_bad) {
-    __shared__ AesSmem sm;
-    aes_load_smem(sm, tables);
+    extern __shared__ uint32_t aes_sm[];
+    aes_load_smem(aes_sm, tables);
+    const uint32_t *tl = aes_sm + (threadIdx.x & 31);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_items) return;
     const uint32_t jb = item_job[i];
     const DevJob &j = jobs[jb];
     const uint4 label = labels[i];
-    uint4 out = aes128_encrypt(sm, j.rk, label);
+    uint4 out = aes128_encrypt(tl, j.rk, label);
     const uint32_t msb = uint4_byte(out, j.out_byte);
     bool bad = msb > j.diff_msb;
     if (msb == j.diff_msb) {
-        out = aes128_encrypt(sm, j.lazy_rk, label);
+        out = aes128_encrypt(tl, j.lazy_rk, label);
         const uint64_t lsb = ((uint64_t)out.x | ((uint64_t)out.y << 32)) & 0x00ffffffffffffffull;
         bad = lsb >= j.diff_lsb;
     }
@@ -271,7 +272,7 @@ int gather_and_judge(uint32_t provider, std::vector<Job *> &jobs, uint64_t n, co
     V_TRY(cudaMemset(d_first_bad, 0xff, dj.size() * 4));
     rc = e->labels_gather(indices.size(), commitments.data(), indices.data(), n, nullptr, reinterpret_cast<uint8_t *>(d_labels));
     if (rc != B200POST_OK) goto done;
-    verify_judge_kernel<<<(n_items + 255) / 256, 256>>>(d_labels, d_item_job, d_jobs, n_items, d_tables, d_first_bad);
+    verify_judge_kernel<<<(n_items + 255) / 256, 256, AES_SMEM_BYTES>>>(d_labels, d_item_job, d_jobs, n_items, d_tables, d_first_bad);
     g_launches += 1;
     V_TRY(cudaGetLastError());
     V_TRY(cudaMemcpy(first_bad.data(), d_first_bad, dj.size() * 4, cudaMemcpyDeviceToHost));
