@@ -109,9 +109,9 @@ int DeviceEngine::ensure(uint64_t N, uint64_t want_slots) {
     while (ctas > 1 && per_cta_layer * (size_t)ctas > budget) ctas--;
     uint64_t wave = (uint64_t)prop_.multiProcessorCount * (uint64_t)ctas * (uint64_t)tpb;
     if (per_slot * wave > budget) {
-        // not even one CTA per SM: shrink to what fits, in whole CTAs
-        wave = budget / per_slot / (uint64_t)tpb * (uint64_t)tpb;
-        if (wave == 0) { set_error("not enough HBM for one CTA of ROMix scratch"); return B200POST_ERR_OUT_OF_MEMORY; }
+        // not even one CTA per SM: shrink to what fits, in whole warps (the kernels take any multiple of 32)
+        wave = budget / per_slot / 32 * 32;
+        if (wave == 0) { set_error("not enough HBM for one warp of ROMix scratch"); return B200POST_ERR_OUT_OF_MEMORY; }
     }
     wave_slots_ = (uint32_t)wave;
 

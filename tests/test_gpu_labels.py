@@ -229,3 +229,38 @@ def test_launch_counter_and_timers(b2):
     assert b2.launch_count() - before >= 4        # K0..K3
     ms, k, lab = b2.romix_time()
     assert k >= 1 and ms > 0 and lab == 64 and b2.last_call_ms() > 0
+
+
+def test_small_scratch_budget_still_correct(b2, orc):
+    """With almost no HBM allowed the layer shrinks to a few warps; results must not change
+    (a node sharing the GPU caps the engine with max_scratch_mib)."""
+    c = hashlib.sha256(b"tiny-budget").digest()
+    try:
+        b2.set_option("max_scratch_mib", 160)                 # 80 slots x 2 pads x 1 MiB at N = 8192 -> 64 slots
+        assert b2.wave_slots(8192) == 64
+        got, vrf = b2.labels_range(c, 8192, 2**33, 200, vrf_difficulty_=b"\xff" * 32)
+        exp, found, idx, l32 = orc.c_labels_range(c, 8192, 2**33, 200, b"\xff" * 32)
+        assert (got == exp).all() and vrf == (idx, l32)
+        b2.set_option("max_scratch_mib", 1)
+        with pytest.raises(b2.B200PostError) as e:
+            b2.labels_range(c, 8192, 0, 4)
+        assert e.value.code == b2.ERR_OUT_OF_MEMORY
+    finally:
+        b2.set_option("max_scratch_mib", 0)
+
+
+def test_largest_supported_n(b2, orc):
+    """N = 2^20 (128 MiB per scratchpad) is the documented cap; one label each way."""
+    c = hashlib.sha256(b"big-n").digest()
+    got, _ = b2.labels_range(c, 1 << 20, 7, 2)
+    assert (got == orc.c_labels_range(c, 1 << 20, 7, 2, threads=2)[0]).all()
+
+
+def test_range_multi_over_all_devices(b2, orc, gpu_ready):
+    """b200post_labels_range_multi: contiguous shards over every device of the box, host-side VRF merge."""
+    ids = [p["id"] for p in gpu_ready]
+    c = hashlib.sha256(b"multi-dev").digest()
+    diff = orc.py_vrf_difficulty(256)
+    got, vrf = b2.labels_range_multi(ids, c, 16, 2**32 - 777, 5003, vrf_difficulty_=diff)
+    exp, found, idx, l32 = orc.c_labels_range(c, 16, 2**32 - 777, 5003, diff)
+    assert (got == exp).all() and vrf == ((idx, l32) if found else None)
