@@ -320,7 +320,7 @@ int DeviceEngine::labels_range(const uint8_t commitment[32], uint64_t N, uint64_
         job.d_diff = d_diff_;
     }
     const int status = run_job(job);
-    if (status != B200POST_OK && status != B200POST_ERR_CANCELLED) return status;
+    if (status != B200POST_OK && status != B200POST_ERR_CANCELLED) { quiesce(); return status; }
     if (status == B200POST_OK && vrf_difficulty && vrf) {
         CU_TRY(cudaMemcpyAsync(h_running_, d_running_, sizeof(VrfCandidate), cudaMemcpyDeviceToHost, stream_));
         CU_TRY(cudaStreamSynchronize(stream_));
@@ -352,11 +352,21 @@ int DeviceEngine::labels_gather(size_t n_items, const uint8_t *commitments, cons
     Job job;
     job.gather = true; job.commitments = commitments; job.indices = indices; job.total = n_items; job.N = N;
     job.out_host = out_host; job.out_dev = out_dev;
-    if ((rc = run_job(job))) return rc;
+    if ((rc = run_job(job))) { quiesce(); return rc; }
     CU_TRY(cudaEventRecord(ev_call_[1], stream_));
     CU_TRY(cudaStreamSynchronize(stream_));
     { float ms = 0; if (cudaEventElapsedTime(&ms, ev_call_[0], ev_call_[1]) == cudaSuccess) last_call_ms_ = ms; }
     return B200POST_OK;
+}
+
+// After a failed job: drain the stream and forget every in-flight buffer, so that the next call starts clean
+// (the error text of the failure is preserved).
+void DeviceEngine::quiesce() {
+    const std::string keep = last_error();
+    if (stream_) cudaStreamSynchronize(stream_);
+    cudaGetLastError();
+    for (int b = 0; b < 2; b++) { pend_[b].live = false; k2_pending_[b] = false; in_pending_[b] = false; }
+    set_error(keep);
 }
 
 uint32_t DeviceEngine::wave_slots(uint64_t N) {

@@ -74,6 +74,7 @@ private:
     int finish_layer(const Job &job, uint64_t layer, uint32_t n_valid, const LabelJob &lj);   // K3 (+K4) + D2H + event
     int retire(const Job &job, int buf);
     void harvest(int buf);
+    void quiesce();   // after an error: drain the stream, drop in-flight bookkeeping
 
     int dev_;
     cudaDeviceProp prop_{};
