@@ -264,3 +264,23 @@ def test_range_multi_over_all_devices(b2, orc, gpu_ready):
     got, vrf = b2.labels_range_multi(ids, c, 16, 2**32 - 777, 5003, vrf_difficulty_=diff)
     exp, found, idx, l32 = orc.c_labels_range(c, 16, 2**32 - 777, 5003, diff)
     assert (got == exp).all() and vrf == ((idx, l32) if found else None)
+
+
+def test_multi_layer_gather_and_device_output(b2, orc):
+    """Scattered items and device-resident output across several layers (layer seams, ragged tail, both
+    buffer parities); N = 2 keeps the oracle fast."""
+    torch = pytest.importorskip("torch")
+    wave = b2.wave_slots(2)
+    rng = np.random.default_rng(17)
+    m = 2 * wave + 4321
+    comms = np.repeat(rng.integers(0, 256, (97, 32), dtype=np.uint8), m // 97 + 1, axis=0)[:m]
+    idx = rng.integers(0, 2**40, m, dtype=np.uint64)
+    got = b2.labels_gather(comms, idx, 2)
+    assert (got == orc.c_labels_gather(comms, idx, 2)).all()
+    c = hashlib.sha256(b"dev-multi").digest()
+    count = 3 * wave + 77
+    buf = torch.empty((count, 16), dtype=torch.uint8, device="cuda:0")
+    vrf = b2.labels_range_dev(c, 2, 2**35, count, buf.data_ptr(), vrf_difficulty_=b"\xff" * 32)
+    torch.cuda.synchronize()
+    exp, found, i, l32 = orc.c_labels_range(c, 2, 2**35, count, b"\xff" * 32)
+    assert (buf.cpu().numpy() == exp).all() and vrf == (i, l32)
