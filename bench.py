@@ -326,6 +326,24 @@ def main() -> None:
     if world == 1 and not args.no_verify:
         verify_extra = bench_verify(b2, local_rank)
 
+    # ALU ceiling probe (N = 1 only): the same ROMix arithmetic with no scratchpad traffic ("nomem" variant; its
+    # outputs are not labels).  The label kernel is integer-issue-bound, so this — not the HBM peak — is the
+    # ceiling its instruction stream can reach on this device at this clock.
+    alu_probe = None
+    if world == 1:
+        keep = {k: b2.get_option(k) for k in ("romix_variant", "tpb")}
+        try:
+            b2.set_option("romix_variant", 3); b2.set_option("tpb", 128)
+            slots = b2.wave_slots(N_SCRYPT, provider=local_rank)
+            b2.labels_range(commitment, N_SCRYPT, 0, slots, provider=local_rank, discard=True)
+            b2.romix_time(provider=local_rank, reset=True)
+            b2.labels_range(commitment, N_SCRYPT, slots, 3 * slots, provider=local_rank, discard=True)
+            ms, k, lab = b2.romix_time(provider=local_rank, reset=True)
+            alu_probe = lab / (ms / 1e3)
+        finally:
+            for k_, v_ in keep.items():
+                b2.set_option(k_, v_)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "labels/s", "n_gpus": world, "steps": args.steps,
@@ -343,6 +361,8 @@ def main() -> None:
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "romix_pipe_kernel" if b2.get_option("romix_variant") == 4 else "romix_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+                         "alu_ceiling_labels_per_s": alu_probe,
+                         "frac_of_alu_ceiling": (labels_per_launch / (romix_avg_ms / 1e3) / alu_probe) if alu_probe and romix_avg_ms > 0 else None,
                          "bytes_per_label": BYTES_PER_LABEL, "labels_per_launch": labels_per_launch,
                          "avg_launch_ms": romix_avg_ms, "launches_timed": int(romix_k),
                          "kernel_share_of_step": (romix_ms / calls_ms) if calls_ms else None},
