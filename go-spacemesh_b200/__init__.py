@@ -246,5 +246,16 @@ def wave_slots(n: int = 8192, provider: int = 0) -> int:
     return int(v.value)
 
 
+def metrics_text() -> str:
+    """Counters of the engine in the Prometheus text format (activation/metrics/metrics.go analogue)."""
+    L = lib()
+    L.b200post_metrics_text.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+    L.b200post_metrics_text.restype = ctypes.c_size_t
+    n = L.b200post_metrics_text(None, 0)
+    buf = ctypes.create_string_buffer(n + 1)
+    L.b200post_metrics_text(buf, n + 1)
+    return buf.value.decode()
+
+
 def shutdown() -> None:
     lib().b200post_shutdown()

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/b200post.h"
+#include "metrics.h"
 
 namespace b200post {
 
@@ -337,6 +338,8 @@ int DeviceEngine::labels_range(const uint8_t commitment[32], uint64_t N, uint64_
     CU_TRY(cudaEventRecord(ev_call_[1], stream_));
     CU_TRY(cudaStreamSynchronize(stream_));
     { float ms = 0; if (cudaEventElapsedTime(&ms, ev_call_[0], ev_call_[1]) == cudaSuccess) last_call_ms_ = ms; }
+    metrics().range_calls_total++; metrics().device_ns_total += (uint64_t)(last_call_ms_ * 1e6);
+    if (status == B200POST_OK) metrics().labels_range_total += count;
     if (status == B200POST_ERR_CANCELLED) set_error("cancelled");
     return status;
 }
@@ -356,6 +359,7 @@ int DeviceEngine::labels_gather(size_t n_items, const uint8_t *commitments, cons
     CU_TRY(cudaEventRecord(ev_call_[1], stream_));
     CU_TRY(cudaStreamSynchronize(stream_));
     { float ms = 0; if (cudaEventElapsedTime(&ms, ev_call_[0], ev_call_[1]) == cudaSuccess) last_call_ms_ = ms; }
+    metrics().gather_calls_total++; metrics().labels_gather_total += n_items; metrics().device_ns_total += (uint64_t)(last_call_ms_ * 1e6);
     return B200POST_OK;
 }
 

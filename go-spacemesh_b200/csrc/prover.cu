@@ -18,6 +18,7 @@
 #include "../../include/b200post_prove.h"
 #include "aes_device.cuh"
 #include "engine.h"
+#include "metrics.h"
 #include "proof_common.h"
 
 namespace b200post {
@@ -257,6 +258,7 @@ int finish(const Scanner &sc, uint32_t nonces, const uint64_t *pows, uint64_t nu
     std::vector<uint64_t> idx;
     if (!sc.winner(&nonce, &idx)) { set_error("no proof found: no nonce reached K2 qualifying labels"); return B200POST_ERR_INVALID_PROOF; }
     (void)nonces;
+    metrics().prove_labels_scanned_total += sc.scanned(); metrics().proofs_generated_total++;
     memset(out, 0, sizeof *out);
     out->nonce = nonce; out->pow = pows[nonce / 16]; out->labels_scanned = sc.scanned();
     out->indices_len = b200post_pack_indices(idx.data(), idx.size(), b200post_bits_per_index(num_labels), out->indices, sizeof out->indices);

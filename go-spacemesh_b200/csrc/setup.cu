@@ -20,6 +20,7 @@
 #include "../../include/b200post_setup.h"
 #include "engine.h"
 #include "host_hash.h"
+#include "metrics.h"
 
 using namespace b200post;
 
@@ -308,6 +309,7 @@ int b200post_setup_start_session(b200post_setup_manager *m, const volatile int *
         if (m->state != B200POST_SETUP_PREPARED) { set_error("post session not prepared"); return B200POST_ERR_STATE; }   // post.go:277
         m->state = B200POST_SETUP_IN_PROGRESS;
     }
+    metrics().setup_sessions_total++;
     auto finish = [&](int32_t state, int rc) { std::lock_guard<std::mutex> lk(m->mu); m->state = state; return rc; };
 
     const uint64_t num_labels = m->num_labels, per_file = m->opts.max_file_size / 16, batch = m->opts.compute_batch_size;
@@ -349,6 +351,7 @@ int b200post_setup_start_session(b200post_setup_manager *m, const volatile int *
             rc = b200post_labels_gather(prov, 1, commitment, &pick, m->opts.scrypt_n, ref);
             if (rc) return finish(B200POST_SETUP_ERROR, rc);
             if (memcmp(ref, buf.data() + (pick - written) * 16, 16)) {
+                metrics().setup_label_mismatch_total++;
                 set_error("reference label mismatch at index " + std::to_string(pick));
                 return finish(B200POST_SETUP_ERROR, B200POST_ERR_LABEL_MISMATCH);
             }

@@ -6,6 +6,7 @@
 // does the cheap per-proof bookkeeping around it.  All conventions marked ASSUMED follow the published
 // post-rs v0.7.x verifier from memory and are "parity unpinned" (DESIGN.md §2).
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -17,6 +18,7 @@
 #include "aes_device.cuh"
 #include "engine.h"
 #include "host_hash.h"
+#include "metrics.h"
 #include "proof_common.h"
 
 namespace b200post {
@@ -350,6 +352,7 @@ struct b200post_verifier {
             process(provider, batch, opts);
             lk.lock();
             batches++; proofs += batch.size();
+            metrics().verify_batches_total++;
             for (Job *j : batch) j->done = true;
             cv_done.notify_all();
         }
@@ -377,6 +380,9 @@ int b200post_verifier_verify(b200post_verifier *v, const b200post_proof *proof, 
     Job j;
     j.proof = proof; j.meta = meta; j.params = params;
     if (options) j.opt = *options; else memset(&j.opt, 0, sizeof j.opt);
+    const auto t_begin = std::chrono::steady_clock::now();
+    metrics().verify_waiting++;                       // metrics.PostVerificationQueue.Inc() (post_verifier.go:319)
+    struct Leave { ~Leave() { metrics().verify_waiting--; } } leave;
     {
         std::unique_lock<std::mutex> lk(v->mu);
         if (v->closed) { set_error("verifier is closed"); return B200POST_ERR_CLOSED; }
@@ -389,6 +395,11 @@ int b200post_verifier_verify(b200post_verifier *v, const b200post_proof *proof, 
     else if (j.status == B200POST_ERR_INVALID_PROOF) set_error(j.bad_index == ~0ull ? "invalid k2pow" : "invalid index");
     else if (j.status == B200POST_ERR_INVALID_ARGUMENT) set_error("malformed proof, metadata or options");
     if (invalid_index) *invalid_index = j.bad_index;
+    if (j.status != B200POST_ERR_CLOSED) {
+        metrics().verify_proofs_total++;
+        if (j.status == B200POST_ERR_INVALID_PROOF) metrics().verify_invalid_total++;
+        observe_verify_seconds(std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count());
+    }
     return j.status;
 }
 
@@ -433,7 +444,9 @@ int b200post_verify_batch(uint32_t provider, size_t n, const b200post_proof *pro
         ptrs[i] = &jobs[i];
     }
     process(provider, ptrs, vo);
+    metrics().verify_batches_total++; metrics().verify_proofs_total += n;
     for (size_t i = 0; i < n; i++) {
+        if (jobs[i].status == B200POST_ERR_INVALID_PROOF) metrics().verify_invalid_total++;
         statuses[i] = jobs[i].status;
         if (invalid_indices) invalid_indices[i] = jobs[i].bad_index;
     }

@@ -140,6 +140,11 @@ double b200post_timer_elapsed_ms(uint32_t provider);
 /* Labels one wave holds for scrypt-N on `provider` under the current options (= resident scratchpads). */
 int b200post_wave_slots(uint32_t provider, uint64_t n, uint64_t *slots);
 
+/* Observability: the engine's counters in the Prometheus text exposition format (the reference's metrics for this
+ * path: activation/metrics/metrics.go:40-52 post_verification_waiting_total / post_verification_seconds,
+ * metrics/public/public.go:19-21).  Writes at most cap-1 bytes + NUL; returns the full length needed. */
+size_t b200post_metrics_text(char *buf, size_t cap);
+
 /* Frees scratch and streams of every device (optional; also runs at library unload). */
 void b200post_shutdown(void);
 

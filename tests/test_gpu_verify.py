@@ -239,3 +239,24 @@ def test_device_epilogue_against_oracle_densely(vf, orc, b2):
         assert (st[i] == b2.OK) == ok and (ok or bad[i] == idx), i
         n_ok += ok
     assert 0 < n_ok < n_proofs
+
+
+def test_metrics_follow_the_work(vf, b2, small_space):
+    import re
+    meta, params, proofs = small_space
+    proof, _ = proofs[0]
+
+    def val(name):
+        m = re.search(rf"^{re.escape(name)} (\S+)$", b2.metrics_text(), re.M)
+        return float(m.group(1))
+
+    before = {k: val(k) for k in ("b200post_verify_proofs_total", "b200post_labels_gather_total",
+                                  "b200post_post_verification_seconds_count")}
+    v = vf.PostVerifier()
+    for _ in range(3):
+        v.verify(proof, meta, params)
+    v.close()
+    assert val("b200post_verify_proofs_total") == before["b200post_verify_proofs_total"] + 3
+    assert val("b200post_labels_gather_total") == before["b200post_labels_gather_total"] + 3 * params.k2
+    assert val("b200post_post_verification_seconds_count") == before["b200post_post_verification_seconds_count"] + 3
+    assert val("b200post_post_verification_waiting_total") == 0

@@ -119,3 +119,14 @@ def test_verifier_needs_a_device(b2):
     with pytest.raises(b2.B200PostError) as e:
         vf.PostVerifier()
     assert e.value.code == b2.ERR_NO_DEVICE
+
+
+def test_metrics_text_exposition(b2):
+    """Prometheus text with the reference's POST metric names (activation/metrics/metrics.go:40-52)."""
+    t = b2.metrics_text()
+    for name in ("b200post_labels_range_total", "b200post_post_verification_waiting_total",
+                 'b200post_post_verification_seconds_bucket{le="1"}', 'b200post_post_verification_seconds_bucket{le="512"}',
+                 'b200post_post_verification_seconds_bucket{le="+Inf"}', "b200post_post_verification_seconds_count"):
+        assert name in t
+    for line in t.splitlines():
+        assert line.startswith("#") or len(line.split(" ")) == 2
