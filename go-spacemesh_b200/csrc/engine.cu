@@ -174,8 +174,7 @@ int DeviceEngine::retire(const Job &job, int b) {
     return B200POST_OK;
 }
 
-int DeviceEngine::stage_layer(const Job &job, uint64_t layer, uint32_t n_valid, LabelJob *lj) {
-    const int b = (int)(layer & 1);
+int DeviceEngine::stage_layer(const Job &job, uint64_t layer, int b, uint32_t n_valid, LabelJob *lj) {
     const uint64_t off = layer * (uint64_t)std::min<uint64_t>(wave_slots_, alloc_slots_);
     if (job.gather) {
         if (in_pending_[b]) { CU_TRY(cudaEventSynchronize(ev_in_[b])); in_pending_[b] = false; }
@@ -196,8 +195,7 @@ int DeviceEngine::stage_layer(const Job &job, uint64_t layer, uint32_t n_valid, 
     return B200POST_OK;
 }
 
-int DeviceEngine::finish_layer(const Job &job, uint64_t layer, uint32_t n_valid, const LabelJob &lj) {
-    const int b = (int)(layer & 1);
+int DeviceEngine::finish_layer(const Job &job, uint64_t layer, int b, uint32_t n_valid, const LabelJob &lj) {
     const uint64_t off = layer * (uint64_t)std::min<uint64_t>(wave_slots_, alloc_slots_);
     const uint32_t n_slots = round_up(n_valid, 32);
     uint8_t *d_out = job.out_dev ? job.out_dev + off * 16 : d_out_[b];
@@ -221,6 +219,7 @@ int DeviceEngine::run_job(const Job &job) {
     auto layer_count = [&](uint64_t m) { return (uint32_t)std::min<uint64_t>(S, job.total - m * S); };
 
     if (variant_ != ROMIX_PIPELINED) {
+        spec_.valid = false;
         for (uint64_t m = 0; m < M; m++) {
             if (job.cancel && *job.cancel) { status = B200POST_ERR_CANCELLED; break; }
             const int b = (int)(m & 1);
@@ -228,7 +227,7 @@ int DeviceEngine::run_job(const Job &job) {
             harvest(b);
             const uint32_t n_valid = layer_count(m);
             LabelJob lj;
-            if ((rc_ = stage_layer(job, m, n_valid, &lj))) return rc_;
+            if ((rc_ = stage_layer(job, m, b, n_valid, &lj))) return rc_;
             RomixParams rp;
             rp.V = V_; rp.X = X_[b]; rp.x_stride = alloc_slots_; rp.N = (uint32_t)job.N; rp.n_slots = round_up(n_valid, 32);
             rp.flags = (uint32_t)options().debug_skip_phase.load(); rp.rc = rc;
@@ -237,25 +236,50 @@ int DeviceEngine::run_job(const Job &job) {
             CU_TRY(cudaEventRecord(ev_k2b_[b], stream_));
             k2_pending_[b] = true; k2_labels_[b] = n_valid;
             g_launches += 1;
-            if ((rc_ = finish_layer(job, m, n_valid, lj))) return rc_;
+            if ((rc_ = finish_layer(job, m, b, n_valid, lj))) return rc_;
         }
     } else {
+        // consume a matching speculation: layer 0 of this call was filled by the previous call's last launch
+        const bool resume = !job.gather && spec_.valid && spec_.N == job.N && spec_.next_start == job.start && spec_.slots == S &&
+                            spec_.alloc_slots == alloc_slots_ && spec_.V == V_ && !memcmp(spec_.commitment, cur_commitment_, 32);
+        const int poff = resume ? spec_.parity : 0;
+        spec_.valid = false;
+        const bool speculate = !job.gather && options().speculate_next.load() != 0 && M >= 4 && job.start + job.total + S > job.start + job.total;
+        auto par = [&](uint64_t m) { return (int)((m + (uint64_t)poff) & 1); };
         LabelJob lj[2];
         uint32_t nv[2] = {0, 0};
+        bool spec_filled = false;
         for (uint64_t m = 0; m <= M; m++) {
             if (m < M && job.cancel && *job.cancel) { status = B200POST_ERR_CANCELLED; break; }
-            const int b = (int)(m & 1);
+            const int b = par(m);
             harvest(b);
+            bool fill = false;
+            uint32_t n_fill = 0;
             if (m < M) {
                 if ((rc_ = retire(job, b))) return rc_;   // layer m-2 used this parity's buffers
                 nv[b] = layer_count(m);
-                if ((rc_ = stage_layer(job, m, nv[b], &lj[b]))) return rc_;
+                if (m == 0 && resume) {
+                    lj[b] = LabelJob{d_mid_[0], 0, nullptr, job.start, nv[b]};   // already filled: X_[b] holds its mid-state
+                } else {
+                    if ((rc_ = stage_layer(job, m, b, nv[b], &lj[b]))) return rc_;
+                    fill = true; n_fill = round_up(nv[b], 32);
+                }
+            } else if (speculate && status == B200POST_OK) {
+                // one layer past the end of this call: the next initialize() batch, if it comes
+                if ((rc_ = retire(job, b))) return rc_;
+                LabelJob next;
+                Job after = job;                       // the range that would follow this call: [start + total, ...)
+                after.start = job.start + job.total;
+                if ((rc_ = stage_layer(after, 0, b, (uint32_t)S, &next))) return rc_;
+                fill = true; n_fill = (uint32_t)S; spec_filled = true;
             }
+            const uint32_t n_mix = m >= 1 ? round_up(nv[b ^ 1], 32) : 0;
+            if (n_fill == 0 && n_mix == 0) continue;   // resumed call: nothing to launch for m = 0
             PipeParams pp;
             pp.V = V_; pp.x_stride = alloc_slots_; pp.N = (uint32_t)job.N; pp.rc = rc;
             pp.Xfill = X_[b]; pp.Xmix = X_[b ^ 1];
-            pp.n_fill = m < M ? round_up(nv[b], 32) : 0;
-            pp.n_mix = m >= 1 ? round_up(nv[b ^ 1], 32) : 0;
+            pp.n_fill = n_fill;
+            pp.n_mix = n_mix;
             pp.fill_parity = (uint32_t)b;
             pp.cta_trace = nullptr;
             // diagnostics: B200POST_CTA_TRACE=<file> dumps {start ns, end ns, smid} per CTA of the last steady launch
@@ -271,7 +295,7 @@ int DeviceEngine::run_job(const Job &job) {
             CU_TRY(launch_romix_pipe(mw_, tpb_, dr_unroll_, pp, stream_));
             CU_TRY(cudaEventRecord(ev_k2b_[b], stream_));
             k2_pending_[b] = true;
-            k2_labels_[b] = 0.5 * ((m < M ? nv[b] : 0) + (m >= 1 ? nv[b ^ 1] : 0));
+            k2_labels_[b] = 0.5 * ((fill ? (m < M ? nv[b] : (uint32_t)S) : 0) + (m >= 1 ? nv[b ^ 1] : 0));
             g_launches += 1;
             if (d_trace) {
                 std::vector<unsigned long long> h((size_t)n_cta * 3);
@@ -283,7 +307,12 @@ int DeviceEngine::run_job(const Job &job) {
                     fclose(f);
                 }
             }
-            if (m >= 1 && (rc_ = finish_layer(job, m - 1, nv[b ^ 1], lj[b ^ 1]))) return rc_;
+            if (m >= 1 && (rc_ = finish_layer(job, m - 1, b ^ 1, nv[b ^ 1], lj[b ^ 1]))) return rc_;
+        }
+        if (spec_filled && status == B200POST_OK) {
+            spec_.valid = true; spec_.N = job.N; spec_.next_start = job.start + job.total; spec_.parity = par(M);
+            spec_.slots = (uint32_t)S; spec_.alloc_slots = alloc_slots_; spec_.V = V_;
+            memcpy(spec_.commitment, cur_commitment_, 32);
         }
     }
     for (int b = 0; b < 2; b++) {
@@ -305,6 +334,7 @@ int DeviceEngine::labels_range(const uint8_t commitment[32], uint64_t N, uint64_
     CU_TRY(cudaEventRecord(ev_call_[0], stream_));
 
     // per-call constants: commitment -> HMAC midstates (K0), VRF threshold, running candidate
+    memcpy(cur_commitment_, commitment, 32);
     CU_TRY(cudaMemcpyAsync(d_commit_[0], commitment, 32, cudaMemcpyHostToDevice, stream_));
     CU_TRY(launch_hmac_midstates(d_commit_[0], 1, d_mid_[0], stream_));
     g_launches += 1;
@@ -353,6 +383,7 @@ int DeviceEngine::labels_gather(size_t n_items, const uint8_t *commitments, cons
     if (rc) return rc;
     CU_TRY(cudaEventRecord(ev_call_[0], stream_));
     Job job;
+    spec_.valid = false;   // the scratch is about to be reused
     job.gather = true; job.commitments = commitments; job.indices = indices; job.total = n_items; job.N = N;
     job.out_host = out_host; job.out_dev = out_dev;
     if ((rc = run_job(job))) { quiesce(); return rc; }
@@ -370,6 +401,7 @@ void DeviceEngine::quiesce() {
     if (stream_) cudaStreamSynchronize(stream_);
     cudaGetLastError();
     for (int b = 0; b < 2; b++) { pend_[b].live = false; k2_pending_[b] = false; in_pending_[b] = false; }
+    spec_.valid = false;
     set_error(keep);
 }
 

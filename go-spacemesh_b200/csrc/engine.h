@@ -22,6 +22,7 @@ struct Options {
     std::atomic<int64_t> dr_unroll{4};         // pipelined kernel: Salsa double-rounds unrolled (4) or rolled (1)
     std::atomic<int64_t> ctas_per_sm{0};       // 0 = occupancy maximum
     std::atomic<int64_t> max_scratch_mib{0};   // 0 = 90 % of free HBM
+    std::atomic<int64_t> speculate_next{1};    // pipelined range jobs of >= 4 layers pre-fill the next range's first layer
     std::atomic<int64_t> debug_skip_phase{0};  // diagnostics only (classic variants): bit0 skip fill, bit1 skip mix
 };
 Options &options();
@@ -70,8 +71,9 @@ private:
     int ensure(uint64_t N, uint64_t want_slots);   // (re)allocates scratch; sets wave_slots_
     void release();
     int run_job(const Job &job);
-    int stage_layer(const Job &job, uint64_t layer, uint32_t n_valid, LabelJob *lj);          // inputs + K0 + K1
-    int finish_layer(const Job &job, uint64_t layer, uint32_t n_valid, const LabelJob &lj);   // K3 (+K4) + D2H + event
+    // b = buffer parity of the layer (layer index + parity offset of the call)
+    int stage_layer(const Job &job, uint64_t layer, int b, uint32_t n_valid, LabelJob *lj);          // inputs + K0 + K1
+    int finish_layer(const Job &job, uint64_t layer, int b, uint32_t n_valid, const LabelJob &lj);   // K3 (+K4) + D2H + event
     int retire(const Job &job, int buf);
     void harvest(int buf);
     void quiesce();   // after an error: drain the stream, drop in-flight bookkeeping
@@ -111,6 +113,19 @@ private:
     cudaEvent_t ev_timer_[2] = {nullptr, nullptr};
     double romix_ms_ = 0, romix_labels_ = 0;
     uint64_t romix_launches_ = 0;
+    // Speculative continuation (pipelined range jobs): the launch that mixes the last layer of a call also fills
+    // the first layer of the range that would follow it (start + count ...).  If the next call is exactly that
+    // range (same commitment, N, buffers), it starts with that layer already filled, so back-to-back initialize()
+    // batches run as one uninterrupted software pipeline instead of draining after every call.
+    struct Speculation {
+        bool valid = false;
+        uint8_t commitment[32] = {0};
+        uint64_t N = 0, next_start = 0;
+        int parity = 0;
+        uint32_t slots = 0, alloc_slots = 0;
+        const void *V = nullptr;
+    } spec_;
+    uint8_t cur_commitment_[32] = {0};
     // current tuning
     int variant_ = ROMIX_PIPELINED, mw_ = 0, tpb_ = 512, dr_unroll_ = 4;
 };

@@ -284,3 +284,38 @@ def test_multi_layer_gather_and_device_output(b2, orc):
     torch.cuda.synchronize()
     exp, found, i, l32 = orc.c_labels_range(c, 2, 2**35, count, b"\xff" * 32)
     assert (buf.cpu().numpy() == exp).all() and vrf == (i, l32)
+
+
+def test_back_to_back_batches_resume_the_pipeline(b2, orc):
+    """Consecutive initialize()-style calls continue from the layer the previous call pre-filled (speculative
+    continuation); results must be identical with and without it, whatever the next call turns out to be."""
+    wave = b2.wave_slots(2)
+    c = hashlib.sha256(b"speculate").digest()
+    other = hashlib.sha256(b"someone else").digest()
+    batch = 4 * wave + 1000                       # >= 4 layers arms the speculation; ragged last layer
+    diff = orc.py_vrf_difficulty(10 * batch)
+    plan = [(c, 500, batch), (c, 500 + batch, batch), (c, 500 + 2 * batch, 37),     # continuation, then a tiny continuation
+            (c, 500 + 2 * batch + 37, batch), (other, 500 + 3 * batch + 37, batch),  # continuation; same range, other identity
+            (c, 9, batch), (c, 9 + batch, 5 * wave)]                                  # a jump, then a continuation again
+    try:
+        results = {}
+        for spec in (1, 0):
+            b2.set_option("speculate_next", spec)
+            out = []
+            for (cm, start, count) in plan:
+                got, vrf = b2.labels_range(cm, 2, start, count, vrf_difficulty_=diff)
+                out.append((got, vrf))
+            results[spec] = out
+        for (cm, start, count), (g1, v1), (g0, v0) in zip(plan, results[1], results[0]):
+            exp, found, idx, l32 = orc.c_labels_range(cm, 2, start, count, diff)
+            assert (g1 == exp).all() and (g0 == exp).all()
+            assert v1 == v0 == ((idx, l32) if found else None)
+        # a gather in between must invalidate the pre-filled layer, not corrupt the next range call
+        b2.set_option("speculate_next", 1)
+        b2.labels_range(c, 2, 0, batch, discard=True)
+        comms = np.tile(np.frombuffer(other, dtype=np.uint8), (300, 1)); idx = np.arange(300, dtype=np.uint64) * 977
+        assert (b2.labels_gather(comms, idx, 2) == orc.c_labels_gather(comms, idx, 2)).all()
+        got, _ = b2.labels_range(c, 2, batch, 2000)
+        assert (got == orc.c_labels_range(c, 2, batch, 2000)[0]).all()
+    finally:
+        b2.set_option("speculate_next", 1)
