@@ -166,8 +166,7 @@ void prepare(Job &j, const b200post_verifier_opts &vo) {
         }
         default: j.status = B200POST_ERR_INVALID_ARGUMENT; return;
     }
-    for (uint64_t v : j.check)
-        if (v >= num_labels && false) { /* post-rs does not range-check: the label is simply recomputed */ }
+    // indices >= num_labels are not rejected here: as upstream, the label is simply recomputed and judged
     commitment_bytes(m.node_id, m.commitment_atx_id, j.commitment);
     cipher_key(m.challenge, nonce_group, p.pow, nullptr, j.key);
     cipher_key(m.challenge, nonce_group, p.pow, &p.nonce, j.lazy_key);
