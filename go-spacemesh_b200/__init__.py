@@ -19,7 +19,10 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libb200post.so"
+import os as _os
+
+# B200POST_LIB=<path> loads an alternative build of the library (kernel experiments); default = in-tree build
+LIB_PATH = Path(_os.environ["B200POST_LIB"]) if _os.environ.get("B200POST_LIB") else _HERE / "libb200post.so"
 
 CPU_PROVIDER_ID = 0xFFFFFFFF  # systest/cluster/nodes.go:997 — refused by this library (no CPU path)
 
