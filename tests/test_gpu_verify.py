@@ -260,3 +260,41 @@ def test_metrics_follow_the_work(vf, b2, small_space):
     assert val("b200post_labels_gather_total") == before["b200post_labels_gather_total"] + 3 * params.k2
     assert val("b200post_post_verification_seconds_count") == before["b200post_post_verification_seconds_count"] + 3
     assert val("b200post_post_verification_waiting_total") == 0
+
+
+def test_prioritized_calls_jump_the_queue(vf, orc):
+    """post_verifier_test.go:93-142 (prioritised jobs are taken first): with one proof per GPU batch and a backlog
+    of ordinary calls, a PrioritizedCall() submitted last must not finish last."""
+    import time
+    rng = np.random.default_rng(5)
+    num_labels, k2 = 2**20, 12
+    bits = vf.bits_per_index(num_labels)
+    params = vf.VerifyParams(k1=2**19, k2=k2, scrypt_n=8192)       # every call costs a full N=8192 launch pair
+    meta = vf.ProofMetadata(bytes(32), bytes(32), bytes(32), 1, num_labels)
+
+    def mk():
+        return vf.Proof(0, vf.pack_indices([int(x) for x in rng.integers(0, num_labels, k2)], bits), 0)
+
+    v = vf.PostVerifier(max_batch_proofs=1)
+    order, lock = [], threading.Lock()
+
+    def call(tag, prioritized):
+        try:
+            v.verify(mk(), meta, params, prioritized=prioritized)
+        except vf.ErrInvalidIndex:
+            pass
+        with lock:
+            order.append(tag)
+
+    normal = [threading.Thread(target=call, args=(f"n{i}", False)) for i in range(10)]
+    for t in normal:
+        t.start()
+    time.sleep(0.05)                                                # let the backlog form
+    pr = threading.Thread(target=call, args=("PRIO", True))
+    pr.start()
+    for t in normal + [pr]:
+        t.join()
+    batches, n = v.stats()
+    v.close()
+    assert n == 11 and batches == 11
+    assert order.index("PRIO") <= 5, order
