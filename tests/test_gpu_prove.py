@@ -85,3 +85,50 @@ def test_no_proof_in_a_space_that_is_too_hard(mods, tmp_path, b2):
     with pytest.raises(b2.B200PostError) as e:
         pr.generate_proof(o.data_dir, bytes(32), cfg)
     assert e.value.code == b2.ERR_INVALID_PROOF and "no proof found" in str(e.value)
+
+
+def test_mainnet_shaped_lifecycle_at_n8192(mods, tmp_path, orc, b2):
+    """The whole POST lifecycle at the mainnet scrypt cost and K2: 4 units x 2^20 labels (64 MiB of POST data),
+    N = 8192, K2 = 37, 288 proving nonces — setup session -> proof over the files -> batched verification,
+    with the stored labels spot-checked against the oracle."""
+    su, pr, vf = mods
+    units, lpu, k1, k2 = 4, 1 << 20, 1 << 9, 37
+    cfg = su.PostConfig(labels_per_unit=lpu, k1=k1, k2=k2, k3=k2, max_num_units=8)
+    mgr = su.PostSetupManager(cfg)
+    o = su.PostSetupOpts(data_dir=str(tmp_path / "post"), num_units=units, max_file_size=16 << 20, provider_id=0, scrypt_n=8192,
+                         compute_batch_size=1 << 20)
+    mgr.prepare_initializer(o, NODE, ATX)
+    mgr.start_session()
+    assert mgr.status() == su.PostSetupStatus(su.STATE_COMPLETE, units * lpu)
+    # spot-check the files
+    c = orc.py_commitment(NODE, ATX)
+    pick = np.unique(np.random.default_rng(2).integers(0, units * lpu, 160)).astype(np.uint64)
+    comms = np.tile(np.frombuffer(c, dtype=np.uint8), (len(pick), 1))
+    exp = orc.c_labels_gather(comms, pick, 8192)
+    per_file = (16 << 20) // 16
+    for row, i in zip(exp, pick):
+        with open(f"{o.data_dir}/postdata_{int(i) // per_file}.bin", "rb") as f:
+            f.seek((int(i) % per_file) * 16)
+            assert f.read(16) == row.tobytes()
+    md = su.load_metadata(o.data_dir)
+    assert md["nonce"] is not None and orc.c_label32(c, md["nonce"], 8192) == md["nonce_value"]
+    assert b2.verify_vrf_nonce(md["nonce"], NODE, ATX, units, lpu, 8192)
+    # prove + verify
+    challenge = bytes(range(90, 122))
+    proof, meta, scanned = pr.generate_proof(o.data_dir, challenge, cfg, nonces=288)
+    assert len(proof.indices) == (k2 * vf.bits_per_index(units * lpu) + 7) // 8 and scanned <= units * lpu
+    params = vf.VerifyParams(k1=k1, k2=k2, scrypt_n=8192)
+    v = vf.PostVerifier()
+    try:
+        v.verify(proof, meta, params)                                       # all K2 indices
+        v.verify(proof, meta, params, mode=vf.MODE_SUBSET, k3=1, seed=b"peer")
+        idx = vf.unpack_indices(proof.indices, vf.bits_per_index(units * lpu), k2)
+        bad = list(idx); bad[20] = (bad[20] + 1) % (units * lpu)             # systest: Indices[i] += 1
+        tampered = vf.Proof(proof.nonce, vf.pack_indices(bad, vf.bits_per_index(units * lpu)), proof.pow)
+        ok, which = orc.py_verify(tampered.nonce, tampered.indices, tampered.pow, NODE, ATX, challenge, units, lpu, k1, k2, 8192)
+        if not ok:
+            with pytest.raises(vf.ErrInvalidIndex) as e:
+                v.verify(tampered, meta, params)
+            assert e.value.index == which
+    finally:
+        v.close()
