@@ -58,11 +58,13 @@ void DeviceEngine::release() {
         cudaFreeHost(h_commit_[b]); h_commit_[b] = nullptr;
         cudaFreeHost(h_idx_[b]); h_idx_[b] = nullptr;
         cudaFree(d_mid_[b]); d_mid_[b] = nullptr;
+        cudaFree(d_cidx_[b]); d_cidx_[b] = nullptr; cudaFreeHost(h_cidx_[b]); h_cidx_[b] = nullptr;
         cudaEvent_t *evs[] = {&ev_done_[b], &ev_in_[b], &ev_k2a_[b], &ev_k2b_[b], &ev_call_[b]};
         for (cudaEvent_t *e : evs) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
         k2_pending_[b] = false; in_pending_[b] = false; pend_[b].live = false;
     }
     for (int b = 0; b < 2; b++) { if (ev_timer_[b]) cudaEventDestroy(ev_timer_[b]); ev_timer_[b] = nullptr; }
+    cudaFree(d_ctab_); d_ctab_ = nullptr; cudaFree(d_cmid_); d_cmid_ = nullptr; ctab_rows_ = 0;
     cudaFree(d_diff_); d_diff_ = nullptr;
     cudaFree(d_cta_cand_); d_cta_cand_ = nullptr;
     cudaFree(d_running_); d_running_ = nullptr;
@@ -132,8 +134,9 @@ int DeviceEngine::ensure(uint64_t N, uint64_t want_slots) {
     if (need > alloc_slots_) {
         CU_TRY(cudaStreamSynchronize(stream_));
         for (int b = 0; b < 2; b++) {
-            cudaFree(X_[b]); cudaFree(d_commit_[b]); cudaFree(d_idx_[b]); cudaFree(d_mid_[b]); cudaFree(d_out_[b]);
-            cudaFreeHost(h_commit_[b]); cudaFreeHost(h_idx_[b]); cudaFreeHost(h_out_[b]);
+            cudaFree(X_[b]); cudaFree(d_commit_[b]); cudaFree(d_idx_[b]); cudaFree(d_mid_[b]); cudaFree(d_out_[b]); cudaFree(d_cidx_[b]);
+            cudaFreeHost(h_commit_[b]); cudaFreeHost(h_idx_[b]); cudaFreeHost(h_out_[b]); cudaFreeHost(h_cidx_[b]);
+            d_cidx_[b] = nullptr; h_cidx_[b] = nullptr;
             X_[b] = nullptr; d_commit_[b] = nullptr; d_idx_[b] = nullptr; d_mid_[b] = nullptr; d_out_[b] = nullptr;
             h_commit_[b] = nullptr; h_idx_[b] = nullptr; h_out_[b] = nullptr;
         }
@@ -148,6 +151,8 @@ int DeviceEngine::ensure(uint64_t N, uint64_t want_slots) {
             CU_TRY(cudaMallocHost(&h_commit_[b], (size_t)need * 32));
             CU_TRY(cudaMallocHost(&h_idx_[b], (size_t)need * 8));
             CU_TRY(cudaMallocHost(&h_out_[b], (size_t)need * 16));
+            CU_TRY(cudaMalloc(&d_cidx_[b], (size_t)need * 4));
+            CU_TRY(cudaMallocHost(&h_cidx_[b], (size_t)need * 4));
         }
         CU_TRY(cudaMalloc(&d_cta_cand_, (size_t)pbkdf2_final_ctas(need) * sizeof(VrfCandidate)));
         alloc_slots_ = need;
@@ -176,7 +181,16 @@ int DeviceEngine::retire(const Job &job, int b) {
 
 int DeviceEngine::stage_layer(const Job &job, uint64_t layer, int b, uint32_t n_valid, LabelJob *lj) {
     const uint64_t off = layer * (uint64_t)std::min<uint64_t>(wave_slots_, alloc_slots_);
-    if (job.gather) {
+    if (job.gather && job.commit_index) {
+        if (in_pending_[b]) { CU_TRY(cudaEventSynchronize(ev_in_[b])); in_pending_[b] = false; }
+        memcpy(h_cidx_[b], job.commit_index + off, (size_t)n_valid * 4);
+        memcpy(h_idx_[b], job.indices + off, (size_t)n_valid * 8);
+        CU_TRY(cudaMemcpyAsync(d_cidx_[b], h_cidx_[b], (size_t)n_valid * 4, cudaMemcpyHostToDevice, stream_));
+        CU_TRY(cudaMemcpyAsync(d_idx_[b], h_idx_[b], (size_t)n_valid * 8, cudaMemcpyHostToDevice, stream_));
+        CU_TRY(cudaEventRecord(ev_in_[b], stream_));
+        in_pending_[b] = true;
+        *lj = LabelJob{d_cmid_, 0, d_idx_[b], 0, n_valid, d_cidx_[b]};
+    } else if (job.gather) {
         if (in_pending_[b]) { CU_TRY(cudaEventSynchronize(ev_in_[b])); in_pending_[b] = false; }
         memcpy(h_commit_[b], job.commitments + off * 32, (size_t)n_valid * 32);
         memcpy(h_idx_[b], job.indices + off, (size_t)n_valid * 8);
@@ -186,9 +200,9 @@ int DeviceEngine::stage_layer(const Job &job, uint64_t layer, int b, uint32_t n_
         in_pending_[b] = true;
         CU_TRY(launch_hmac_midstates(d_commit_[b], n_valid, d_mid_[b], stream_));
         g_launches += 1;
-        *lj = LabelJob{d_mid_[b], 16, d_idx_[b], 0, n_valid};
+        *lj = LabelJob{d_mid_[b], 16, d_idx_[b], 0, n_valid, nullptr};
     } else {
-        *lj = LabelJob{d_mid_[0], 0, nullptr, job.start + off, n_valid};
+        *lj = LabelJob{d_mid_[0], 0, nullptr, job.start + off, n_valid, nullptr};
     }
     CU_TRY(launch_pbkdf2_expand(*lj, X_[b], alloc_slots_, round_up(n_valid, 32), stream_));
     g_launches += 1;
@@ -259,7 +273,7 @@ int DeviceEngine::run_job(const Job &job) {
                 if ((rc_ = retire(job, b))) return rc_;   // layer m-2 used this parity's buffers
                 nv[b] = layer_count(m);
                 if (m == 0 && resume) {
-                    lj[b] = LabelJob{d_mid_[0], 0, nullptr, job.start, nv[b]};   // already filled: X_[b] holds its mid-state
+                    lj[b] = LabelJob{d_mid_[0], 0, nullptr, job.start, nv[b], nullptr};   // already filled: X_[b] holds its mid-state
                 } else {
                     if ((rc_ = stage_layer(job, m, b, nv[b], &lj[b]))) return rc_;
                     fill = true; n_fill = round_up(nv[b], 32);
@@ -403,6 +417,36 @@ void DeviceEngine::quiesce() {
     for (int b = 0; b < 2; b++) { pend_[b].live = false; k2_pending_[b] = false; in_pending_[b] = false; }
     spec_.valid = false;
     set_error(keep);
+}
+
+int DeviceEngine::labels_gather_indexed(size_t n_items, size_t n_commit, const uint8_t *commitments, const uint32_t *commit_index,
+                                        const uint64_t *indices, uint64_t N, uint8_t *out_host, uint8_t *out_dev) {
+    std::lock_guard<std::mutex> lk(mu_);
+    CU_TRY(cudaSetDevice(dev_));
+    if (n_items == 0) return B200POST_OK;
+    int rc = ensure(N, n_items);
+    if (rc) return rc;
+    if (n_commit > ctab_rows_) {
+        CU_TRY(cudaStreamSynchronize(stream_));
+        cudaFree(d_ctab_); cudaFree(d_cmid_); d_ctab_ = nullptr; d_cmid_ = nullptr; ctab_rows_ = 0;
+        CU_TRY(cudaMalloc(&d_ctab_, n_commit * 32));
+        CU_TRY(cudaMalloc(&d_cmid_, n_commit * 64));
+        ctab_rows_ = n_commit;
+    }
+    CU_TRY(cudaEventRecord(ev_call_[0], stream_));
+    CU_TRY(cudaMemcpyAsync(d_ctab_, commitments, n_commit * 32, cudaMemcpyHostToDevice, stream_));
+    CU_TRY(launch_hmac_midstates(d_ctab_, (uint32_t)n_commit, d_cmid_, stream_));
+    g_launches += 1;
+    spec_.valid = false;   // the scratch is about to be reused
+    Job job;
+    job.gather = true; job.commit_index = commit_index; job.indices = indices; job.total = n_items; job.N = N;
+    job.out_host = out_host; job.out_dev = out_dev;
+    if ((rc = run_job(job))) { quiesce(); return rc; }
+    CU_TRY(cudaEventRecord(ev_call_[1], stream_));
+    CU_TRY(cudaStreamSynchronize(stream_));
+    { float ms = 0; if (cudaEventElapsedTime(&ms, ev_call_[0], ev_call_[1]) == cudaSuccess) last_call_ms_ = ms; }
+    metrics().gather_calls_total++; metrics().labels_gather_total += n_items; metrics().device_ns_total += (uint64_t)(last_call_ms_ * 1e6);
+    return B200POST_OK;
 }
 
 uint32_t DeviceEngine::wave_slots(uint64_t N) {

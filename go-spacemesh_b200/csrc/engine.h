@@ -46,6 +46,10 @@ public:
     // out_dev (optional): device buffer of n_items*16 bytes on this device; the labels then never leave HBM
     int labels_gather(size_t n_items, const uint8_t *commitments, const uint64_t *indices, uint64_t N, uint8_t *out_host,
                       uint8_t *out_dev = nullptr);
+    // same with the commitments given once (n_commit x 32 bytes) and a per-item row index into them: the verify
+    // path recomputes ~37 labels per identity, so midstates and H2D shrink by that factor
+    int labels_gather_indexed(size_t n_items, size_t n_commit, const uint8_t *commitments, const uint32_t *commit_index,
+                              const uint64_t *indices, uint64_t N, uint8_t *out_host, uint8_t *out_dev);
     // accumulated ROMix kernel device time, launches, and label-equivalents processed by those launches
     void romix_time(double *ms_total, uint64_t *launches, double *labels, bool reset);
     // device time (CUDA events on the engine's stream) of the last labels_range / labels_gather call
@@ -63,6 +67,7 @@ private:
         bool gather = false;
         const uint8_t *commitments = nullptr;   // gather: n x 32 (host)
         const uint64_t *indices = nullptr;      // gather: n (host)
+        const uint32_t *commit_index = nullptr; // indexed gather: per-item row of the call-level midstate table
         uint64_t start = 0, total = 0, N = 0;
         uint8_t *out_host = nullptr, *out_dev = nullptr;
         const uint32_t *d_diff = nullptr;
@@ -97,6 +102,8 @@ private:
     uint8_t *h_commit_[2] = {nullptr, nullptr};    // pinned staging for gather inputs
     uint64_t *h_idx_[2] = {nullptr, nullptr};
     uint32_t *d_mid_[2] = {nullptr, nullptr};
+    uint32_t *d_cidx_[2] = {nullptr, nullptr}, *h_cidx_[2] = {nullptr, nullptr};   // indexed gather: per-item commitment rows
+    uint8_t *d_ctab_ = nullptr; uint32_t *d_cmid_ = nullptr; size_t ctab_rows_ = 0;  // call-level commitment / midstate table
     uint32_t *d_diff_ = nullptr;
     VrfCandidate *d_cta_cand_ = nullptr;
     VrfCandidate *d_running_ = nullptr;

@@ -108,7 +108,7 @@ __global__ void hmac_midstates_kernel(const uint8_t *__restrict__ commitments, u
 }
 
 __device__ __forceinline__ void load_mid(const LabelJob &job, uint32_t slot, HmacMid &m) {
-    const uint32_t *p = job.mid + (size_t)job.mid_stride * slot;
+    const uint32_t *p = job.mid_index ? job.mid + 16 * (size_t)job.mid_index[slot] : job.mid + (size_t)job.mid_stride * slot;
 #pragma unroll
     for (int k = 0; k < 8; k++) { m.inner[k] = p[k]; m.outer[k] = p[8 + k]; }
 }

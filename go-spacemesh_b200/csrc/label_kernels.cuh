@@ -57,6 +57,7 @@ struct LabelJob {
     const uint64_t *indices;    // nullptr => index = start + slot
     uint64_t start;
     uint32_t n_valid;           // slots that correspond to requested labels (<= n_slots)
+    const uint32_t *mid_index;  // optional: per-slot row of `mid` (many items sharing few commitments); overrides mid_stride
 };
 
 struct VrfCandidate {           // 48 bytes

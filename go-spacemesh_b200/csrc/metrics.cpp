@@ -39,6 +39,8 @@ extern "C" size_t b200post_metrics_text(char *buf, size_t cap) {
     line("b200post_verify_proofs_total", "proofs verified", "counter", m.verify_proofs_total);
     line("b200post_verify_invalid_total", "proofs rejected with an invalid index or pow", "counter", m.verify_invalid_total);
     line("b200post_verify_batches_total", "GPU batches dispatched by the verifier", "counter", m.verify_batches_total);
+    line("b200post_verify_prepare_us_total", "host time spent unpacking indices and deriving keys (wall, microseconds)", "counter", m.verify_prepare_us_total);
+    line("b200post_verify_gather_judge_us_total", "time spent in the label gather and the judge kernel incl. copies (wall, microseconds)", "counter", m.verify_gather_judge_us_total);
     o += "# HELP b200post_post_verification_seconds Verify latency (post_verification_seconds)\n# TYPE b200post_post_verification_seconds histogram\n";
     double bound = 1.0;
     for (int k = 0; k < 10; k++, bound *= 2)

@@ -13,6 +13,7 @@ struct Metrics {
     std::atomic<uint64_t> range_calls_total{0}, gather_calls_total{0};
     std::atomic<uint64_t> device_ns_total{0};         // device time of all label calls (CUDA events), ns
     std::atomic<uint64_t> verify_proofs_total{0}, verify_invalid_total{0}, verify_batches_total{0};
+    std::atomic<uint64_t> verify_prepare_us_total{0}, verify_gather_judge_us_total{0};   // host unpack/key stage, device stage (wall)
     std::atomic<int64_t> verify_waiting{0};           // PostVerificationQueue gauge: callers inside Verify()
     // PostVerificationLatency: cumulative histogram, upper bounds 1 s x 2^k (k = 0..9), last = +Inf
     std::atomic<uint64_t> verify_seconds_bucket[11];

@@ -10,6 +10,7 @@
 #include <condition_variable>
 #include <cstring>
 #include <deque>
+#include <map>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -227,85 +228,119 @@ void parallel_for(size_t n, F fn) {
         cudaError_t e__ = (expr);                                                     \
         if (e__ != cudaSuccess) {                                                     \
             set_error(std::string(#expr) + ": " + cudaGetErrorString(e__));           \
-            rc = e__ == cudaErrorMemoryAllocation ? B200POST_ERR_OUT_OF_MEMORY : B200POST_ERR_CUDA; \
-            goto done;                                                                \
+            return e__ == cudaErrorMemoryAllocation ? B200POST_ERR_OUT_OF_MEMORY : B200POST_ERR_CUDA; \
         }                                                                             \
     } while (0)
 
 // Recompute the labels of all OK jobs with scrypt-N `n` (gather kernels, labels stay in HBM) and run the
 // device epilogue.  first_bad[k] = position of the first failing label of the k-th such job, or 0xffffffff.
-int gather_and_judge(uint32_t provider, std::vector<Job *> &jobs, uint64_t n, const std::vector<uint8_t> &commitments,
-                     const std::vector<uint64_t> &indices, std::vector<uint32_t> &first_bad) {
+// grow-only device buffers of the judge stage, one set per provider: a batch costs no cudaMalloc/cudaFree once warm
+struct JudgeScratch {
+    std::mutex mu;
+    uint4 *labels = nullptr; uint32_t *item_job = nullptr, *first_bad = nullptr; DevJob *jobs = nullptr; AesTables *tables = nullptr;
+    size_t cap_items = 0, cap_jobs = 0;
+    int reserve(size_t n_items, size_t n_jobs, const AesTables &host_tables) {
+        if (!tables) {
+            if (cudaMalloc(&tables, sizeof(AesTables)) != cudaSuccess) return B200POST_ERR_CUDA;
+            if (cudaMemcpy(tables, &host_tables, sizeof(AesTables), cudaMemcpyHostToDevice) != cudaSuccess) return B200POST_ERR_CUDA;
+        }
+        if (n_items > cap_items) {
+            cudaFree(labels); cudaFree(item_job); labels = nullptr; item_job = nullptr; cap_items = 0;
+            const size_t c = n_items + n_items / 4;
+            if (cudaMalloc(&labels, c * 16) != cudaSuccess || cudaMalloc(&item_job, c * 4) != cudaSuccess) return B200POST_ERR_OUT_OF_MEMORY;
+            cap_items = c;
+        }
+        if (n_jobs > cap_jobs) {
+            cudaFree(jobs); cudaFree(first_bad); jobs = nullptr; first_bad = nullptr; cap_jobs = 0;
+            const size_t c = n_jobs + n_jobs / 4;
+            if (cudaMalloc(&jobs, c * sizeof(DevJob)) != cudaSuccess || cudaMalloc(&first_bad, c * 4) != cudaSuccess) return B200POST_ERR_OUT_OF_MEMORY;
+            cap_jobs = c;
+        }
+        return B200POST_OK;
+    }
+};
+JudgeScratch &judge_scratch(uint32_t provider) {
+    static std::mutex mu;
+    static std::map<uint32_t, JudgeScratch *> *all = new std::map<uint32_t, JudgeScratch *>;   // never destroyed: the CUDA context may be gone at exit
+    std::lock_guard<std::mutex> lk(mu);
+    JudgeScratch *&s = (*all)[provider];
+    if (!s) s = new JudgeScratch;
+    return *s;
+}
+
+// `indices` holds every checked label index of the batch, job after job (Job::first_item); each job's commitment is
+// uploaded once and items refer to it by row (DeviceEngine::labels_gather_indexed).
+int gather_and_judge(uint32_t provider, std::vector<Job *> &jobs, uint64_t n, const std::vector<uint64_t> &indices,
+                     std::vector<uint32_t> &first_bad) {
     DeviceEngine *e = engine_for(provider);
     if (!e) return B200POST_ERR_NO_DEVICE;
-    std::vector<DevJob> dj;
+    std::vector<Job *> live;
+    for (Job *j : jobs) if (j->status == B200POST_OK && j->params->scrypt_n == n) live.push_back(j);
+    std::vector<DevJob> dj(live.size());
+    std::vector<uint8_t> commitments(live.size() * 32);
     std::vector<uint32_t> item_job(indices.size());
-    for (Job *j : jobs) {
-        if (j->status != B200POST_OK || j->params->scrypt_n != n) continue;
-        DevJob d;
+    parallel_for(live.size(), [&](size_t i) {
+        Job *j = live[i];
+        DevJob &d = dj[i];
         memset(&d, 0, sizeof d);
         const Aes128 a(j->key), l(j->lazy_key);
         memcpy(d.rk, a.rk, sizeof d.rk);
         memcpy(d.lazy_rk, l.rk, sizeof d.lazy_rk);
         d.first_item = (uint32_t)j->first_item; d.n_items = (uint32_t)j->check.size();
         d.out_byte = j->out_byte; d.diff_msb = j->diff_msb; d.diff_lsb = j->diff_lsb;
-        for (size_t k = 0; k < j->check.size(); k++) item_job[j->first_item + k] = (uint32_t)dj.size();
-        dj.push_back(d);
-    }
+        memcpy(&commitments[i * 32], j->commitment, 32);
+        for (size_t k = 0; k < j->check.size(); k++) item_job[j->first_item + k] = (uint32_t)i;
+    });
     first_bad.assign(dj.size(), 0xffffffffu);
     if (indices.empty()) return B200POST_OK;
     static AesTables host_tables;
     static std::once_flag once;
     std::call_once(once, [] { aes_build_tables(host_tables); });
 
-    int rc = B200POST_OK;
-    uint4 *d_labels = nullptr; uint32_t *d_item_job = nullptr, *d_first_bad = nullptr; DevJob *d_jobs = nullptr; AesTables *d_tables = nullptr;
     const uint32_t n_items = (uint32_t)indices.size();
     V_TRY(cudaSetDevice(e->device()));
-    V_TRY(cudaMalloc(&d_labels, (size_t)n_items * 16));
-    V_TRY(cudaMalloc(&d_item_job, (size_t)n_items * 4));
-    V_TRY(cudaMalloc(&d_jobs, dj.size() * sizeof(DevJob)));
-    V_TRY(cudaMalloc(&d_first_bad, dj.size() * 4));
-    V_TRY(cudaMalloc(&d_tables, sizeof(AesTables)));
-    V_TRY(cudaMemcpy(d_item_job, item_job.data(), (size_t)n_items * 4, cudaMemcpyHostToDevice));
-    V_TRY(cudaMemcpy(d_jobs, dj.data(), dj.size() * sizeof(DevJob), cudaMemcpyHostToDevice));
-    V_TRY(cudaMemcpy(d_tables, &host_tables, sizeof(AesTables), cudaMemcpyHostToDevice));
-    V_TRY(cudaMemset(d_first_bad, 0xff, dj.size() * 4));
-    rc = e->labels_gather(indices.size(), commitments.data(), indices.data(), n, nullptr, reinterpret_cast<uint8_t *>(d_labels));
-    if (rc != B200POST_OK) goto done;
-    verify_judge_kernel<<<(n_items + 255) / 256, 256, AES_SMEM_BYTES>>>(d_labels, d_item_job, d_jobs, n_items, d_tables, d_first_bad);
+    JudgeScratch &s = judge_scratch(provider);
+    std::lock_guard<std::mutex> lk(s.mu);
+    int rc = s.reserve(n_items, dj.size(), host_tables);
+    if (rc != B200POST_OK) return rc;
+    V_TRY(cudaMemcpy(s.item_job, item_job.data(), (size_t)n_items * 4, cudaMemcpyHostToDevice));
+    V_TRY(cudaMemcpy(s.jobs, dj.data(), dj.size() * sizeof(DevJob), cudaMemcpyHostToDevice));
+    V_TRY(cudaMemset(s.first_bad, 0xff, dj.size() * 4));
+    rc = e->labels_gather_indexed(indices.size(), dj.size(), commitments.data(), item_job.data(), indices.data(), n, nullptr,
+                                  reinterpret_cast<uint8_t *>(s.labels));
+    if (rc != B200POST_OK) return rc;
+    verify_judge_kernel<<<(n_items + 255) / 256, 256, AES_SMEM_BYTES>>>(s.labels, s.item_job, s.jobs, n_items, s.tables, s.first_bad);
     g_launches += 1;
     V_TRY(cudaGetLastError());
-    V_TRY(cudaMemcpy(first_bad.data(), d_first_bad, dj.size() * 4, cudaMemcpyDeviceToHost));
-done:
-    cudaFree(d_labels); cudaFree(d_item_job); cudaFree(d_jobs); cudaFree(d_first_bad); cudaFree(d_tables);
-    return rc;
+    V_TRY(cudaMemcpy(first_bad.data(), s.first_bad, dj.size() * 4, cudaMemcpyDeviceToHost));
+    return B200POST_OK;
 }
 
 // One GPU batch: jobs may use different scrypt N; group by N (in practice a single value).
 int process(uint32_t provider, std::vector<Job *> &jobs, const b200post_verifier_opts &vo) {
+    const auto t0 = std::chrono::steady_clock::now();
     if (vo.pow_verify) { for (Job *j : jobs) prepare(*j, vo); }   // the callback's thread-safety is the caller's business
     else parallel_for(jobs.size(), [&](size_t i) { prepare(*jobs[i], vo); });
+    const auto t1 = std::chrono::steady_clock::now();
+    metrics().verify_prepare_us_total += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+    struct Stage { std::chrono::steady_clock::time_point from; ~Stage() {
+        metrics().verify_gather_judge_us_total += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - from).count(); } } stage{t1};
     std::vector<uint64_t> ns;
     for (Job *j : jobs)
         if (j->status == B200POST_OK && std::find(ns.begin(), ns.end(), j->params->scrypt_n) == ns.end()) ns.push_back(j->params->scrypt_n);
     for (uint64_t n : ns) {
-        std::vector<uint8_t> commitments;
         std::vector<uint64_t> indices;
         size_t total = 0;
         for (Job *j : jobs) if (j->status == B200POST_OK && j->params->scrypt_n == n) total += j->check.size();
-        commitments.reserve(total * 32); indices.reserve(total);
+        indices.reserve(total);
         for (Job *j : jobs) {
             if (j->status != B200POST_OK || j->params->scrypt_n != n) continue;
             j->first_item = indices.size();
-            for (uint64_t idx : j->check) {
-                commitments.insert(commitments.end(), j->commitment, j->commitment + 32);
-                indices.push_back(idx);
-            }
+            indices.insert(indices.end(), j->check.begin(), j->check.end());
         }
         int rc = B200POST_ERR_INVALID_ARGUMENT;
         std::vector<uint32_t> first_bad;
-        if (n >= 2 && n <= (1ull << 20) && (n & (n - 1)) == 0) rc = gather_and_judge(provider, jobs, n, commitments, indices, first_bad);
+        if (n >= 2 && n <= (1ull << 20) && (n & (n - 1)) == 0) rc = gather_and_judge(provider, jobs, n, indices, first_bad);
         size_t k = 0;
         for (Job *j : jobs) {
             if (j->status != B200POST_OK || j->params->scrypt_n != n) continue;
