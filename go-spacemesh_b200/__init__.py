@@ -81,6 +81,7 @@ def lib() -> ctypes.CDLL:
     L.b200post_labels_range_multi.argtypes = [ctypes.POINTER(u32), ctypes.c_int, u8p, u64, u64, u64, vp, vp,
                                               ctypes.POINTER(VrfNonce), vp]
     L.b200post_labels_gather.argtypes = [u32, ctypes.c_size_t, vp, vp, u64, vp]
+    L.b200post_labels_gather_indexed.argtypes = [u32, ctypes.c_size_t, ctypes.c_size_t, vp, vp, vp, u64, vp]
     L.b200post_commitment.argtypes = [u8p, u8p, vp]
     L.b200post_commitment.restype = None
     L.b200post_vrf_difficulty.argtypes = [u64, vp]
@@ -198,6 +199,20 @@ def labels_gather(commitments: np.ndarray, indices: np.ndarray, n: int, *, provi
     out = np.empty((indices.shape[0], 16), dtype=np.uint8)
     _check(lib().b200post_labels_gather(provider, indices.shape[0], commitments.ctypes.data, indices.ctypes.data, n,
                                         out.ctypes.data))
+    return out
+
+
+def labels_gather_indexed(commitments: np.ndarray, commitment_index: np.ndarray, indices: np.ndarray, n: int, *,
+                          provider: int = 0) -> np.ndarray:
+    """labels_gather for items sharing few commitments: item i uses commitments[commitment_index[i]]."""
+    commitments = np.ascontiguousarray(commitments, dtype=np.uint8).reshape(-1, 32)
+    commitment_index = np.ascontiguousarray(commitment_index, dtype=np.uint32)
+    indices = np.ascontiguousarray(indices, dtype=np.uint64)
+    if commitment_index.shape[0] != indices.shape[0]:
+        raise ValueError("commitment_index and indices differ in length")
+    out = np.empty((indices.shape[0], 16), dtype=np.uint8)
+    _check(lib().b200post_labels_gather_indexed(provider, indices.shape[0], commitments.shape[0], commitments.ctypes.data,
+                                                commitment_index.ctypes.data, indices.ctypes.data, n, out.ctypes.data))
     return out
 
 

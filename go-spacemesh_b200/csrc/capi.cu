@@ -160,6 +160,21 @@ int b200post_labels_gather(uint32_t provider, size_t n_items, const uint8_t *com
     return e->labels_gather(n_items, commitments, indices, n, out16);
 }
 
+int b200post_labels_gather_indexed(uint32_t provider, size_t n_items, size_t n_commitments, const uint8_t *commitments,
+                                   const uint32_t *commitment_index, const uint64_t *indices, uint64_t n, uint8_t *out16) {
+    if (!valid_n(n) || (n_items && (!commitments || !commitment_index || !indices || !out16 || !n_commitments)) ||
+        n_commitments > 0xffffffffull) {
+        set_error("invalid argument");
+        return B200POST_ERR_INVALID_ARGUMENT;
+    }
+    for (size_t i = 0; i < n_items; i++)
+        if (commitment_index[i] >= n_commitments) { set_error("commitment_index out of range"); return B200POST_ERR_INVALID_ARGUMENT; }
+    if (provider == B200POST_CPU_PROVIDER_ID) { engine_for(provider); return B200POST_ERR_UNSUPPORTED; }
+    DeviceEngine *e = engine_for(provider);
+    if (!e) return B200POST_ERR_NO_DEVICE;
+    return e->labels_gather_indexed(n_items, n_commitments, commitments, commitment_index, indices, n, out16, nullptr);
+}
+
 void b200post_commitment(const uint8_t node_id[32], const uint8_t commitment_atx_id[32], uint8_t out[32]) {
     commitment_bytes(node_id, commitment_atx_id, out);
 }

@@ -151,6 +151,26 @@ func LabelsGather(provider uint32, commitments []byte, indices []uint64, scryptN
 	return out, statusErr(rc)
 }
 
+// LabelsGatherIndexed is LabelsGather for items that share few commitments (one identity checked at K2
+// indices): commitments is m x 32 bytes and item i uses row rows[i].
+func LabelsGatherIndexed(provider uint32, commitments []byte, rows []uint32, indices []uint64, scryptN uint64) ([]byte, error) {
+	n := len(indices)
+	if len(rows) != n || len(commitments)%32 != 0 {
+		return nil, errors.New("b200post: one row per index and 32 bytes per commitment")
+	}
+	out := make([]byte, 16*n)
+	if n == 0 {
+		return out, nil
+	}
+	if len(commitments) == 0 {
+		return nil, errors.New("b200post: no commitments")
+	}
+	rc := C.b200post_labels_gather_indexed(C.uint32_t(provider), C.size_t(n), C.size_t(len(commitments)/32),
+		(*C.uint8_t)(unsafe.Pointer(&commitments[0])), (*C.uint32_t)(unsafe.Pointer(&rows[0])),
+		(*C.uint64_t)(unsafe.Pointer(&indices[0])), C.uint64_t(scryptN), (*C.uint8_t)(unsafe.Pointer(&out[0])))
+	return out, statusErr(rc)
+}
+
 // VerifyVRFNonce is the drop-in for verifying.VerifyVRFNonce (activation/validation.go:277).
 func VerifyVRFNonce(provider uint32, nonce uint64, nodeID, commitmentAtxID []byte, numUnits uint32, labelsPerUnit, scryptN uint64) (bool, error) {
 	var valid C.int

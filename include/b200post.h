@@ -108,6 +108,13 @@ int b200post_labels_range_multi(const uint32_t *providers, int n_providers, cons
 int b200post_labels_gather(uint32_t provider, size_t n_items, const uint8_t *commitments,
                            const uint64_t *indices, uint64_t n, uint8_t *out16);
 
+/* Same for items that share few commitments (one identity checked at K2 indices): commitments =
+ * n_commitments x 32 bytes (HOST), commitment_index = n_items u32 rows into it (HOST, each < n_commitments).
+ * Midstates are derived once per commitment and 4 instead of 32 bytes per item cross PCIe. */
+int b200post_labels_gather_indexed(uint32_t provider, size_t n_items, size_t n_commitments, const uint8_t *commitments,
+                                   const uint32_t *commitment_index, const uint64_t *indices, uint64_t n,
+                                   uint8_t *out16);
+
 /* commitment = blake3(node_id || commitment_atx_id)  (hash/hash.go:16-25 primitive). */
 void b200post_commitment(const uint8_t node_id[32], const uint8_t commitment_atx_id[32], uint8_t out[32]);
 

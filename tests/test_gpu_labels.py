@@ -126,6 +126,23 @@ def test_gather_distinct_commitments(b2, orc):
         assert (got == orc.c_labels_gather(comms[:k], idx[:k], n)).all()
 
 
+def test_gather_indexed_matches_plain_gather(b2, orc):
+    """Items sharing few commitments (the verify shape: K2 indices per identity), several layers at N = 2 and a
+    ragged batch at the network N; argument checks."""
+    rng = np.random.default_rng(11)
+    for n, items, ncomm in ((2, 3 * b2.wave_slots(2) + 77, 1000), (8192, 37 * 9 + 5, 10)):
+        table = rng.integers(0, 256, (ncomm, 32), dtype=np.uint8)
+        rows = rng.integers(0, ncomm, items, dtype=np.uint32)
+        idx = rng.integers(0, 2**40, items, dtype=np.uint64)
+        got = b2.labels_gather_indexed(table, rows, idx, n)
+        if n == 2:
+            assert (got == orc.c_labels_gather(table[rows], idx, n)).all()
+        assert (got == b2.labels_gather(table[rows], idx, n)).all()
+    with pytest.raises(b2.B200PostError):
+        b2.labels_gather_indexed(table, np.array([ncomm], dtype=np.uint32), np.array([1], dtype=np.uint64), 8192)
+    assert b2.labels_gather_indexed(table, np.zeros(0, np.uint32), np.zeros(0, np.uint64), 8192).shape == (0, 16)
+
+
 def test_vrf_min_and_tie_break(b2, orc):
     """With difficulty = 0xff..ff the scan returns the global minimum; the lowest index wins ties
     (same label can only repeat for the same index, so ties are exercised through overlapping calls)."""
