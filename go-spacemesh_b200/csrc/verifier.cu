@@ -104,6 +104,32 @@ size_t b200post_unpack_indices(const uint8_t *packed, size_t packed_len, uint32_
     return n;
 }
 
+int b200post_verify_batch_multi(const uint32_t *providers, int n_providers, size_t n, const b200post_proof *proofs,
+                                const b200post_proof_metadata *metas, const b200post_verify_params *params,
+                                const b200post_verify_options *options, const b200post_verifier_opts *opts, int *statuses,
+                                uint64_t *invalid_indices) {
+    if (!providers || n_providers <= 0) { set_error("invalid argument"); return B200POST_ERR_INVALID_ARGUMENT; }
+    if (n_providers == 1 || n < 2) return b200post_verify_batch(providers[0], n, proofs, metas, params, options, opts, statuses, invalid_indices);
+    for (int d = 0; d < n_providers; d++)
+        if (!engine_for(providers[d])) return providers[d] == B200POST_CPU_PROVIDER_ID ? B200POST_ERR_UNSUPPORTED : B200POST_ERR_NO_DEVICE;
+    const size_t parts = std::min<size_t>((size_t)n_providers, n);
+    std::vector<int> rcs(parts, B200POST_OK);
+    std::vector<std::string> errs(parts);
+    std::vector<std::thread> th;
+    for (size_t d = 0; d < parts; d++) {
+        const size_t lo = n * d / parts, hi = n * (d + 1) / parts;
+        th.emplace_back([=, &rcs, &errs] {
+            rcs[d] = b200post_verify_batch(providers[d], hi - lo, proofs + lo, metas + lo, params, options ? options + lo : nullptr,
+                                           opts, statuses + lo, invalid_indices ? invalid_indices + lo : nullptr);
+            if (rcs[d] != B200POST_OK) errs[d] = b200post_last_error();   // the error text is thread-local
+        });
+    }
+    for (auto &t : th) t.join();
+    for (size_t d = 0; d < parts; d++)
+        if (rcs[d] != B200POST_OK) { set_error(errs[d]); return rcs[d]; }
+    return B200POST_OK;
+}
+
 }  // extern "C"
 
 namespace b200post {

@@ -101,6 +101,7 @@ def _bind():
     L.b200post_verify_batch.argtypes = [ctypes.c_uint32, ctypes.c_size_t, ctypes.POINTER(_Proof), ctypes.POINTER(_Meta),
                                         ctypes.POINTER(_Params), ctypes.POINTER(_Options), ctypes.POINTER(_VerifierOpts),
                                         ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_uint64)]
+    L.b200post_verify_batch_multi.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.c_int] + L.b200post_verify_batch.argtypes[1:]
     L.b200post_bits_per_index.argtypes = [ctypes.c_uint64]
     L.b200post_bits_per_index.restype = ctypes.c_uint32
     L.b200post_proving_difficulty.argtypes = [ctypes.c_uint32, ctypes.c_uint64]
@@ -227,8 +228,19 @@ class PreparedBatch:
             raise B200PostError(rc, lib().b200post_last_error().decode(errors="replace"))
         return list(self.st[:self.n]), list(self.bad[:self.n])
 
+    def run_multi(self, providers: list[int]):
+        """The batch split over several B200s (contiguous runs of proofs, one host thread per device)."""
+        ids = (ctypes.c_uint32 * len(providers))(*providers)
+        rc = _bind().b200post_verify_batch_multi(ids, len(providers), self.n, self.cps, self.cms, ctypes.byref(self.cq),
+                                                 self.cos, None, self.st, self.bad)
+        if rc != OK:
+            raise B200PostError(rc, lib().b200post_last_error().decode(errors="replace"))
+        return list(self.st[:self.n]), list(self.bad[:self.n])
+
 
 def verify_batch(proofs: list[Proof], metas: list[ProofMetadata], params: VerifyParams, *, provider: int = 0,
-                 options: list[dict] | None = None):
-    """One synchronous GPU batch (BASELINE.json configs[2]).  Returns (statuses, invalid_indices)."""
-    return PreparedBatch(proofs, metas, params, options).run(provider)
+                 providers: list[int] | None = None, options: list[dict] | None = None):
+    """One synchronous GPU batch (BASELINE.json configs[2]).  Returns (statuses, invalid_indices).  With
+    `providers` the batch is split over those devices."""
+    batch = PreparedBatch(proofs, metas, params, options)
+    return batch.run_multi(providers) if providers else batch.run(provider)

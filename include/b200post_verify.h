@@ -100,6 +100,13 @@ int b200post_verify_batch(uint32_t provider, size_t n, const b200post_proof *pro
                           const b200post_verify_params *params, const b200post_verify_options *options /* n or NULL */,
                           const b200post_verifier_opts *opts, int *statuses, uint64_t *invalid_indices);
 
+/* The same batch split over `n_providers` devices: contiguous runs of proofs, one host thread per device, no
+ * data-path collective (proofs are independent — SURVEY.md §8e).  Results land in the caller's order. */
+int b200post_verify_batch_multi(const uint32_t *providers, int n_providers, size_t n, const b200post_proof *proofs,
+                                const b200post_proof_metadata *metas, const b200post_verify_params *params,
+                                const b200post_verify_options *options /* n or NULL */, const b200post_verifier_opts *opts,
+                                int *statuses, uint64_t *invalid_indices);
+
 /* Helpers shared with the Go side (all ASSUMED post-rs conventions, see PARITY NOTE). */
 uint32_t b200post_bits_per_index(uint64_t num_labels);                       /* floor(log2(num_labels)) + 1       */
 uint64_t b200post_proving_difficulty(uint32_t k1, uint64_t num_labels);      /* floor(2^64 * k1 / num_labels)      */

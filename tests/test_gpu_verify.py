@@ -241,6 +241,29 @@ def test_device_epilogue_against_oracle_densely(vf, orc, b2):
     assert 0 < n_ok < n_proofs
 
 
+def test_batch_split_over_devices(vf, b2):
+    """b200post_verify_batch_multi: same verdicts, in the caller's order, as the one-device batch.  On a one-GPU
+    box the provider is listed twice, which still exercises the split, the per-device threads and the merge."""
+    rng = np.random.default_rng(5)
+    n_proofs, k2, num_units, lpu = 701, 8, 4, 256
+    bits = vf.bits_per_index(num_units * lpu)
+    params = vf.VerifyParams(k1=900, k2=k2, scrypt_n=2)
+    proofs, metas = [], []
+    for i in range(n_proofs):
+        ident = bytes(rng.integers(0, 256, 96, dtype=np.uint8))
+        ix = [int(x) for x in rng.integers(0, num_units * lpu, k2)]
+        proofs.append(vf.Proof(int(rng.integers(0, 64)), vf.pack_indices(ix, bits) if i != 300 else b"", i))
+        metas.append(vf.ProofMetadata(ident[:32], ident[32:64], ident[64:], num_units, lpu))
+    gpus = [p["id"] for p in b2.providers() if p["id"] != b2.CPU_PROVIDER_ID]
+    devs = gpus if len(gpus) > 1 else [gpus[0], gpus[0]]
+    one = vf.verify_batch(proofs, metas, params, provider=gpus[0])
+    many = vf.verify_batch(proofs, metas, params, providers=devs)
+    assert one == many and one[0][300] == b2.ERR_EMPTY_PROOF and 0 < sum(1 for s in one[0] if s == b2.OK) < n_proofs
+    assert vf.verify_batch(proofs[:1], metas[:1], params, providers=devs) == ([one[0][0]], [one[1][0]])
+    with pytest.raises(b2.B200PostError):
+        vf.verify_batch(proofs, metas, params, providers=[gpus[0], 12345])
+
+
 def test_metrics_follow_the_work(vf, b2, small_space):
     import re
     meta, params, proofs = small_space
