@@ -389,9 +389,9 @@ struct b200post_verifier {
     std::deque<Job *> prioritized, normal;
     bool closed = false;
     uint64_t batches = 0, proofs = 0;
-    std::thread worker;
+    std::vector<std::thread> workers;     // one per device; all drain the same two queues
 
-    void run() {
+    void run(uint32_t provider) {
         std::unique_lock<std::mutex> lk(mu);
         for (;;) {
             cv_work.wait(lk, [&] { return closed || !prioritized.empty() || !normal.empty(); });
@@ -405,7 +405,12 @@ struct b200post_verifier {
             }
             // drain everything queued (prioritised first): while the GPU works on this batch the next one fills
             std::vector<Job *> batch;
-            const size_t cap = opts.max_batch_proofs ? opts.max_batch_proofs : 16384;
+            // several devices: leave the others their share of a long queue, but do not shred a short one
+            size_t cap = opts.max_batch_proofs ? opts.max_batch_proofs : 16384;
+            if (workers.size() > 1) {
+                const size_t queued = prioritized.size() + normal.size();
+                cap = std::min(cap, std::max<size_t>(64, (queued + workers.size() - 1) / workers.size()));
+            }
             while (batch.size() < cap && !prioritized.empty()) { batch.push_back(prioritized.front()); prioritized.pop_front(); }
             while (batch.size() < cap && !normal.empty()) { batch.push_back(normal.front()); normal.pop_front(); }
             lk.unlock();
@@ -425,10 +430,23 @@ int b200post_verifier_new(uint32_t provider, const b200post_verifier_opts *opts,
     if (!out) { set_error("invalid argument"); return B200POST_ERR_INVALID_ARGUMENT; }
     *out = nullptr;
     if (!engine_for(provider)) return provider == B200POST_CPU_PROVIDER_ID ? B200POST_ERR_UNSUPPORTED : B200POST_ERR_NO_DEVICE;
+    return b200post_verifier_new_multi(&provider, 1, opts, out);
+}
+
+int b200post_verifier_new_multi(const uint32_t *providers, int n_providers, const b200post_verifier_opts *opts,
+                                b200post_verifier **out) {
+    if (!out || !providers || n_providers <= 0) { set_error("invalid argument"); return B200POST_ERR_INVALID_ARGUMENT; }
+    *out = nullptr;
+    for (int d = 0; d < n_providers; d++)
+        if (!engine_for(providers[d])) return providers[d] == B200POST_CPU_PROVIDER_ID ? B200POST_ERR_UNSUPPORTED : B200POST_ERR_NO_DEVICE;
     b200post_verifier *v = new b200post_verifier;
-    v->provider = provider;
+    v->provider = providers[0];
     if (opts) v->opts = *opts;
-    v->worker = std::thread([v] { v->run(); });
+    v->workers.reserve((size_t)n_providers);     // run() reads workers.size(): no reallocation while threads start
+    {
+        std::lock_guard<std::mutex> lk(v->mu);
+        for (int d = 0; d < n_providers; d++) { const uint32_t p = providers[d]; v->workers.emplace_back([v, p] { v->run(p); }); }
+    }
     *out = v;
     return B200POST_OK;
 }
@@ -471,7 +489,7 @@ int b200post_verifier_close(b200post_verifier *v) {
         v->closed = true;
     }
     v->cv_work.notify_all();
-    if (v->worker.joinable()) v->worker.join();
+    for (auto &w : v->workers) if (w.joinable()) w.join();
     return B200POST_OK;
 }
 

@@ -92,6 +92,7 @@ def _bind():
         return L
     vp = ctypes.c_void_p
     L.b200post_verifier_new.argtypes = [ctypes.c_uint32, ctypes.POINTER(_VerifierOpts), ctypes.POINTER(vp)]
+    L.b200post_verifier_new_multi.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.c_int, ctypes.POINTER(_VerifierOpts), ctypes.POINTER(vp)]
     L.b200post_verifier_verify.argtypes = [vp, ctypes.POINTER(_Proof), ctypes.POINTER(_Meta), ctypes.POINTER(_Params),
                                            ctypes.POINTER(_Options), ctypes.POINTER(ctypes.c_uint64)]
     L.b200post_verifier_close.argtypes = [vp]
@@ -173,12 +174,16 @@ def _raise(rc: int, bad: int):
 class PostVerifier:
     """activation.PostVerifier: Verify(ctx, proof, metadata, opts...) error; Close() error."""
 
-    def __init__(self, provider: int = 0, pow_verify=None, max_batch_proofs: int = 0):
+    def __init__(self, provider: int = 0, pow_verify=None, max_batch_proofs: int = 0, providers: list[int] | None = None):
         L = _bind()
         self._cb = POW_VERIFY_FN(pow_verify) if pow_verify else ctypes.cast(None, POW_VERIFY_FN)
         opts = _VerifierOpts(self._cb, None, max_batch_proofs)
         self._h = ctypes.c_void_p()
-        rc = L.b200post_verifier_new(provider, ctypes.byref(opts), ctypes.byref(self._h))
+        if providers:     # one dispatcher, a worker per device
+            ids = (ctypes.c_uint32 * len(providers))(*providers)
+            rc = L.b200post_verifier_new_multi(ids, len(providers), ctypes.byref(opts), ctypes.byref(self._h))
+        else:
+            rc = L.b200post_verifier_new(provider, ctypes.byref(opts), ctypes.byref(self._h))
         if rc != OK:
             raise B200PostError(rc, L.b200post_last_error().decode(errors="replace"))
 

@@ -87,6 +87,11 @@ int b200post_verifier_verify(b200post_verifier *v, const b200post_proof *proof, 
                              const b200post_verify_params *params, const b200post_verify_options *options,
                              uint64_t *invalid_index);
 
+/* One dispatcher over several devices: a worker per device drains the same queues (long queues are shared out,
+ * short ones go to whichever device is idle).  Verify/Close/free/stats as above. */
+int b200post_verifier_new_multi(const uint32_t *providers, int n_providers, const b200post_verifier_opts *opts,
+                                b200post_verifier **out);
+
 /* PostVerifier.Close: wakes every waiter with B200POST_ERR_CLOSED; idempotent; later Verify calls fail fast. */
 int b200post_verifier_close(b200post_verifier *v);
 void b200post_verifier_free(b200post_verifier *v);

@@ -132,11 +132,14 @@ def test_closed_verifier(vf, small_space):
     assert str(e.value) == "verifier is closed"
 
 
-def test_concurrent_callers_are_coalesced(vf, orc, small_space):
-    """Safe for concurrent use (post_verifier.go:227); concurrent Verify calls share GPU batches."""
+@pytest.mark.parametrize("multi", [False, True])
+def test_concurrent_callers_are_coalesced(vf, orc, b2, small_space, multi):
+    """Safe for concurrent use (post_verifier.go:227); concurrent Verify calls share GPU batches.  `multi`: one
+    dispatcher with a worker per device (a one-GPU box lists its device twice: two workers, one engine)."""
     meta, params, proofs = small_space
     bits = vf.bits_per_index(1024)
-    v = vf.PostVerifier()
+    gpus = [p["id"] for p in b2.providers() if p["id"] != b2.CPU_PROVIDER_ID]
+    v = vf.PostVerifier(providers=gpus if len(gpus) > 1 else gpus * 2) if multi else vf.PostVerifier()
     work = []
     for nonce, (proof, hits) in proofs.items():
         work.append((proof, None))
