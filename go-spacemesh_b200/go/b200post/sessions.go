@@ -185,6 +185,19 @@ func NewVerifier(provider uint32) (*Verifier, error) {
 	return v, nil
 }
 
+// NewVerifierOn builds one verifier over several B200s: a worker per device drains the same queue.
+func NewVerifierOn(providers []uint32) (*Verifier, error) {
+	if len(providers) == 0 {
+		return nil, errors.New("b200post: no providers")
+	}
+	v := &Verifier{}
+	rc := C.b200post_verifier_new_multi((*C.uint32_t)(unsafe.Pointer(&providers[0])), C.int(len(providers)), nil, &v.h)
+	if err := statusErr(rc); err != nil {
+		return nil, err
+	}
+	return v, nil
+}
+
 func (v *Verifier) Verify(p *Proof, m *ProofMetadata, k1, k2 uint32, scryptN uint64, o VerifyOptions) error {
 	if len(p.Indices) == 0 {
 		return errors.New("proof indices are empty")
