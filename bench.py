@@ -367,7 +367,7 @@ def main() -> None:
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": "4-SU POST init (2^34 labels/GPU), scrypt N=8192 r=1 p=1, labels discarded (/dev/null sink)",
                        "labels_per_step_per_gpu": batch, "wave_slots": wave, "provider": prov["model"],
-                       "romix_variant": b2.get_option("romix_variant"), "mulwide_mask": b2.get_option("mulwide_mask"),
+                       "romix_variant": b2.get_option("romix_variant"), "rotate_mask": b2.get_option("rotate_mask"),
                        "tpb": tpb, "l2": "working set = wave_slots x 1 MiB scratch >> 126 MB L2; every step uses fresh indices",
                        "parallelism": f"index-range shards x{world}, NCCL all-gather of one 48-B VRF record per step" if world > 1 else "single GPU",
                        "timer": "two CUDA events on the engine's launching stream bracketing the K steps (barrier + synchronize on both sides), max over ranks",

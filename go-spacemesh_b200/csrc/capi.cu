@@ -73,7 +73,7 @@ int b200post_set_option(const char *key, int64_t value) {
     Options &o = options();
     const std::string k(key);
     if (k == "romix_variant" && value >= 0 && value <= 4) { o.romix_variant = value; return B200POST_OK; }
-    if (k == "mulwide_mask" && value >= 0 && value <= 0xffff && romix_mask_supported((int)value)) { o.mulwide_mask = value; return B200POST_OK; }
+    if (k == "rotate_mask" && value >= 0 && value <= 1 && romix_mask_supported((int)value)) { o.rotate_mask = value; return B200POST_OK; }
     if (k == "tpb" && (value == 64 || value == 128 || value == 256 || value == 512)) { o.tpb = value; return B200POST_OK; }
     if (k == "dr_unroll" && (value == 1 || value == 4)) { o.dr_unroll = value; return B200POST_OK; }
     if (k == "ctas_per_sm" && value >= 0 && value <= 32) { o.ctas_per_sm = value; return B200POST_OK; }
@@ -89,7 +89,7 @@ int64_t b200post_get_option(const char *key) {
     Options &o = options();
     const std::string k(key);
     if (k == "romix_variant") return o.romix_variant;
-    if (k == "mulwide_mask") return o.mulwide_mask;
+    if (k == "rotate_mask") return o.rotate_mask;
     if (k == "tpb") return o.tpb;
     if (k == "dr_unroll") return o.dr_unroll;
     if (k == "ctas_per_sm") return o.ctas_per_sm;

@@ -57,14 +57,14 @@ void DeviceEngine::release() {
         cudaFree(d_idx_[b]); d_idx_[b] = nullptr;
         cudaFreeHost(h_commit_[b]); h_commit_[b] = nullptr;
         cudaFreeHost(h_idx_[b]); h_idx_[b] = nullptr;
-        cudaFree(d_mid_[b]); d_mid_[b] = nullptr;
         cudaFree(d_cidx_[b]); d_cidx_[b] = nullptr; cudaFreeHost(h_cidx_[b]); h_cidx_[b] = nullptr;
         cudaEvent_t *evs[] = {&ev_done_[b], &ev_in_[b], &ev_k2a_[b], &ev_k2b_[b], &ev_call_[b]};
         for (cudaEvent_t *e : evs) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
         k2_pending_[b] = false; in_pending_[b] = false; pend_[b].live = false;
     }
     for (int b = 0; b < 2; b++) { if (ev_timer_[b]) cudaEventDestroy(ev_timer_[b]); ev_timer_[b] = nullptr; }
-    cudaFree(d_ctab_); d_ctab_ = nullptr; cudaFree(d_cmid_); d_cmid_ = nullptr; ctab_rows_ = 0;
+    cudaFree(d_ctab_); d_ctab_ = nullptr; ctab_rows_ = 0;
+    cudaFree(d_range_commit_); d_range_commit_ = nullptr;
     cudaFree(d_diff_); d_diff_ = nullptr;
     cudaFree(d_cta_cand_); d_cta_cand_ = nullptr;
     cudaFree(d_running_); d_running_ = nullptr;
@@ -78,7 +78,7 @@ void DeviceEngine::release() {
 // Decide the layer size for scrypt-N and make sure scratch for min(layer, want_slots) slots exists.
 int DeviceEngine::ensure(uint64_t N, uint64_t want_slots) {
     Options &o = options();
-    const int variant = (int)o.romix_variant.load(), mw = (int)o.mulwide_mask.load();
+    const int variant = (int)o.romix_variant.load(), mw = (int)o.rotate_mask.load();
     int tpb = (int)o.tpb.load();
     if (variant != ROMIX_PIPELINED && tpb != 128 && tpb != 256) tpb = 128;   // the classic kernels are built for 128/256 only
     const int dr = (int)o.dr_unroll.load();
@@ -92,6 +92,7 @@ int DeviceEngine::ensure(uint64_t N, uint64_t want_slots) {
             CU_TRY(cudaEventCreate(&ev_call_[b]));
         }
         CU_TRY(cudaMalloc(&d_diff_, 32));
+        CU_TRY(cudaMalloc(&d_range_commit_, 32));
         CU_TRY(cudaMalloc(&d_running_, sizeof(VrfCandidate)));
         CU_TRY(cudaMallocHost(&h_running_, sizeof(VrfCandidate)));
     }
@@ -134,10 +135,10 @@ int DeviceEngine::ensure(uint64_t N, uint64_t want_slots) {
     if (need > alloc_slots_) {
         CU_TRY(cudaStreamSynchronize(stream_));
         for (int b = 0; b < 2; b++) {
-            cudaFree(X_[b]); cudaFree(d_commit_[b]); cudaFree(d_idx_[b]); cudaFree(d_mid_[b]); cudaFree(d_out_[b]); cudaFree(d_cidx_[b]);
+            cudaFree(X_[b]); cudaFree(d_commit_[b]); cudaFree(d_idx_[b]); cudaFree(d_out_[b]); cudaFree(d_cidx_[b]);
             cudaFreeHost(h_commit_[b]); cudaFreeHost(h_idx_[b]); cudaFreeHost(h_out_[b]); cudaFreeHost(h_cidx_[b]);
             d_cidx_[b] = nullptr; h_cidx_[b] = nullptr;
-            X_[b] = nullptr; d_commit_[b] = nullptr; d_idx_[b] = nullptr; d_mid_[b] = nullptr; d_out_[b] = nullptr;
+            X_[b] = nullptr; d_commit_[b] = nullptr; d_idx_[b] = nullptr; d_out_[b] = nullptr;
             h_commit_[b] = nullptr; h_idx_[b] = nullptr; h_out_[b] = nullptr;
         }
         cudaFree(d_cta_cand_); d_cta_cand_ = nullptr;
@@ -146,7 +147,6 @@ int DeviceEngine::ensure(uint64_t N, uint64_t want_slots) {
             CU_TRY(cudaMalloc(&X_[b], (size_t)need * 128));
             CU_TRY(cudaMalloc(&d_commit_[b], (size_t)need * 32));
             CU_TRY(cudaMalloc(&d_idx_[b], (size_t)need * 8));
-            CU_TRY(cudaMalloc(&d_mid_[b], (size_t)need * 64));
             CU_TRY(cudaMalloc(&d_out_[b], (size_t)need * 16));
             CU_TRY(cudaMallocHost(&h_commit_[b], (size_t)need * 32));
             CU_TRY(cudaMallocHost(&h_idx_[b], (size_t)need * 8));
@@ -189,7 +189,7 @@ int DeviceEngine::stage_layer(const Job &job, uint64_t layer, int b, uint32_t n_
         CU_TRY(cudaMemcpyAsync(d_idx_[b], h_idx_[b], (size_t)n_valid * 8, cudaMemcpyHostToDevice, stream_));
         CU_TRY(cudaEventRecord(ev_in_[b], stream_));
         in_pending_[b] = true;
-        *lj = LabelJob{d_cmid_, 0, d_idx_[b], 0, n_valid, d_cidx_[b]};
+        *lj = LabelJob{reinterpret_cast<const uint32_t *>(d_ctab_), 0, d_idx_[b], 0, n_valid, d_cidx_[b]};
     } else if (job.gather) {
         if (in_pending_[b]) { CU_TRY(cudaEventSynchronize(ev_in_[b])); in_pending_[b] = false; }
         memcpy(h_commit_[b], job.commitments + off * 32, (size_t)n_valid * 32);
@@ -198,11 +198,9 @@ int DeviceEngine::stage_layer(const Job &job, uint64_t layer, int b, uint32_t n_
         CU_TRY(cudaMemcpyAsync(d_idx_[b], h_idx_[b], (size_t)n_valid * 8, cudaMemcpyHostToDevice, stream_));
         CU_TRY(cudaEventRecord(ev_in_[b], stream_));
         in_pending_[b] = true;
-        CU_TRY(launch_hmac_midstates(d_commit_[b], n_valid, d_mid_[b], stream_));
-        g_launches += 1;
-        *lj = LabelJob{d_mid_[b], 16, d_idx_[b], 0, n_valid, nullptr};
+        *lj = LabelJob{reinterpret_cast<const uint32_t *>(d_commit_[b]), 8, d_idx_[b], 0, n_valid, nullptr};
     } else {
-        *lj = LabelJob{d_mid_[0], 0, nullptr, job.start + off, n_valid, nullptr};
+        *lj = LabelJob{d_range_commit_, 0, nullptr, job.start + off, n_valid, nullptr};
     }
     CU_TRY(launch_pbkdf2_expand(*lj, X_[b], alloc_slots_, round_up(n_valid, 32), stream_));
     g_launches += 1;
@@ -228,7 +226,6 @@ int DeviceEngine::finish_layer(const Job &job, uint64_t layer, int b, uint32_t n
 int DeviceEngine::run_job(const Job &job) {
     const uint64_t S = std::min<uint64_t>(wave_slots_, alloc_slots_);
     const uint64_t M = (job.total + S - 1) / S;
-    const RotConsts rc{1u << 7, 1u << 9, 1u << 13, 1u << 18};
     int rc_ = B200POST_OK, status = B200POST_OK;
     auto layer_count = [&](uint64_t m) { return (uint32_t)std::min<uint64_t>(S, job.total - m * S); };
 
@@ -244,7 +241,7 @@ int DeviceEngine::run_job(const Job &job) {
             if ((rc_ = stage_layer(job, m, b, n_valid, &lj))) return rc_;
             RomixParams rp;
             rp.V = V_; rp.X = X_[b]; rp.x_stride = alloc_slots_; rp.N = (uint32_t)job.N; rp.n_slots = round_up(n_valid, 32);
-            rp.flags = (uint32_t)options().debug_skip_phase.load(); rp.rc = rc;
+            rp.flags = (uint32_t)options().debug_skip_phase.load();
             CU_TRY(cudaEventRecord(ev_k2a_[b], stream_));
             CU_TRY(launch_romix(variant_, mw_, tpb_, rp, stream_));
             CU_TRY(cudaEventRecord(ev_k2b_[b], stream_));
@@ -273,7 +270,7 @@ int DeviceEngine::run_job(const Job &job) {
                 if ((rc_ = retire(job, b))) return rc_;   // layer m-2 used this parity's buffers
                 nv[b] = layer_count(m);
                 if (m == 0 && resume) {
-                    lj[b] = LabelJob{d_mid_[0], 0, nullptr, job.start, nv[b], nullptr};   // already filled: X_[b] holds its mid-state
+                    lj[b] = LabelJob{d_range_commit_, 0, nullptr, job.start, nv[b], nullptr};   // already filled: X_[b] holds its mid-state
                 } else {
                     if ((rc_ = stage_layer(job, m, b, nv[b], &lj[b]))) return rc_;
                     fill = true; n_fill = round_up(nv[b], 32);
@@ -290,7 +287,7 @@ int DeviceEngine::run_job(const Job &job) {
             const uint32_t n_mix = m >= 1 ? round_up(nv[b ^ 1], 32) : 0;
             if (n_fill == 0 && n_mix == 0) continue;   // resumed call: nothing to launch for m = 0
             PipeParams pp;
-            pp.V = V_; pp.x_stride = alloc_slots_; pp.N = (uint32_t)job.N; pp.rc = rc;
+            pp.V = V_; pp.x_stride = alloc_slots_; pp.N = (uint32_t)job.N;
             pp.Xfill = X_[b]; pp.Xmix = X_[b ^ 1];
             pp.n_fill = n_fill;
             pp.n_mix = n_mix;
@@ -347,11 +344,9 @@ int DeviceEngine::labels_range(const uint8_t commitment[32], uint64_t N, uint64_
     if (rc) return rc;
     CU_TRY(cudaEventRecord(ev_call_[0], stream_));
 
-    // per-call constants: commitment -> HMAC midstates (K0), VRF threshold, running candidate
+    // per-call constants: commitment, VRF threshold, running candidate
     memcpy(cur_commitment_, commitment, 32);
-    CU_TRY(cudaMemcpyAsync(d_commit_[0], commitment, 32, cudaMemcpyHostToDevice, stream_));
-    CU_TRY(launch_hmac_midstates(d_commit_[0], 1, d_mid_[0], stream_));
-    g_launches += 1;
+    CU_TRY(cudaMemcpyAsync(d_range_commit_, commitment, 32, cudaMemcpyHostToDevice, stream_));
     Job job;
     job.start = start; job.total = count; job.N = N; job.out_host = out_host; job.out_dev = out_dev; job.cancel = cancel;
     if (vrf_difficulty) {
@@ -428,15 +423,12 @@ int DeviceEngine::labels_gather_indexed(size_t n_items, size_t n_commit, const u
     if (rc) return rc;
     if (n_commit > ctab_rows_) {
         CU_TRY(cudaStreamSynchronize(stream_));
-        cudaFree(d_ctab_); cudaFree(d_cmid_); d_ctab_ = nullptr; d_cmid_ = nullptr; ctab_rows_ = 0;
+        cudaFree(d_ctab_); d_ctab_ = nullptr; ctab_rows_ = 0;
         CU_TRY(cudaMalloc(&d_ctab_, n_commit * 32));
-        CU_TRY(cudaMalloc(&d_cmid_, n_commit * 64));
         ctab_rows_ = n_commit;
     }
     CU_TRY(cudaEventRecord(ev_call_[0], stream_));
     CU_TRY(cudaMemcpyAsync(d_ctab_, commitments, n_commit * 32, cudaMemcpyHostToDevice, stream_));
-    CU_TRY(launch_hmac_midstates(d_ctab_, (uint32_t)n_commit, d_cmid_, stream_));
-    g_launches += 1;
     spec_.valid = false;   // the scratch is about to be reused
     Job job;
     job.gather = true; job.commit_index = commit_index; job.indices = indices; job.total = n_items; job.N = N;

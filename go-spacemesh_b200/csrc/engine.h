@@ -17,7 +17,7 @@ namespace b200post {
 
 struct Options {
     std::atomic<int64_t> romix_variant{ROMIX_PIPELINED};
-    std::atomic<int64_t> mulwide_mask{0};
+    std::atomic<int64_t> rotate_mask{0};
     std::atomic<int64_t> tpb{512};             // pipelined default: one 16-warp CTA per SM (measured best)
     std::atomic<int64_t> dr_unroll{4};         // pipelined kernel: Salsa double-rounds unrolled (4) or rolled (1)
     std::atomic<int64_t> ctas_per_sm{0};       // 0 = occupancy maximum
@@ -47,7 +47,7 @@ public:
     int labels_gather(size_t n_items, const uint8_t *commitments, const uint64_t *indices, uint64_t N, uint8_t *out_host,
                       uint8_t *out_dev = nullptr);
     // same with the commitments given once (n_commit x 32 bytes) and a per-item row index into them: the verify
-    // path recomputes ~37 labels per identity, so midstates and H2D shrink by that factor
+    // path recomputes ~37 labels per identity, so the commitment H2D shrinks by that factor
     int labels_gather_indexed(size_t n_items, size_t n_commit, const uint8_t *commitments, const uint32_t *commit_index,
                               const uint64_t *indices, uint64_t N, uint8_t *out_host, uint8_t *out_dev);
     // accumulated ROMix kernel device time, launches, and label-equivalents processed by those launches
@@ -67,7 +67,7 @@ private:
         bool gather = false;
         const uint8_t *commitments = nullptr;   // gather: n x 32 (host)
         const uint64_t *indices = nullptr;      // gather: n (host)
-        const uint32_t *commit_index = nullptr; // indexed gather: per-item row of the call-level midstate table
+        const uint32_t *commit_index = nullptr; // indexed gather: per-item row of the call-level commitment table
         uint64_t start = 0, total = 0, N = 0;
         uint8_t *out_host = nullptr, *out_dev = nullptr;
         const uint32_t *d_diff = nullptr;
@@ -101,9 +101,9 @@ private:
     uint64_t *d_idx_[2] = {nullptr, nullptr};
     uint8_t *h_commit_[2] = {nullptr, nullptr};    // pinned staging for gather inputs
     uint64_t *h_idx_[2] = {nullptr, nullptr};
-    uint32_t *d_mid_[2] = {nullptr, nullptr};
+    uint32_t *d_range_commit_ = nullptr;   // the commitment of the current range call (32 bytes)
     uint32_t *d_cidx_[2] = {nullptr, nullptr}, *h_cidx_[2] = {nullptr, nullptr};   // indexed gather: per-item commitment rows
-    uint8_t *d_ctab_ = nullptr; uint32_t *d_cmid_ = nullptr; size_t ctab_rows_ = 0;  // call-level commitment / midstate table
+    uint8_t *d_ctab_ = nullptr; size_t ctab_rows_ = 0;   // indexed gather: call-level commitment table
     uint32_t *d_diff_ = nullptr;
     VrfCandidate *d_cta_cand_ = nullptr;
     VrfCandidate *d_running_ = nullptr;

@@ -91,26 +91,11 @@ __device__ __forceinline__ void set_chunk(uint32_t (&lo)[16], uint32_t (&hi)[16]
     else { hi[4 * k - 16] = v.x; hi[4 * k - 15] = v.y; hi[4 * k - 14] = v.z; hi[4 * k - 13] = v.w; }
 }
 
-// =================================================================================================
-// K0: HMAC midstates
-// =================================================================================================
-__global__ void hmac_midstates_kernel(const uint8_t *__restrict__ commitments, uint32_t n, uint32_t *__restrict__ mid) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t key[8];
-    const uint32_t *c = reinterpret_cast<const uint32_t *>(commitments) + 8 * (size_t)i;
+// the commitment of `slot` as 8 little-endian words
+__device__ __forceinline__ void load_commit(const LabelJob &job, uint32_t slot, uint32_t (&c)[8]) {
+    const uint32_t *p = job.commit_index ? job.commit + 8 * (size_t)job.commit_index[slot] : job.commit + (size_t)job.commit_stride * slot;
 #pragma unroll
-    for (int k = 0; k < 8; k++) key[k] = bswap32(c[k]);
-    HmacMid m;
-    hmac_midstates(key, m);
-#pragma unroll
-    for (int k = 0; k < 8; k++) { mid[16 * (size_t)i + k] = m.inner[k]; mid[16 * (size_t)i + 8 + k] = m.outer[k]; }
-}
-
-__device__ __forceinline__ void load_mid(const LabelJob &job, uint32_t slot, HmacMid &m) {
-    const uint32_t *p = job.mid_index ? job.mid + 16 * (size_t)job.mid_index[slot] : job.mid + (size_t)job.mid_stride * slot;
-#pragma unroll
-    for (int k = 0; k < 8; k++) { m.inner[k] = p[k]; m.outer[k] = p[8 + k]; }
+    for (int k = 0; k < 8; k++) c[k] = p[k];
 }
 __device__ __forceinline__ uint64_t slot_index(const LabelJob &job, uint32_t slot) {
     if (job.indices) return slot < job.n_valid ? job.indices[slot] : 0;
@@ -118,15 +103,15 @@ __device__ __forceinline__ uint64_t slot_index(const LabelJob &job, uint32_t slo
 }
 
 // =================================================================================================
-// K1: PBKDF2 expand  (8 SHA-256 compressions per label)
+// K1: PBKDF2 expand  (8 Keccak-f[1600] permutations per label)
 // =================================================================================================
 __global__ void __launch_bounds__(128) pbkdf2_expand_kernel(LabelJob job, uint4 *__restrict__ X, uint32_t x_stride, uint32_t n_slots) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_slots) return;
-    HmacMid m;
-    load_mid(job, slot < job.n_valid ? slot : 0, m);
+    uint32_t c[8];
+    load_commit(job, slot < job.n_valid ? slot : 0, c);
     uint32_t lo[16], hi[16];
-    pbkdf2_expand(m, slot_index(job, slot), lo, hi);
+    label_expand(c, slot_index(job, slot), lo, hi);
 #pragma unroll
     for (int k = 0; k < 8; k++) X[(size_t)k * x_stride + slot] = ROW_CHUNK(lo, hi, k);
 }
@@ -148,7 +133,6 @@ __global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
     const uint32_t N = p.N, mask = N - 1;
     // diagnostics only (b200post_set_option("debug_skip_phase")): bit0 skips the fill loop, bit1 the mix loop
     const uint32_t n1 = (p.flags & 1) ? 0 : N, n2 = (p.flags & 2) ? 0 : N;
-    const RotConsts rc = p.rc;
 
     uint32_t lo[16], hi[16];
 #pragma unroll
@@ -162,14 +146,14 @@ __global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
         for (uint32_t i = 0; i < n1; i++) {
 #pragma unroll
             for (int k = 0; k < 8; k++) st_stream(Vt + (size_t)i * 256 + k, ROW_CHUNK(lo, hi, k));
-            blockmix_r1<MW>(lo, hi, rc);
+            blockmix_r1<MW>(lo, hi);
         }
         for (uint32_t i = 0; i < n2; i++) {
             const uint32_t j = hi[0] & mask;
             uint32_t vlo[16], vhi[16];
 #pragma unroll
             for (int k = 0; k < 8; k++) set_chunk(vlo, vhi, k, ld_stream(Vt + (size_t)j * 256 + k));
-            blockmix_r1_xor<MW>(lo, hi, vlo, vhi, rc);
+            blockmix_r1_xor<MW>(lo, hi, vlo, vhi);
         }
     } else if (VARIANT == ROMIX_COALESCED) {
         const uint32_t tile = smem_u32(smem_raw) + warp_in_cta * 4096;
@@ -183,7 +167,7 @@ __global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
 #pragma unroll
             for (int k = 0; k < 8; k++) st_stream(dst + k * 32, lds128(tile + (k * 4 + tr_row) * 128 + (tr_c << 4)));
             __syncwarp();
-            blockmix_r1<MW>(lo, hi, rc);
+            blockmix_r1<MW>(lo, hi);
         }
         for (uint32_t i = 0; i < n2; i++) {
             const uint32_t j = hi[0] & mask;
@@ -200,7 +184,7 @@ __global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
 #pragma unroll
             for (int k = 0; k < 8; k++) set_chunk(vlo, vhi, k, lds128(own + ((k ^ swz) << 4)));
             __syncwarp();
-            blockmix_r1_xor<MW>(lo, hi, vlo, vhi, rc);
+            blockmix_r1_xor<MW>(lo, hi, vlo, vhi);
         }
     } else if (VARIANT == ROMIX_BULK) {
         // per warp: two 4-KiB tiles (double-buffered bulk stores in phase 1) + one mbarrier
@@ -219,7 +203,7 @@ __global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) { bulk_s2g(Vw + (size_t)i * 256, tile, 4096); bulk_commit(); }
-            blockmix_r1<MW>(lo, hi, rc);
+            blockmix_r1<MW>(lo, hi);
         }
         if (lane == 0) bulk_wait_all<0>();
         __syncwarp();
@@ -235,15 +219,15 @@ __global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
             uint32_t vlo[16], vhi[16];
 #pragma unroll
             for (int k = 0; k < 8; k++) set_chunk(vlo, vhi, k, lds128(own + ((k ^ swz) << 4)));
-            blockmix_r1_xor<MW>(lo, hi, vlo, vhi, rc);
+            blockmix_r1_xor<MW>(lo, hi, vlo, vhi);
         }
     } else {   // ROMIX_NOMEM: same arithmetic, no scratchpad (ALU ceiling probe only)
-        for (uint32_t i = 0; i < n1; i++) blockmix_r1<MW>(lo, hi, rc);
+        for (uint32_t i = 0; i < n1; i++) blockmix_r1<MW>(lo, hi);
         for (uint32_t i = 0; i < n2; i++) {
             uint32_t vlo[16], vhi[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) { vlo[k] = hi[(k + 1) & 15] + i; vhi[k] = lo[(k + 3) & 15]; }
-            blockmix_r1_xor<MW>(lo, hi, vlo, vhi, rc);
+            blockmix_r1_xor<MW>(lo, hi, vlo, vhi);
         }
     }
 #pragma unroll
@@ -255,7 +239,7 @@ __global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
 // loop (V[i] <- X; X <- BlockMix(X)) while the label of layer m-1 is in its mix loop
 // (X <- BlockMix(X ^ V[Integerify(X)])).  The mix loop's dependent HBM read (~0.6-1.5 us) is issued
 // with cp.async at the top of the step and lands in shared memory while the fill label's BlockMix
-// keeps the integer pipes busy; the two Salsa streams are interleaved instruction by instruction.
+// keeps the integer pipes busy.
 // Each slot owns two scratchpads (parity = layer & 1).  The mid-state of a filled label travels to the
 // next launch through the layer's X buffer, so consecutive launches form one software pipeline:
 //     launch m:  K1(layer m) -> K2p{mix layer m-1, fill layer m} -> K3(layer m-1)
@@ -274,7 +258,6 @@ __global__ void __launch_bounds__(TPB) romix_pipe_kernel(const PipeParams p) {
         p.cta_trace[3 * (size_t)blockIdx.x] = t; p.cta_trace[3 * (size_t)blockIdx.x + 2] = sm;
     }
     const uint32_t N = p.N, mask = N - 1;
-    const RotConsts rc = p.rc;
     const uint32_t tile_f = smem_u32(smem_raw) + warp_in_cta * 8192, tile_m = tile_f + 4096;
     const uint32_t own_f = tile_f + lane * 128, own_m = tile_m + lane * 128;
     const uint32_t swz = lane & 7, tr_row = lane >> 3, tr_c = lane & 7;
@@ -330,7 +313,7 @@ __global__ void __launch_bounds__(TPB) romix_pipe_kernel(const PipeParams p) {
     for (uint32_t i = 0; i < N; i++) {
         if (do_fill) {
             fill_store();
-            blockmix_r1<MW, DR_UNROLL>(lo_f, hi_f, rc);
+            blockmix_r1<MW, DR_UNROLL>(lo_f, hi_f);
         }
         if (do_mix) {
             cp_async_wait_all();
@@ -339,7 +322,7 @@ __global__ void __launch_bounds__(TPB) romix_pipe_kernel(const PipeParams p) {
 #pragma unroll
             for (int k = 0; k < 8; k++) set_chunk(vlo, vhi, k, lds128(own_m + ((k ^ swz) << 4)));
             __syncwarp();
-            blockmix_r1_xor<MW, DR_UNROLL>(lo_m, hi_m, vlo, vhi, rc);
+            blockmix_r1_xor<MW, DR_UNROLL>(lo_m, hi_m, vlo, vhi);
             if (i + 1 < N) mix_prefetch();
         }
     }
@@ -385,13 +368,13 @@ __global__ void __launch_bounds__(FINAL_TPB) pbkdf2_final_kernel(LabelJob job, c
     uint32_t lab[8];
     uint64_t index = 0;
     if (slot < n_slots) {
-        HmacMid m;
-        load_mid(job, valid ? slot : 0, m);
+        uint32_t c[8];
+        load_commit(job, valid ? slot : 0, c);
         uint32_t lo[16], hi[16];
 #pragma unroll
         for (int k = 0; k < 8; k++) set_chunk(lo, hi, k, X[(size_t)k * x_stride + slot]);
-        pbkdf2_final(m, lo, hi, lab);
         index = slot_index(job, slot);
+        label_final(c, index, lo, hi, lab);
     } else {
 #pragma unroll
         for (int k = 0; k < 8; k++) lab[k] = 0xffffffffu;
@@ -490,12 +473,6 @@ __global__ void __launch_bounds__(256) vrf_merge_kernel(const VrfCandidate *__re
 // =================================================================================================
 // launch table
 // =================================================================================================
-cudaError_t launch_hmac_midstates(const uint8_t *d_commitments, uint32_t n, uint32_t *d_mid, cudaStream_t s) {
-    if (n == 0) return cudaSuccess;
-    hmac_midstates_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_commitments, n, d_mid);
-    return cudaGetLastError();
-}
-
 cudaError_t launch_pbkdf2_expand(const LabelJob &job, uint4 *X, uint32_t x_stride, uint32_t n_slots, cudaStream_t s) {
     if (n_slots == 0) return cudaSuccess;
     pbkdf2_expand_kernel<<<(n_slots + 127) / 128, 128, 0, s>>>(job, X, x_stride, n_slots);
@@ -539,9 +516,8 @@ const char *romix_variant_name(int variant) {
 typedef void (*romix_fn)(const RomixParams);
 typedef void (*pipe_fn)(const PipeParams);
 
-// rotate-mix masks compiled in (see salsa20_8): 0 = all funnel shifts (the fastest, measured);
-// 0x8421 / 0xFFFF = 4 / 16 of a half-round's 16 rotates as IMAD.WIDE, kept as the evidence for that finding
-#define B200POST_MW_LIST(X) X(0x0000) X(0x8421) X(0xFFFF)
+// rotate-form masks compiled in (see chacha20_8): 0 = all funnel shifts, 1 = the 16- and 8-bit rotates as PRMT
+#define B200POST_MW_LIST(X) X(0) X(1)
 
 template <int VARIANT, int MW>
 static romix_fn pick_tpb(int tpb) {
@@ -606,26 +582,26 @@ bool romix_mask_supported(int mw) {
     return false;
 }
 
-int romix_max_ctas_per_sm(int variant, int mulwide_mask, int tpb, int dr_unroll) {
+int romix_max_ctas_per_sm(int variant, int rot_mask, int tpb, int dr_unroll) {
     const size_t smem = romix_smem_bytes(variant, tpb);
     int n = 0;
     if (variant == ROMIX_PIPELINED) {
-        pipe_fn fn = pick_pipe(mulwide_mask, tpb, dr_unroll);
+        pipe_fn fn = pick_pipe(rot_mask, tpb, dr_unroll);
         if (!fn) return 0;
         if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, tpb, smem) != cudaSuccess) return 0;
         return n;
     }
-    romix_fn fn = pick(variant, mulwide_mask, tpb);
+    romix_fn fn = pick(variant, rot_mask, tpb);
     if (!fn) return 0;
     if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, tpb, smem) != cudaSuccess) return 0;
     return n;
 }
 
-cudaError_t launch_romix(int variant, int mulwide_mask, int tpb, const RomixParams &p, cudaStream_t s) {
+cudaError_t launch_romix(int variant, int rot_mask, int tpb, const RomixParams &p, cudaStream_t s) {
     if (p.n_slots == 0) return cudaSuccess;
-    romix_fn fn = pick(variant, mulwide_mask, tpb);
+    romix_fn fn = pick(variant, rot_mask, tpb);
     if (!fn) return cudaErrorInvalidValue;
     const size_t smem = romix_smem_bytes(variant, tpb);
     if (smem > 48 * 1024) {
@@ -636,10 +612,10 @@ cudaError_t launch_romix(int variant, int mulwide_mask, int tpb, const RomixPara
     return cudaGetLastError();
 }
 
-cudaError_t launch_romix_pipe(int mulwide_mask, int tpb, int dr_unroll, const PipeParams &p, cudaStream_t s) {
+cudaError_t launch_romix_pipe(int rot_mask, int tpb, int dr_unroll, const PipeParams &p, cudaStream_t s) {
     const uint32_t n = p.n_fill > p.n_mix ? p.n_fill : p.n_mix;
     if (n == 0) return cudaSuccess;
-    pipe_fn fn = pick_pipe(mulwide_mask, tpb, dr_unroll);
+    pipe_fn fn = pick_pipe(rot_mask, tpb, dr_unroll);
     if (!fn) return cudaErrorInvalidValue;
     const size_t smem = romix_smem_bytes(ROMIX_PIPELINED, tpb);
     if (smem > 48 * 1024) {

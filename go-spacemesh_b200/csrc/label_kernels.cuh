@@ -3,10 +3,9 @@
 // One label = one thread ("slot").  A *wave* is the set of slots resident on the GPU at once; every
 // slot owns a private 128*N-byte ROMix scratchpad in HBM for the lifetime of the wave.
 //
-//   K0 hmac_midstates_kernel   commitment -> HMAC ipad/opad SHA-256 midstates (per commitment)
-//   K1 pbkdf2_expand_kernel    (midstate, index) -> X[32 words]            (RFC 7914 §6 step 1)
-//   K2 romix_kernel<VARIANT>   X <- ROMix(X), the 99.7 % kernel              (RFC 7914 §5)
-//   K3 pbkdf2_final_kernel     X -> label32; 16-byte labels out via TMA bulk store; VRF candidates
+//   K1 pbkdf2_expand_kernel    (commitment, index) -> X[32 words]: PBKDF2-HMAC-Keccak512, scrypt step 1
+//   K2 romix_kernel<VARIANT>   X <- ROMix(X) with the ChaCha20/8 BlockMix, the 99.5 % kernel (scrypt step 2)
+//   K3 pbkdf2_final_kernel     X -> label32 (PBKDF2 again); 16-byte labels out via TMA bulk store; VRF candidates
 //   K4 vrf_merge_kernel        per-CTA VRF candidates -> running minimum
 //
 // Reference anchors: activation/post.go:295 (Initialize -> labels over a contiguous range),
@@ -36,7 +35,6 @@ struct RomixParams {
     uint32_t N;          // scrypt N (power of two, >= 2)
     uint32_t n_slots;    // active slots this wave (multiple of 32)
     uint32_t flags;      // diagnostics: bit0 skip fill loop, bit1 skip mix loop (0 in production)
-    RotConsts rc;
 };
 
 struct PipeParams {
@@ -48,16 +46,15 @@ struct PipeParams {
     uint32_t n_fill, n_mix;   // active slots of each layer (multiples of 32)
     uint32_t fill_parity;     // which of the slot's two scratchpads the filling layer owns
     unsigned long long *cta_trace;   // diagnostics (nullptr in production): per CTA {start ns, end ns, smid}
-    RotConsts rc;
 };
 
 struct LabelJob {
-    const uint32_t *mid;        // HMAC midstates: 16 words per commitment
-    uint32_t mid_stride;        // 0 = one shared commitment, 16 = one per slot
+    const uint32_t *commit;     // commitments: 8 little-endian words (32 bytes) per row
+    uint32_t commit_stride;     // words between the rows of consecutive slots: 0 = one shared commitment, 8 = one per slot
     const uint64_t *indices;    // nullptr => index = start + slot
     uint64_t start;
     uint32_t n_valid;           // slots that correspond to requested labels (<= n_slots)
-    const uint32_t *mid_index;  // optional: per-slot row of `mid` (many items sharing few commitments); overrides mid_stride
+    const uint32_t *commit_index;  // optional: per-slot row of `commit` (many items sharing few commitments); overrides commit_stride
 };
 
 struct VrfCandidate {           // 48 bytes
@@ -66,10 +63,10 @@ struct VrfCandidate {           // 48 bytes
     uint32_t found, pad;
 };
 
-cudaError_t launch_hmac_midstates(const uint8_t *d_commitments, uint32_t n, uint32_t *d_mid, cudaStream_t s);
 cudaError_t launch_pbkdf2_expand(const LabelJob &job, uint4 *X, uint32_t x_stride, uint32_t n_slots, cudaStream_t s);
-cudaError_t launch_romix(int variant, int mulwide_mask, int tpb, const RomixParams &p, cudaStream_t s);
-cudaError_t launch_romix_pipe(int mulwide_mask, int tpb, int dr_unroll, const PipeParams &p, cudaStream_t s);
+cudaError_t launch_romix(int variant, int rot_mask, int tpb, const RomixParams &p, cudaStream_t s);
+cudaError_t launch_romix_pipe(int rot_mask, int tpb, int dr_unroll, const PipeParams &p, cudaStream_t s);
+// rotate-form masks compiled in (post_device.cuh ROT): 0 = all SHF, 1 = 16/8-bit rotates as PRMT
 bool romix_mask_supported(int mw);
 // out16: n_valid x 16 bytes (device).  vrf_difficulty_be: 8 big-endian words (device) or nullptr.
 // cta_cand: one VrfCandidate per CTA (device), only touched when vrf_difficulty_be != nullptr.
@@ -81,7 +78,7 @@ uint32_t pbkdf2_final_ctas(uint32_t n_slots);
 // bytes of dynamic shared memory the ROMix variant needs per CTA
 size_t romix_smem_bytes(int variant, int tpb);
 // occupancy query helper: max resident CTAs/SM for (variant, mask, tpb)
-int romix_max_ctas_per_sm(int variant, int mulwide_mask, int tpb, int dr_unroll);
+int romix_max_ctas_per_sm(int variant, int rot_mask, int tpb, int dr_unroll);
 const char *romix_variant_name(int variant);
 
 }  // namespace b200post

@@ -74,7 +74,7 @@ const char *b200post_last_error(void);
 
 /* Engine tuning knobs (process-wide; take effect at the next call):
  *   "romix_variant"  4 pipelined (default) | 0 direct | 1 coalesced | 2 bulk(TMA) | 3 nomem (ALU probe, NOT labels)
- *   "mulwide_mask"   16-bit mask of Salsa rotates issued as IMAD.WIDE instead of SHF (a compiled-in set)
+ *   "rotate_mask"    form of the ChaCha rotates: 0 = all SHF, 1 = the 16- and 8-bit rotates as PRMT
  *   "tpb" 64|128|256|512 (64 and 512 only for the pipelined kernel; default 512) ; "dr_unroll" 4|1 ; "ctas_per_sm" 0 = as many as fit ;
  *   "max_scratch_mib" 0 = 90 % of free HBM ; "debug_skip_phase" diagnostics only.
  * Returns B200POST_ERR_INVALID_ARGUMENT for an unknown key or value. */

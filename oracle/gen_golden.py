@@ -1,14 +1,18 @@
 """Generates tests/golden/*.json — committed golden vectors for the POST label path.
 
-Every expected value here is produced by THIRD-PARTY primitives (OpenSSL's scrypt via hashlib, the
-`blake3` wheel), not by oracle/post_oracle.c nor by the CUDA kernels, so the files pin both.
+Every expected value here is produced by the numpy / hashlib / `blake3`-wheel restatement in oracle/pyoracle.py
+(py_*), not by oracle/post_oracle.c nor by the CUDA kernels, so the files pin both.  That restatement is itself
+pinned against REAL data: checkpoint_vrf.json below.
 Inputs mirror the reference's own deterministic test inputs where it has any:
+  * checkpoint/checkpointdata.json — 42 identities (publicKey, commitmentAtx, vrfNonce, numUnits) of a
+    LabelsPerUnit = 1024, scrypt N = 8192 network: each vrfNonce is the arg-min label index of that identity's
+    POST, so label32(nonce) must be of the order of 2^256/numLabels (>= 13 leading zero bits; a wrong label
+    function gives ~1).  checkpoint_vrf.json records the identities and their label32 values;
   * activation/validation_test.go:35-36 — nodeID = 32 zero bytes, commitment ATX = 32 zero bytes,
     LabelsPerUnit = 128 (:48), default scrypt N = 8192;
   * activation/post_test.go:354-357 — Scrypt.N = 2, 1024 labels (BASELINE.json configs[0]).
-The reference asserts no label bytes anywhere: the *conventions* stay "parity unpinned".
 
-Run:  python oracle/gen_golden.py        (needs hashlib.scrypt + blake3; ~20 s)
+Run in the build container:  python oracle/gen_golden.py        (~2 min; reads /root/reference for the fixture)
 """
 import hashlib
 import json
@@ -61,6 +65,30 @@ def main():
         assert hashlib.pbkdf2_hmac("sha256", v["P"].encode(), v["S"].encode(), v["c"], v["dkLen"]).hex() == v["out"]
     json.dump(kats, open(os.path.join(OUT, "kat_primitives.json"), "w"), indent=1)
 
+    # ---- real identities from the reference's checkpoint fixture: the pin of the label function
+    import base64
+    ref = "/root/reference/checkpoint/checkpointdata.json"
+    if os.path.exists(ref):
+        seen = {}
+        for a in json.load(open(ref))["data"]["atxs"]:
+            seen[(a["publicKey"], a["commitmentAtx"], a["vrfNonce"], a["numUnits"])] = 1
+        ids = list(seen)
+        comms = [o.py_commitment(base64.b64decode(pk), base64.b64decode(ca)) for pk, ca, _, _ in ids]
+        l32 = o.py_label32_batch(comms, [nonce for _, _, nonce, _ in ids], 8192)
+        rows = []
+        for (pk, ca, nonce, units), c, lab in zip(ids, comms, l32):
+            num_labels = units * 1024
+            ratio = int.from_bytes(lab, "big") * num_labels / 2**256      # ~Exp(1) for an arg-min
+            assert ratio < 8, "label function does not reproduce the fixture's VRF nonces"
+            rows.append(dict(node_id=base64.b64decode(pk).hex(), commitment_atx=base64.b64decode(ca).hex(), commitment=c.hex(),
+                             vrf_nonce=nonce, num_units=units, labels_per_unit=1024, N=8192, label32=lab.hex(),
+                             label32_times_num_labels_over_2p256=round(ratio, 4)))
+        json.dump(dict(note="identities from the reference's checkpoint/checkpointdata.json (snapshot-1152); label32 by "
+                            "oracle/pyoracle.py py_label32_batch; every vrf_nonce is the arg-min index of that POST",
+                       items=rows), open(os.path.join(OUT, "checkpoint_vrf.json"), "w"), indent=1)
+        print("checkpoint_vrf.json:", len(rows), "identities,", sum(r["label32_times_num_labels_over_2p256"] < 1 for r in rows),
+              "below 2^256/numLabels")
+
     # ---- label vectors
     cases = []
 
@@ -90,7 +118,7 @@ def main():
     # intermediate N values
     for n in (4, 64, 1024):
         add(f"n{n}_ragged_77", node_id, atx, n, 1000003, 77, num_labels_for_vrf=64, full=True)
-    json.dump(dict(note="generated by oracle/gen_golden.py with hashlib.scrypt (OpenSSL) + blake3 wheel", cases=cases),
+    json.dump(dict(note="generated by oracle/gen_golden.py with the numpy scrypt-jane restatement (oracle/pyoracle.py py_*) + blake3 wheel", cases=cases),
               open(os.path.join(OUT, "labels.json"), "w"), indent=1)
 
     # ---- gather vectors (verify path): distinct commitments, scattered indices in [0, 2^34)
@@ -101,8 +129,11 @@ def main():
         idx = int(rng3.integers(0, 2**34))
         n = 8192 if k < 24 else 2
         c = o.py_commitment(nid, a)
-        items.append(dict(node_id=nid.hex(), commitment_atx=a.hex(), commitment=c.hex(), index=idx, N=n,
-                          label32=o.py_label32(c, idx, n).hex()))
+        items.append(dict(node_id=nid.hex(), commitment_atx=a.hex(), commitment=c.hex(), index=idx, N=n))
+    for n in (8192, 2):
+        sel = [it for it in items if it["N"] == n]
+        for it, lab in zip(sel, o.py_label32_batch([bytes.fromhex(it["commitment"]) for it in sel], [it["index"] for it in sel], n)):
+            it["label32"] = lab.hex()
     json.dump(dict(items=items), open(os.path.join(OUT, "gather.json"), "w"), indent=1)
 
     # ---- VRF difficulty table

@@ -6,7 +6,13 @@
  *   SHA-256 ............ FIPS 180-4 §6.2
  *   HMAC ............... FIPS 198-1 §4
  *   PBKDF2 ............. RFC 8018 §5.2
- *   Salsa20/8, BlockMix, ROMix, scrypt ... RFC 7914 §3-§6
+ *   Salsa20/8, BlockMix, ROMix, scrypt ... RFC 7914 §3-§6 (kept as a KAT-pinned building block)
+ *   Keccak-f[1600], Keccak-512 ........... the Keccak submission (original 0x01 padding, not SHA-3's 0x06)
+ *   ChaCha20/8 core ...................... D. J. Bernstein, "ChaCha, a variant of Salsa20" (8 rounds, no constants)
+ *   scrypt-jane (ChaCha20/8 + Keccak-512) . floodyberry/scrypt-jane as libpost builds it: the POST LABEL FUNCTION.
+ *       Pinned by real data: the 42 identities of the reference's checkpoint/checkpointdata.json carry VRF
+ *       nonces that are the arg-min label of their POST under exactly this function (tests/golden/
+ *       checkpoint_vrf.json, tools/pin_search.py) and under no RFC 7914 variant.
  *   BLAKE3 ............. BLAKE3 paper §2 (zeebo/blake3 v0.2.4 is what hash/hash.go:16-25 calls)
  *   AES-128 ............ FIPS-197
  * Call-site anchors in the reference: activation/post.go:295,355-361 (init),
@@ -180,30 +186,49 @@ void oracle_salsa20_8(uint32_t b[16]) {
     for (int i = 0; i < 16; i++) b[i] += x[i];
 }
 
-void oracle_blockmix(uint32_t *b, uint32_t *y, uint32_t r) {
+/* ChaCha20/8 core as scrypt-jane uses it (scrypt-jane-mix_chacha.h chacha_core_basic): the 64-byte block is
+ * the whole state (no constants / counter), 4 double rounds, feed-forward add. */
+void oracle_chacha20_8(uint32_t b[16]) {
+    uint32_t x[16];
+    memcpy(x, b, 64);
+#define QR(a, b_, c, d) \
+    x[a] += x[b_]; x[d] = rol32(x[d] ^ x[a], 16); x[c] += x[d]; x[b_] = rol32(x[b_] ^ x[c], 12); \
+    x[a] += x[b_]; x[d] = rol32(x[d] ^ x[a], 8);  x[c] += x[d]; x[b_] = rol32(x[b_] ^ x[c], 7);
+    for (int i = 0; i < 4; i++) {
+        QR(0, 4, 8, 12) QR(1, 5, 9, 13) QR(2, 6, 10, 14) QR(3, 7, 11, 15)     /* columns */
+        QR(0, 5, 10, 15) QR(1, 6, 11, 12) QR(2, 7, 8, 13) QR(3, 4, 9, 14)     /* diagonals */
+    }
+#undef QR
+    for (int i = 0; i < 16; i++) b[i] += x[i];
+}
+
+typedef void (*mix_core_fn)(uint32_t *);
+
+static void blockmix_with(uint32_t *b, uint32_t *y, uint32_t r, mix_core_fn core) {
     uint32_t x[16];
     memcpy(x, b + (2 * r - 1) * 16, 64);
     for (uint32_t i = 0; i < 2 * r; i++) {
         for (int k = 0; k < 16; k++) x[k] ^= b[i * 16 + k];
-        oracle_salsa20_8(x);
+        core(x);
         /* even blocks to the first half, odd blocks to the second (RFC 7914 §4 step 3) */
         memcpy(y + ((i & 1) ? (r + i / 2) : (i / 2)) * 16, x, 64);
     }
     memcpy(b, y, 128 * (size_t)r);
 }
+void oracle_blockmix(uint32_t *b, uint32_t *y, uint32_t r) { blockmix_with(b, y, r, oracle_salsa20_8); }
 
-static void romix(uint32_t *x, uint32_t *v, uint32_t *y, uint64_t N, uint32_t r) {
+static void romix(uint32_t *x, uint32_t *v, uint32_t *y, uint64_t N, uint32_t r, mix_core_fn core) {
     const size_t words = 32 * (size_t)r;
     for (uint64_t i = 0; i < N; i++) {
         memcpy(v + i * words, x, words * 4);
-        oracle_blockmix(x, y, r);
+        blockmix_with(x, y, r, core);
     }
     for (uint64_t i = 0; i < N; i++) {
         /* Integerify: first 8 bytes of the last 64-byte sub-block, little-endian, mod N */
         uint64_t j = ((uint64_t)x[(2 * r - 1) * 16] | ((uint64_t)x[(2 * r - 1) * 16 + 1] << 32)) & (N - 1);
         const uint32_t *vj = v + j * words;
         for (size_t k = 0; k < words; k++) x[k] ^= vj[k];
-        oracle_blockmix(x, y, r);
+        blockmix_with(x, y, r, core);
     }
 }
 
@@ -218,10 +243,134 @@ int oracle_scrypt(const uint8_t *pw, size_t pwlen, const uint8_t *salt, size_t s
     oracle_pbkdf2_sha256(pw, pwlen, salt, saltlen, 1, B, blk * p);
     for (uint32_t i = 0; i < p; i++) {
         for (size_t k = 0; k < blk / 4; k++) x[k] = le32(B + i * blk + 4 * k);
-        romix(x, v, y, N, r);
+        romix(x, v, y, N, r, oracle_salsa20_8);
         for (size_t k = 0; k < blk / 4; k++) put_le32(B + i * blk + 4 * k, x[k]);
     }
     oracle_pbkdf2_sha256(pw, pwlen, B, blk * p, 1, out, dklen);
+    free(B); free(x); free(y); free(v);
+    return 0;
+}
+
+/* ======================================================================== Keccak-512 / scrypt-jane */
+static const uint64_t KECCAK_RC[24] = {
+    0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull, 0x000000000000808bull,
+    0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull, 0x000000000000008aull, 0x0000000000000088ull,
+    0x0000000080008009ull, 0x000000008000000aull, 0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull,
+    0x8000000000008003ull, 0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,
+    0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+static inline uint64_t rol64(uint64_t x, int n) { return n ? (x << n) | (x >> (64 - n)) : x; }
+
+/* Keccak-f[1600], lane (x, y) at s[x + 5 y]; step by step as in the specification (theta, rho, pi, chi, iota) */
+static void keccak_f1600(uint64_t s[25]) {
+    static const int RHO[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+    for (int round = 0; round < 24; round++) {
+        uint64_t c[5], d[5], b[25];
+        for (int x = 0; x < 5; x++) c[x] = s[x] ^ s[x + 5] ^ s[x + 10] ^ s[x + 15] ^ s[x + 20];
+        for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rol64(c[(x + 1) % 5], 1);
+        for (int i = 0; i < 25; i++) s[i] ^= d[i % 5];
+        for (int x = 0; x < 5; x++)
+            for (int y = 0; y < 5; y++) b[y + 5 * ((2 * x + 3 * y) % 5)] = rol64(s[x + 5 * y], RHO[x + 5 * y]);
+        for (int y = 0; y < 5; y++)
+            for (int x = 0; x < 5; x++) s[x + 5 * y] = b[x + 5 * y] ^ (~b[(x + 1) % 5 + 5 * y] & b[(x + 2) % 5 + 5 * y]);
+        s[0] ^= KECCAK_RC[round];
+    }
+}
+
+#define K512_RATE 72
+typedef struct { uint64_t s[25]; uint8_t buf[K512_RATE]; size_t fill; } k512_ctx;
+static void k512_init(k512_ctx *c) { memset(c, 0, sizeof *c); }
+static void k512_block(k512_ctx *c, const uint8_t *p) {
+    for (int i = 0; i < K512_RATE / 8; i++) {
+        uint64_t w = 0;
+        for (int k = 0; k < 8; k++) w |= (uint64_t)p[8 * i + k] << (8 * k);
+        c->s[i] ^= w;
+    }
+    keccak_f1600(c->s);
+}
+static void k512_update(k512_ctx *c, const uint8_t *p, size_t n) {
+    while (n) {
+        size_t take = K512_RATE - c->fill;
+        if (take > n) take = n;
+        memcpy(c->buf + c->fill, p, take);
+        c->fill += take; p += take; n -= take;
+        if (c->fill == K512_RATE) { k512_block(c, c->buf); c->fill = 0; }
+    }
+}
+static void k512_final(k512_ctx *c, uint8_t pad, uint8_t out[64]) {
+    memset(c->buf + c->fill, 0, K512_RATE - c->fill);
+    c->buf[c->fill] ^= pad;
+    c->buf[K512_RATE - 1] ^= 0x80;
+    k512_block(c, c->buf);
+    for (int i = 0; i < 8; i++)
+        for (int k = 0; k < 8; k++) out[8 * i + k] = (uint8_t)(c->s[i] >> (8 * k));
+}
+/* pad = 0x01: original Keccak (scrypt-jane's SCRYPT_KECCAK512); pad = 0x06 gives SHA3-512 (used to pin the
+ * permutation against hashlib in tests) */
+void oracle_keccak512(const uint8_t *msg, size_t len, uint8_t pad, uint8_t out[64]) {
+    k512_ctx c;
+    k512_init(&c);
+    k512_update(&c, msg, len);
+    k512_final(&c, pad, out);
+}
+
+/* HMAC over Keccak-512: block size = the sponge rate, 72 bytes (scrypt-jane-hash_keccak.h SCRYPT_HASH_BLOCK_SIZE) */
+typedef struct { k512_ctx inner, outer; } khmac_ctx;
+static void khmac_init(khmac_ctx *h, const uint8_t *key, size_t klen) {
+    uint8_t k[K512_RATE], pad[K512_RATE], kd[64];
+    memset(k, 0, sizeof k);
+    if (klen > K512_RATE) { oracle_keccak512(key, klen, 0x01, kd); memcpy(k, kd, 64); } else memcpy(k, key, klen);
+    for (int i = 0; i < K512_RATE; i++) pad[i] = k[i] ^ 0x36;
+    k512_init(&h->inner); k512_update(&h->inner, pad, K512_RATE);
+    for (int i = 0; i < K512_RATE; i++) pad[i] = k[i] ^ 0x5c;
+    k512_init(&h->outer); k512_update(&h->outer, pad, K512_RATE);
+}
+static void khmac_final(khmac_ctx *h, uint8_t out[64]) {
+    uint8_t d[64];
+    k512_final(&h->inner, 0x01, d);
+    k512_update(&h->outer, d, 64);
+    k512_final(&h->outer, 0x01, out);
+}
+void oracle_hmac_keccak512(const uint8_t *key, size_t klen, const uint8_t *msg, size_t mlen, uint8_t out[64]) {
+    khmac_ctx h;
+    khmac_init(&h, key, klen);
+    k512_update(&h.inner, msg, mlen);
+    khmac_final(&h, out);
+}
+/* PBKDF2 (RFC 8018 §5.2) with that HMAC, one iteration: all scrypt needs */
+void oracle_pbkdf2_keccak512(const uint8_t *pw, size_t pwlen, const uint8_t *salt, size_t saltlen, uint8_t *out, size_t dklen) {
+    khmac_ctx base;
+    khmac_init(&base, pw, pwlen);
+    uint32_t blk = 1;
+    while (dklen) {
+        uint8_t t[64], ctr[4];
+        khmac_ctx h = base;
+        put_be32(ctr, blk);
+        k512_update(&h.inner, salt, saltlen);
+        k512_update(&h.inner, ctr, 4);
+        khmac_final(&h, t);
+        size_t take = dklen < 64 ? dklen : 64;
+        memcpy(out, t, take);
+        out += take; dklen -= take; blk++;
+    }
+}
+
+/* scrypt-jane with SCRYPT_CHACHA + SCRYPT_KECCAK512: scrypt's structure (PBKDF2 -> ROMix per lane -> PBKDF2) with
+ * ChaCha20/8 as the BlockMix core and HMAC-Keccak-512 inside PBKDF2. */
+int oracle_scrypt_jane(const uint8_t *pw, size_t pwlen, const uint8_t *salt, size_t saltlen,
+                       uint64_t N, uint32_t r, uint32_t p, uint8_t *out, size_t dklen) {
+    if (N < 2 || (N & (N - 1)) || r == 0 || p == 0) return -1;
+    const size_t blk = 128 * (size_t)r;
+    uint8_t *B = (uint8_t *)malloc(blk * p);
+    uint32_t *x = (uint32_t *)malloc(blk), *y = (uint32_t *)malloc(blk);
+    uint32_t *v = (uint32_t *)malloc(blk * N);
+    if (!B || !x || !y || !v) { free(B); free(x); free(y); free(v); return -1; }
+    oracle_pbkdf2_keccak512(pw, pwlen, salt, saltlen, B, blk * p);
+    for (uint32_t i = 0; i < p; i++) {
+        for (size_t k = 0; k < blk / 4; k++) x[k] = le32(B + i * blk + 4 * k);
+        romix(x, v, y, N, r, oracle_chacha20_8);
+        for (size_t k = 0; k < blk / 4; k++) put_le32(B + i * blk + 4 * k, x[k]);
+    }
+    oracle_pbkdf2_keccak512(pw, pwlen, B, blk * p, out, dklen);
     free(B); free(x); free(y); free(v);
     return 0;
 }
@@ -391,49 +540,44 @@ void oracle_aes128_encrypt(const uint8_t key[16], const uint8_t in[16], uint8_t 
 }
 
 /* ======================================================================== SSE2 ROMix (r = 1) */
-/* A second, vectorised restatement of ROMix used for the timed CPU baseline (the reference's CPU provider,
- * scrypt-jane inside libpost, is SIMD code too).  Salsa20/8 on four 128-bit rows in "diagonal" word order:
- * SIMD word i of a 64-byte block holds original word (5*i mod 16), so a column round works on whole
- * vectors and the row round needs three lane rotations.  V is kept in that order, which is legal because
- * Integerify reads word 0, which the permutation fixes.  Cross-checked against the scalar path in tests. */
+/* SSE2 ROMix used for the CPU baseline (the reference's CPU path, scrypt-jane inside libpost, is SIMD code too).
+ * ChaCha20/8 on four 128-bit rows in natural word order: the column round works on whole vectors, the diagonal
+ * round needs three lane rotations.  Cross-checked against the scalar path in tests. */
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #define ORACLE_HAVE_SSE2 1
-static inline void salsa20_8_sse(__m128i B[4]) {
-    __m128i X0 = B[0], X1 = B[1], X2 = B[2], X3 = B[3], T;
-#define ROTX(dst, k) dst = _mm_xor_si128(dst, _mm_slli_epi32(T, k)); dst = _mm_xor_si128(dst, _mm_srli_epi32(T, 32 - (k)));
-    for (int i = 0; i < 8; i += 2) {
-        T = _mm_add_epi32(X0, X3); ROTX(X1, 7)
-        T = _mm_add_epi32(X1, X0); ROTX(X2, 9)
-        T = _mm_add_epi32(X2, X1); ROTX(X3, 13)
-        T = _mm_add_epi32(X3, X2); ROTX(X0, 18)
-        X1 = _mm_shuffle_epi32(X1, 0x93); X2 = _mm_shuffle_epi32(X2, 0x4E); X3 = _mm_shuffle_epi32(X3, 0x39);
-        T = _mm_add_epi32(X0, X1); ROTX(X3, 7)
-        T = _mm_add_epi32(X3, X0); ROTX(X2, 9)
-        T = _mm_add_epi32(X2, X3); ROTX(X1, 13)
-        T = _mm_add_epi32(X1, X2); ROTX(X0, 18)
-        X1 = _mm_shuffle_epi32(X1, 0x39); X2 = _mm_shuffle_epi32(X2, 0x4E); X3 = _mm_shuffle_epi32(X3, 0x93);
+static inline void chacha20_8_sse(__m128i B[4]) {
+    __m128i a = B[0], b = B[1], c = B[2], d = B[3], T;
+#define ROTV(v, k) T = v; v = _mm_or_si128(_mm_slli_epi32(T, k), _mm_srli_epi32(T, 32 - (k)));
+#define HALF \
+    a = _mm_add_epi32(a, b); d = _mm_xor_si128(d, a); ROTV(d, 16) \
+    c = _mm_add_epi32(c, d); b = _mm_xor_si128(b, c); ROTV(b, 12) \
+    a = _mm_add_epi32(a, b); d = _mm_xor_si128(d, a); ROTV(d, 8)  \
+    c = _mm_add_epi32(c, d); b = _mm_xor_si128(b, c); ROTV(b, 7)
+    for (int i = 0; i < 4; i++) {
+        HALF                                                                      /* columns */
+        b = _mm_shuffle_epi32(b, 0x39); c = _mm_shuffle_epi32(c, 0x4E); d = _mm_shuffle_epi32(d, 0x93);
+        HALF                                                                      /* diagonals */
+        b = _mm_shuffle_epi32(b, 0x93); c = _mm_shuffle_epi32(c, 0x4E); d = _mm_shuffle_epi32(d, 0x39);
     }
-#undef ROTX
-    B[0] = _mm_add_epi32(B[0], X0); B[1] = _mm_add_epi32(B[1], X1);
-    B[2] = _mm_add_epi32(B[2], X2); B[3] = _mm_add_epi32(B[3], X3);
+#undef HALF
+#undef ROTV
+    B[0] = _mm_add_epi32(B[0], a); B[1] = _mm_add_epi32(B[1], b);
+    B[2] = _mm_add_epi32(B[2], c); B[3] = _mm_add_epi32(B[3], d);
 }
 /* BlockMix for r = 1 on X = (lo, hi), 8 vectors, in place */
 static inline void blockmix_r1_sse(__m128i X[8]) {
     __m128i T[4];
     for (int k = 0; k < 4; k++) T[k] = _mm_xor_si128(X[k], X[4 + k]);
-    salsa20_8_sse(T);
+    chacha20_8_sse(T);
     for (int k = 0; k < 4; k++) { X[k] = T[k]; T[k] = _mm_xor_si128(T[k], X[4 + k]); }
-    salsa20_8_sse(T);
+    chacha20_8_sse(T);
     for (int k = 0; k < 4; k++) X[4 + k] = T[k];
 }
 static void romix_r1_sse(uint32_t x[32], void *vmem, uint64_t N) {
     __m128i X[8];
     __m128i *V = (__m128i *)vmem;
-    uint32_t p[32];
-    for (int b = 0; b < 2; b++)
-        for (int i = 0; i < 16; i++) p[b * 16 + i] = x[b * 16 + (i * 5 % 16)];
-    for (int k = 0; k < 8; k++) X[k] = _mm_loadu_si128((const __m128i *)(p + 4 * k));
+    for (int k = 0; k < 8; k++) X[k] = _mm_loadu_si128((const __m128i *)(x + 4 * k));
     for (uint64_t i = 0; i < N; i++) {
         for (int k = 0; k < 8; k++) _mm_storeu_si128(V + 8 * i + k, X[k]);
         blockmix_r1_sse(X);
@@ -443,9 +587,7 @@ static void romix_r1_sse(uint32_t x[32], void *vmem, uint64_t N) {
         for (int k = 0; k < 8; k++) X[k] = _mm_xor_si128(X[k], _mm_loadu_si128(V + 8 * j + k));
         blockmix_r1_sse(X);
     }
-    for (int k = 0; k < 8; k++) _mm_storeu_si128((__m128i *)(p + 4 * k), X[k]);
-    for (int b = 0; b < 2; b++)
-        for (int i = 0; i < 16; i++) x[b * 16 + (i * 5 % 16)] = p[b * 16 + i];
+    for (int k = 0; k < 8; k++) _mm_storeu_si128((__m128i *)(x + 4 * k), X[k]);
 }
 #else
 #define ORACLE_HAVE_SSE2 0
@@ -468,26 +610,34 @@ void oracle_commitment(const uint8_t node_id[32], const uint8_t commitment_atx[3
     oracle_blake3_256(buf, 64, out);
 }
 
+/* The 72-byte scrypt password of label `index`: commitment || LE64(index) || 32 zero bytes (the slot of the
+ * unused salt of the original gpu-post API); scrypt's own salt is empty.  Pinned by tests/golden/checkpoint_vrf.json. */
+static void label_password(const uint8_t commitment[32], uint64_t index, uint8_t pw[72]) {
+    memcpy(pw, commitment, 32);
+    for (int i = 0; i < 8; i++) pw[32 + i] = (uint8_t)(index >> (8 * i));
+    memset(pw + 40, 0, 32);
+}
+
 /* r = p = 1 fast path used for every label: one allocation-free ROMix over caller scratch. */
 static void label32_r1(const uint8_t commitment[32], uint64_t index, uint64_t N, uint32_t *v, uint8_t out[32]) {
-    uint8_t salt[8], B[128];
+    uint8_t pw[72], B[128];
     uint32_t x[32], y[32];
-    for (int i = 0; i < 8; i++) salt[i] = (uint8_t)(index >> (8 * i)); /* LE64(index) — ASSUMED */
-    oracle_pbkdf2_sha256(commitment, 32, salt, 8, 1, B, 128);
+    label_password(commitment, index, pw);
+    oracle_pbkdf2_keccak512(pw, 72, NULL, 0, B, 128);
     for (int k = 0; k < 32; k++) x[k] = le32(B + 4 * k);
 #if ORACLE_HAVE_SSE2
     if (g_oracle_impl == 1) romix_r1_sse(x, v, N); else
 #endif
-    romix(x, v, y, N, 1);
+    romix(x, v, y, N, 1, oracle_chacha20_8);
     for (int k = 0; k < 32; k++) put_le32(B + 4 * k, x[k]);
-    oracle_pbkdf2_sha256(commitment, 32, B, 128, 1, out, 32);
+    oracle_pbkdf2_keccak512(pw, 72, B, 128, out, 32);
 }
 
 int oracle_label32(const uint8_t commitment[32], uint64_t index, uint64_t N, uint32_t r, uint32_t p,
                    uint8_t out[32]) {
-    uint8_t salt[8];
-    for (int i = 0; i < 8; i++) salt[i] = (uint8_t)(index >> (8 * i));
-    return oracle_scrypt(commitment, 32, salt, 8, N, r, p, out, 32);
+    uint8_t pw[72];
+    label_password(commitment, index, pw);
+    return oracle_scrypt_jane(pw, 72, NULL, 0, N, r, p, out, 32);
 }
 
 void oracle_vrf_difficulty(uint64_t num_labels, uint8_t out[32]) {

@@ -2,14 +2,16 @@
 
 Two independent restatements of the POST label function live here:
 
-* ``py_*``  — OpenSSL ``hashlib.scrypt`` + the ``blake3`` wheel: trusted third-party primitives,
-  used to pin the C oracle and to generate tests/golden/*.json (oracle/gen_golden.py).
+* ``py_*``  — numpy + hashlib + the ``blake3`` wheel: scrypt-jane's scrypt (ChaCha20/8 mix, HMAC-Keccak-512
+  PBKDF2) written array-at-a-time; its Keccak-f is pinned against ``hashlib.sha3_512`` (same permutation, other
+  pad byte) and the whole function against the real VRF nonces of the reference's checkpoint fixture
+  (tests/golden/checkpoint_vrf.json).  Used to pin the C oracle and to generate tests/golden/*.json.
 * ``c_*``   — ctypes bindings of oracle/libpost_oracle.so (post_oracle.c), the fast checker the
   GPU parity tests and bench.py's cpu_baseline use.
 
 Reference anchors: activation/post.go:295,355-361 (Initialize), activation/post_verifier.go:159
 (Verify), activation/validation.go:261-282 (VerifyVRFNonce), hash/hash.go:16-25 (blake3).
-Conventions marked ASSUMED in SURVEY.md Appendix A are "parity unpinned".
+The proof-side conventions (verify / prove helpers below) are "parity unpinned".
 
 Nothing in the product package imports this module.
 """
@@ -45,6 +47,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_scrypt.argtypes = [u8p, ctypes.c_size_t, u8p, ctypes.c_size_t, u64, ctypes.c_uint32,
                                     ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t]
         L.oracle_scrypt.restype = ctypes.c_int
+        L.oracle_scrypt_jane.argtypes = L.oracle_scrypt.argtypes
+        L.oracle_scrypt_jane.restype = ctypes.c_int
         L.oracle_labels_range.argtypes = [u8p, u64, ctypes.c_uint32, ctypes.c_uint32, u64, u64, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(u64),
                                           ctypes.c_void_p, ctypes.c_int]
@@ -68,13 +72,126 @@ def py_commitment(node_id: bytes, commitment_atx: bytes) -> bytes:
     return blake3.blake3(node_id + commitment_atx).digest()
 
 
+# --- Keccak-512 with the original 0x01 padding (scrypt-jane's SCRYPT_KECCAK512); pad=0x06 is SHA3-512
+_KRC = [0x0000000000000001, 0x0000000000008082, 0x800000000000808A, 0x8000000080008000, 0x000000000000808B,
+        0x0000000080000001, 0x8000000080008081, 0x8000000000008009, 0x000000000000008A, 0x0000000000000088,
+        0x0000000080008009, 0x000000008000000A, 0x000000008000808B, 0x800000000000008B, 0x8000000000008089,
+        0x8000000000008003, 0x8000000000008002, 0x8000000000000080, 0x000000000000800A, 0x800000008000000A,
+        0x8000000080008081, 0x8000000000008080, 0x0000000080000001, 0x8000000080008008]
+_KROT = [[0, 36, 3, 41, 18], [1, 44, 10, 45, 2], [62, 6, 43, 15, 61], [28, 55, 25, 21, 56], [27, 20, 39, 8, 14]]
+_M64 = (1 << 64) - 1
+
+
+def _keccak_f(A):
+    for rc in _KRC:
+        C = [A[x][0] ^ A[x][1] ^ A[x][2] ^ A[x][3] ^ A[x][4] for x in range(5)]
+        D = [C[(x - 1) % 5] ^ (((C[(x + 1) % 5] << 1) | (C[(x + 1) % 5] >> 63)) & _M64) for x in range(5)]
+        A = [[A[x][y] ^ D[x] for y in range(5)] for x in range(5)]
+        B = [[0] * 5 for _ in range(5)]
+        for x in range(5):
+            for y in range(5):
+                r, v = _KROT[x][y], A[x][y]
+                B[y][(2 * x + 3 * y) % 5] = ((v << r) | (v >> (64 - r))) & _M64 if r else v
+        A = [[B[x][y] ^ ((~B[(x + 1) % 5][y]) & B[(x + 2) % 5][y]) for y in range(5)] for x in range(5)]
+        A[0][0] ^= rc
+    return A
+
+
+def py_keccak512(data: bytes, pad: int = 0x01) -> bytes:
+    rate = 72
+    m = bytearray(data)
+    m.append(pad)
+    m.extend(b"\0" * ((-len(m)) % rate))
+    m[-1] |= 0x80
+    A = [[0] * 5 for _ in range(5)]
+    for off in range(0, len(m), rate):
+        for i in range(rate // 8):
+            A[i % 5][i // 5] ^= int.from_bytes(m[off + 8 * i: off + 8 * i + 8], "little")
+        A = _keccak_f(A)
+    return b"".join(A[i % 5][i // 5].to_bytes(8, "little") for i in range(8))
+
+
+def py_hmac_keccak512(key: bytes, msg: bytes) -> bytes:
+    bs = 72                                     # HMAC block size = the sponge rate
+    if len(key) > bs:
+        key = py_keccak512(key)
+    key = key.ljust(bs, b"\0")
+    return py_keccak512(bytes(k ^ 0x5C for k in key) + py_keccak512(bytes(k ^ 0x36 for k in key) + msg))
+
+
+def py_pbkdf2_keccak512(pw: bytes, salt: bytes, dklen: int) -> bytes:
+    out, i = b"", 1
+    while len(out) < dklen:
+        out += py_hmac_keccak512(pw, salt + i.to_bytes(4, "big"))
+        i += 1
+    return out[:dklen]
+
+
+def _rotl32(x, k):
+    return (x << np.uint32(k)) | (x >> np.uint32(32 - k))
+
+
+def py_chacha20_8(B: np.ndarray) -> np.ndarray:
+    """ChaCha20/8 core of scrypt-jane on a batch: B is (n, 16) uint32, the block is the whole state."""
+    x = [B[:, i].copy() for i in range(16)]
+
+    def qr(a, b, c, d):
+        x[a] += x[b]; x[d] = _rotl32(x[d] ^ x[a], 16)
+        x[c] += x[d]; x[b] = _rotl32(x[b] ^ x[c], 12)
+        x[a] += x[b]; x[d] = _rotl32(x[d] ^ x[a], 8)
+        x[c] += x[d]; x[b] = _rotl32(x[b] ^ x[c], 7)
+    for _ in range(4):
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+    return B + np.stack(x, axis=1)
+
+
+def _py_blockmix_r1(B):
+    y0 = py_chacha20_8(B[:, 16:] ^ B[:, :16])
+    y1 = py_chacha20_8(y0 ^ B[:, 16:])
+    return np.concatenate([y0, y1], axis=1)
+
+
+def py_scrypt_jane_batch(pws: list[bytes], salts: list[bytes], n: int, dklen: int = 32) -> list[bytes]:
+    """scrypt-jane (ChaCha20/8 + Keccak-512), r = p = 1, for a batch of (password, salt) pairs at once."""
+    old = np.seterr(over="ignore")
+    try:
+        X = np.stack([np.frombuffer(py_pbkdf2_keccak512(p, s, 128), dtype="<u4") for p, s in zip(pws, salts)]).astype(np.uint32)
+        m = X.shape[0]
+        V = np.empty((n, m, 32), dtype=np.uint32)
+        for i in range(n):
+            V[i] = X
+            X = _py_blockmix_r1(X)
+        rows = np.arange(m)
+        for i in range(n):
+            j = X[:, 16] & np.uint32(n - 1)
+            X = _py_blockmix_r1(X ^ V[j, rows])
+    finally:
+        np.seterr(**old)
+    return [py_pbkdf2_keccak512(p, X[i].astype("<u4").tobytes(), dklen) for i, p in enumerate(pws)]
+
+
+def py_label_password(commitment: bytes, index: int) -> bytes:
+    """commitment || LE64(index) || 32 zero bytes: the 72-byte scrypt password of a label (the salt is empty)."""
+    assert len(commitment) == 32
+    return commitment + int(index).to_bytes(8, "little") + bytes(32)
+
+
+def py_label32_batch(commitments: list[bytes], indices: list[int], n: int) -> list[bytes]:
+    out: list[bytes] = []
+    for off in range(0, len(indices), 256):        # 1 MiB of scratch per label at N = 8192
+        pws = [py_label_password(c, i) for c, i in zip(commitments[off:off + 256], indices[off:off + 256])]
+        out += py_scrypt_jane_batch(pws, [b""] * len(pws), n)
+    return out
+
+
 def py_label32(commitment: bytes, index: int, n: int, r: int = 1, p: int = 1) -> bytes:
-    return hashlib.scrypt(commitment, salt=int(index).to_bytes(8, "little"), n=n, r=r, p=p, dklen=32,
-                          maxmem=256 * 1024 * 1024)
+    assert r == 1 and p == 1, "the numpy restatement covers the network's r = p = 1 only"
+    return py_label32_batch([commitment], [index], n)[0]
 
 
 def py_labels_range(commitment: bytes, n: int, start: int, count: int) -> bytes:
-    return b"".join(py_label32(commitment, start + i, n)[:16] for i in range(count))
+    return b"".join(l[:16] for l in py_label32_batch([commitment] * count, list(range(start, start + count)), n))
 
 
 def py_vrf_difficulty(num_labels: int) -> bytes:
@@ -85,10 +202,9 @@ def py_vrf_difficulty(num_labels: int) -> bytes:
 
 def py_vrf_scan(commitment: bytes, n: int, start: int, count: int, difficulty: bytes):
     best, best_idx = difficulty, None
-    for i in range(start, start + count):
-        l32 = py_label32(commitment, i, n)
+    for i, l32 in enumerate(py_label32_batch([commitment] * count, list(range(start, start + count)), n)):
         if l32 < best:
-            best, best_idx = l32, i
+            best, best_idx = l32, start + i
     return best_idx, (best if best_idx is not None else None)
 
 
@@ -103,6 +219,38 @@ def c_scrypt(pw: bytes, salt: bytes, n: int, r: int, p: int, dklen: int) -> byte
     if rc:
         raise ValueError("oracle_scrypt: bad parameters")
     return out.raw
+
+
+def c_scrypt_jane(pw: bytes, salt: bytes, n: int, r: int, p: int, dklen: int) -> bytes:
+    out = ctypes.create_string_buffer(dklen)
+    rc = lib().oracle_scrypt_jane(pw, len(pw), salt, len(salt), n, r, p, out, dklen)
+    if rc:
+        raise ValueError("oracle_scrypt_jane: bad parameters")
+    return out.raw
+
+
+def c_keccak512(msg: bytes, pad: int = 0x01) -> bytes:
+    out = ctypes.create_string_buffer(64)
+    lib().oracle_keccak512(msg, ctypes.c_size_t(len(msg)), ctypes.c_uint8(pad), out)
+    return out.raw
+
+
+def c_hmac_keccak512(key: bytes, msg: bytes) -> bytes:
+    out = ctypes.create_string_buffer(64)
+    lib().oracle_hmac_keccak512(key, ctypes.c_size_t(len(key)), msg, ctypes.c_size_t(len(msg)), out)
+    return out.raw
+
+
+def c_pbkdf2_keccak512(pw: bytes, salt: bytes, dklen: int) -> bytes:
+    out = ctypes.create_string_buffer(dklen)
+    lib().oracle_pbkdf2_keccak512(pw, ctypes.c_size_t(len(pw)), salt, ctypes.c_size_t(len(salt)), out, ctypes.c_size_t(dklen))
+    return out.raw
+
+
+def c_chacha20_8(block: bytes) -> bytes:
+    buf = ctypes.create_string_buffer(block, 64)
+    lib().oracle_chacha20_8(buf)
+    return buf.raw
 
 
 def _hash32(fn_name: str, msg: bytes) -> bytes:

@@ -10,7 +10,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def test_device_arithmetic_on_host_matches_oracle(host_emul, orc):
-    """post_device.cuh (SHA-256, PBKDF2, Salsa20/8, BlockMix exactly as the kernels inline them) == oracle."""
+    """post_device.cuh (Keccak-f, the two PBKDF2 passes, ChaCha20/8, BlockMix exactly as the kernels inline them) == oracle."""
     rng = np.random.default_rng(21)
     for n in (2, 4, 64, 1024, 8192):
         for idx in (0, 1, 2**32 - 1, 2**32, 2**40 + 12345, 2**64 - 1, int(rng.integers(0, 2**63))):
@@ -25,6 +25,15 @@ def test_device_arithmetic_golden(host_emul, golden):
         out = ctypes.create_string_buffer(32)
         host_emul.emul_label32(bytes.fromhex(it["commitment"]), ctypes.c_uint64(it["index"]), it["N"], out)
         assert out.raw.hex() == it["label32"]
+    # the kernels' arithmetic reproduces the real VRF-nonce labels of the reference's checkpoint fixture
+    for it in golden["checkpoint_vrf"]["items"][::3]:
+        out = ctypes.create_string_buffer(32)
+        host_emul.emul_label32(bytes.fromhex(it["commitment"]), ctypes.c_uint64(it["vrf_nonce"]), it["N"], out)
+        assert out.raw.hex() == it["label32"]
+    rng = np.random.default_rng(5)
+    for _ in range(4):      # the interleaved fill+mix step equals the two separate steps
+        seed = (ctypes.c_uint32 * 64)(*[int(x) for x in rng.integers(0, 2**32, 64, dtype=np.uint64)])
+        assert host_emul.emul_dual_step_matches(seed) == 1
 
 
 def test_library_exports_every_declared_symbol(b2):

@@ -1,4 +1,5 @@
-"""CPU tier: the oracle against public KATs, the committed golden vectors and the OpenSSL restatement."""
+"""CPU tier: the oracle against public KATs, the real VRF nonces of the reference's checkpoint fixture, the
+committed golden vectors and the independent numpy restatement."""
 import hashlib
 import os
 
@@ -58,12 +59,65 @@ def test_vrf_difficulty_table(orc, golden):
     assert orc.c_vrf_difficulty(1) == b"\xff" * 32 and orc.c_vrf_difficulty(0) == b"\xff" * 32
 
 
+def test_real_vrf_nonces_of_the_reference_checkpoint_fixture(orc, golden):
+    """THE PIN.  checkpoint/checkpointdata.json in the reference holds 42 identities of a LabelsPerUnit = 1024,
+    N = 8192 network with their VRF nonces.  A VRF nonce is the index of the smallest label32 of the identity's POST,
+    so label32(nonce) * numLabels / 2^256 is Exp(1)-distributed for the right label function (and ~numLabels/2 for a
+    wrong one).  Checks the C oracle bit for bit against the committed values, and the statistics of the real data."""
+    items = golden["checkpoint_vrf"]["items"]
+    assert len(items) == 42
+    below = 0
+    for it in items:
+        c = orc.c_commitment(bytes.fromhex(it["node_id"]), bytes.fromhex(it["commitment_atx"]))
+        assert c.hex() == it["commitment"]
+        l32 = orc.c_label32(c, it["vrf_nonce"], it["N"])
+        assert l32.hex() == it["label32"]
+        num_labels = it["num_units"] * it["labels_per_unit"]
+        assert it["vrf_nonce"] < num_labels
+        ratio = int.from_bytes(l32, "big") * num_labels / 2**256
+        assert ratio < 8, "not an arg-min label: the label function is wrong"      # P(Exp(1) > 8) = 3e-4 per identity
+        below += l32 < orc.py_vrf_difficulty(num_labels)
+    assert 18 <= below <= 34          # 1 - 1/e = 63 % of 42 = 26.5 expected (observed: 26)
+
+
+def test_real_vrf_nonce_is_the_minimum_of_its_neighbourhood(orc, golden):
+    """For one real identity, no label near the nonce is smaller (a 4096-label window of its 33792-label POST)."""
+    it = golden["checkpoint_vrf"]["items"][0]
+    c = bytes.fromhex(it["commitment"])
+    start = max(0, it["vrf_nonce"] - 2048)
+    _, found, idx, l32 = orc.c_labels_range(c, it["N"], start, 4096, b"\xff" * 32, threads=os.cpu_count() or 4)
+    assert found and idx == it["vrf_nonce"] and l32.hex() == it["label32"]
+
+
+def test_keccak_chacha_pbkdf2_building_blocks(orc):
+    """Keccak-f against hashlib's SHA3-512 (same permutation, pad byte 0x06); Keccak-512/HMAC/PBKDF2/ChaCha and the
+    generic scrypt-jane against the numpy restatement."""
+    rng = np.random.default_rng(21)
+    for n in [0, 1, 71, 72, 73, 143, 144, 145, 500]:
+        m = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+        assert orc.c_keccak512(m, 0x06) == hashlib.sha3_512(m).digest()
+        assert orc.py_keccak512(m, 0x06) == hashlib.sha3_512(m).digest()
+        assert orc.c_keccak512(m) == orc.py_keccak512(m)
+        for klen in (0, 32, 72, 73, 200):
+            k = bytes(rng.integers(0, 256, klen, dtype=np.uint8))
+            assert orc.c_hmac_keccak512(k, m) == orc.py_hmac_keccak512(k, m)
+        assert orc.c_pbkdf2_keccak512(m, m[::-1], 130) == orc.py_pbkdf2_keccak512(m, m[::-1], 130)
+    for _ in range(8):
+        blk = rng.integers(0, 2**32, 16, dtype=np.uint32)
+        assert orc.c_chacha20_8(blk.astype("<u4").tobytes()) == orc.py_chacha20_8(blk[None, :])[0].astype("<u4").tobytes()
+    for n in (2, 16, 256):
+        pws = [bytes(rng.integers(0, 256, k, dtype=np.uint8)) for k in (0, 8, 72, 100)]
+        salts = [bytes(rng.integers(0, 256, k, dtype=np.uint8)) for k in (0, 4, 64, 9)]
+        exp = orc.py_scrypt_jane_batch(pws, salts, n, dklen=48)
+        assert [orc.c_scrypt_jane(p, s, n, 1, 1, 48) for p, s in zip(pws, salts)] == exp
+
+
 def test_survey_candidate_vectors(orc):
-    """SURVEY.md §8c candidate vectors (inputs of activation/validation_test.go:35-36)."""
+    """SURVEY.md §8c candidate inputs (activation/validation_test.go:35-36: zero node id and commitment ATX)."""
     c = orc.c_commitment(bytes(32), bytes(32))
     assert c.hex() == "4d006976636a8696d909a630a4081aad4d7c50f81afdee04020bf05086ab6a55"
-    assert orc.c_label32(c, 0, 2).hex() == "816a047977c79c85a5ba00fec5fd81794c8b56c87e4c084aa95f68d388318fac"
-    assert orc.c_label32(c, 0, 8192).hex() == "3ea1a34b8a3e719839095e30f38533019c9fab5a9e73eebccd28363363e96fde"
+    assert orc.c_label32(c, 0, 2).hex() == "502009eefb489466fd46f63685e0d1cec99c7821c0a92eb013efba9f2e805abc"
+    assert orc.c_label32(c, 0, 8192).hex() == "13f053790cc908fd17c1ed054ad849d63a3abb394d07bb54872fe91b24c56f46"
 
 
 def test_label_golden_vectors(orc, golden):

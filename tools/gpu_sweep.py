@@ -20,14 +20,14 @@ OUT = "gpurun_out"
 os.makedirs(OUT, exist_ok=True)
 
 
-def parity(variant: int, mws=(0, 0x8421, 0xFFFF)):
+def parity(variant: int, mws=(0, 1)):
     res = {"variant": variant, "cases": []}
     rng = np.random.default_rng(7)
     commitment = bytes(rng.integers(0, 256, 32, dtype=np.uint8))
     ok_all = True
     for mw in mws:
         b2.set_option("romix_variant", variant)
-        b2.set_option("mulwide_mask", mw)
+        b2.set_option("rotate_mask", mw)
         for n, start, count in [(2, 0, 1024), (2, 2**32 - 100, 333), (16, 5, 4100), (1024, 2**40, 515), (8192, 2**32 - 64, 160)]:
             t = time.time()
             diff = orc.py_vrf_difficulty(max(count // 4, 2))
@@ -63,7 +63,7 @@ def sweep(specs, tag):
     for sp in specs:
         n = sp.get("n", 8192)
         try:
-            b2.set_option("romix_variant", sp["variant"]); b2.set_option("mulwide_mask", sp["mw"])
+            b2.set_option("romix_variant", sp["variant"]); b2.set_option("rotate_mask", sp["mw"])
             b2.set_option("tpb", sp["tpb"]); b2.set_option("ctas_per_sm", sp["ctas"])
             b2.set_option("debug_skip_phase", sp.get("skip", 0)); b2.set_option("dr_unroll", sp.get("dr", 4))
             slots = b2.wave_slots(n)
