@@ -377,9 +377,10 @@ def main() -> None:
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "romix_pipe_kernel" if b2.get_option("romix_variant") == 4 else "romix_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                         # integer roofline of the label function: 9.04 M alu-pipe ops per label at the measured
-                         # 64 ops/clk/SM (profiles/r01_alubench.log) and the maximum SM clock
-                         "int_roofline_labels_per_s": prov["sm_count"] * 64 * 1.965e9 / (16384 * (512 + 40)),
+                         # integer roofline of the label function: 2N BlockMix x 553 alu-pipe instructions (512 XOR/rotate
+                         # of two ChaCha20/8 cores + 41 XOR/address, counted in the SASS) = 9.06 M per label, at the
+                         # measured 64 ops/clk/SM (profiles/r01_alubench.log) and the maximum SM clock
+                         "int_roofline_labels_per_s": prov["sm_count"] * 64 * 1.965e9 / (16384 * 553),
                          "alu_ceiling_labels_per_s": alu_probe,
                          "frac_of_alu_ceiling": (labels_per_launch / (romix_avg_ms / 1e3) / alu_probe) if alu_probe and romix_avg_ms > 0 else None,
                          "bytes_per_label": BYTES_PER_LABEL, "labels_per_launch": labels_per_launch,

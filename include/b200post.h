@@ -110,7 +110,7 @@ int b200post_labels_gather(uint32_t provider, size_t n_items, const uint8_t *com
 
 /* Same for items that share few commitments (one identity checked at K2 indices): commitments =
  * n_commitments x 32 bytes (HOST), commitment_index = n_items u32 rows into it (HOST, each < n_commitments).
- * Midstates are derived once per commitment and 4 instead of 32 bytes per item cross PCIe. */
+ * 4 instead of 32 bytes per item cross PCIe. */
 int b200post_labels_gather_indexed(uint32_t provider, size_t n_items, size_t n_commitments, const uint8_t *commitments,
                                    const uint32_t *commitment_index, const uint64_t *indices, uint64_t n,
                                    uint8_t *out16);

@@ -243,7 +243,7 @@ def test_launch_counter_and_timers(b2):
     before = b2.launch_count()
     b2.romix_time(reset=True)
     b2.labels_range(bytes(32), 2, 0, 64, discard=True)
-    assert b2.launch_count() - before >= 4        # K0..K3
+    assert b2.launch_count() - before >= 3        # K1..K3
     ms, k, lab = b2.romix_time()
     assert k >= 1 and ms > 0 and lab == 64 and b2.last_call_ms() > 0
 
