@@ -81,7 +81,8 @@ const char *b200post_last_error(void);
 int b200post_set_option(const char *key, int64_t value);
 int64_t b200post_get_option(const char *key);
 
-/* label[i] = scrypt(P = commitment, S = LE64(i), N = n, r = 1, p = 1, dkLen = 32)[0:16] for
+/* label[i] = scrypt_jane(P = commitment || LE64(i) || 0^32, S = "", N = n, r = 1, p = 1, dkLen = 32)[0:16]
+ * (scrypt with the ChaCha20/8 mix and HMAC-Keccak-512 PBKDF2 = libpost's label function) for
  * i in [start, start+count).  out16 = HOST buffer of 16*count bytes (may be NULL to discard, e.g. a
  * /dev/null init).  If vrf_difficulty != NULL (32 bytes, big-endian) the VRF-nonce scan runs over the
  * full 32-byte outputs and *nonce is filled (nonce may not be NULL then).
