@@ -1,5 +1,5 @@
 """Dev tool (GPU box): one verify batch (2000 proofs x 37, N=8192) and one proving scan (2^22 labels, 288 nonces),
-for an ncu launch list of the non-init kernels (K0, K1, K2p, K3, K5, K6a, K6b)."""
+for an ncu launch list of the non-init kernels (K1, K2p, K3, K5, K6a, K6b)."""
 import importlib, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
