@@ -33,7 +33,7 @@ md.append(f"\nDerived: slots = {slots}; algorithmic bytes per launch = slots x 2
 md.append(f"Label-equivalents/s in this (profiled) launch: {slots/ms*1e3:,.0f}; {alg/ms/1e6:,.0f} GB/s algorithmic.\n")
 md.append("\nWarp stall reasons (cycles per issued instruction):\n\n| stall | ratio |\n|---|---|\n")
 md += [f"| {n} | {v:.3f} |\n" for n, v in stalls[:10]]
-md.append("\nReading: the alu pipe (LOP3 + SHF of the ChaCha20/8 add-xor-rotate steps) is the busiest unit (math_pipe_throttle / not_selected are the top stalls, long_scoreboard is gone); fmaheavy carries the IMAD.IADD adds; DRAM sits near 45 % of its peak: the kernel is integer-issue-bound, not HBM-bound (DESIGN.md §4).\n")
+md.append("\nReading: the alu pipe (LOP3 + SHF of the ChaCha20/8 add-xor-rotate steps) is the busiest unit (math_pipe_throttle / not_selected are the top stalls, long_scoreboard is gone); fmaheavy carries the IMAD.IADD adds; DRAM sits near 49 % of its peak: the kernel is integer-issue-bound, not HBM-bound (DESIGN.md §4).\n")
 open(f'profiles/{tag}_romix_pipe_ncu_full.md', 'w').write(''.join(md))
 json.dump({"kernel": d['Kernel Name'][0], "slots": slots, "dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr,
            "algorithmic_bytes_per_launch": alg, "source": f"profiles/{tag}_romix_pipe_ncu_full.md"},
