@@ -539,7 +539,7 @@ void oracle_aes128_encrypt(const uint8_t key[16], const uint8_t in[16], uint8_t 
     memcpy(out, s, 16);
 }
 
-/* ======================================================================== SSE2 ROMix (r = 1) */
+/* ======================================================================== SSE2 / AVX2 ROMix (r = 1) */
 /* SSE2 ROMix used for the CPU baseline (the reference's CPU path, scrypt-jane inside libpost, is SIMD code too).
  * ChaCha20/8 on four 128-bit rows in natural word order: the column round works on whole vectors, the diagonal
  * round needs three lane rotations.  Cross-checked against the scalar path in tests. */
@@ -589,14 +589,78 @@ static void romix_r1_sse(uint32_t x[32], void *vmem, uint64_t N) {
     }
     for (int k = 0; k < 8; k++) _mm_storeu_si128((__m128i *)(x + 4 * k), X[k]);
 }
+#if defined(__AVX2__)
+#include <immintrin.h>
+#define ORACLE_HAVE_AVX2 1
+/* Two labels per thread: the low 128-bit lane of every vector belongs to label A, the high lane to label B (all AVX2
+ * integer ops used here work per lane).  16- and 8-bit rotates are one byte shuffle. */
+static inline void chacha20_8_avx2(__m256i B[4]) {
+    const __m256i R16 = _mm256_setr_epi8(2, 3, 0, 1, 6, 7, 4, 5, 10, 11, 8, 9, 14, 15, 12, 13, 2, 3, 0, 1, 6, 7, 4, 5, 10, 11, 8, 9, 14, 15, 12, 13);
+    const __m256i R8 = _mm256_setr_epi8(3, 0, 1, 2, 7, 4, 5, 6, 11, 8, 9, 10, 15, 12, 13, 14, 3, 0, 1, 2, 7, 4, 5, 6, 11, 8, 9, 10, 15, 12, 13, 14);
+    __m256i a = B[0], b = B[1], c = B[2], d = B[3];
+#define ROTS(v, k) v = _mm256_or_si256(_mm256_slli_epi32(v, k), _mm256_srli_epi32(v, 32 - (k)));
+#define HALF2 \
+    a = _mm256_add_epi32(a, b); d = _mm256_shuffle_epi8(_mm256_xor_si256(d, a), R16); \
+    c = _mm256_add_epi32(c, d); b = _mm256_xor_si256(b, c); ROTS(b, 12) \
+    a = _mm256_add_epi32(a, b); d = _mm256_shuffle_epi8(_mm256_xor_si256(d, a), R8); \
+    c = _mm256_add_epi32(c, d); b = _mm256_xor_si256(b, c); ROTS(b, 7)
+    for (int i = 0; i < 4; i++) {
+        HALF2
+        b = _mm256_shuffle_epi32(b, 0x39); c = _mm256_shuffle_epi32(c, 0x4E); d = _mm256_shuffle_epi32(d, 0x93);
+        HALF2
+        b = _mm256_shuffle_epi32(b, 0x93); c = _mm256_shuffle_epi32(c, 0x4E); d = _mm256_shuffle_epi32(d, 0x39);
+    }
+#undef HALF2
+#undef ROTS
+    B[0] = _mm256_add_epi32(B[0], a); B[1] = _mm256_add_epi32(B[1], b);
+    B[2] = _mm256_add_epi32(B[2], c); B[3] = _mm256_add_epi32(B[3], d);
+}
+static inline void blockmix_r1_avx2(__m256i X[8]) {
+    __m256i T[4];
+    for (int k = 0; k < 4; k++) T[k] = _mm256_xor_si256(X[k], X[4 + k]);
+    chacha20_8_avx2(T);
+    for (int k = 0; k < 4; k++) { X[k] = T[k]; T[k] = _mm256_xor_si256(T[k], X[4 + k]); }
+    chacha20_8_avx2(T);
+    for (int k = 0; k < 4; k++) X[4 + k] = T[k];
+}
+/* ROMix of labels A and B in lock-step; va / vb are their private 128*N-byte scratchpads */
+static void romix_r1_avx2_x2(uint32_t xa[32], uint32_t xb[32], void *va, void *vb, uint64_t N) {
+    __m256i X[8];
+    __m128i *VA = (__m128i *)va, *VB = (__m128i *)vb;
+    for (int k = 0; k < 8; k++)
+        X[k] = _mm256_set_m128i(_mm_loadu_si128((const __m128i *)(xb + 4 * k)), _mm_loadu_si128((const __m128i *)(xa + 4 * k)));
+    for (uint64_t i = 0; i < N; i++) {
+        for (int k = 0; k < 8; k++) {
+            _mm_storeu_si128(VA + 8 * i + k, _mm256_castsi256_si128(X[k]));
+            _mm_storeu_si128(VB + 8 * i + k, _mm256_extracti128_si256(X[k], 1));
+        }
+        blockmix_r1_avx2(X);
+    }
+    for (uint64_t i = 0; i < N; i++) {
+        const uint64_t ja = (uint32_t)_mm_cvtsi128_si32(_mm256_castsi256_si128(X[4])) & (N - 1);
+        const uint64_t jb = (uint32_t)_mm_cvtsi128_si32(_mm256_extracti128_si256(X[4], 1)) & (N - 1);
+        for (int k = 0; k < 8; k++)
+            X[k] = _mm256_xor_si256(X[k], _mm256_set_m128i(_mm_loadu_si128(VB + 8 * jb + k), _mm_loadu_si128(VA + 8 * ja + k)));
+        blockmix_r1_avx2(X);
+    }
+    for (int k = 0; k < 8; k++) {
+        _mm_storeu_si128((__m128i *)(xa + 4 * k), _mm256_castsi256_si128(X[k]));
+        _mm_storeu_si128((__m128i *)(xb + 4 * k), _mm256_extracti128_si256(X[k], 1));
+    }
+}
+#else
+#define ORACLE_HAVE_AVX2 0
+#endif
 #else
 #define ORACLE_HAVE_SSE2 0
+#define ORACLE_HAVE_AVX2 0
 #endif
 
-static int g_oracle_impl = ORACLE_HAVE_SSE2;   /* 0 = scalar restatement, 1 = SSE2 */
+static int g_oracle_impl = ORACLE_HAVE_AVX2 ? 2 : ORACLE_HAVE_SSE2;   /* 0 = scalar restatement, 1 = SSE2, 2 = AVX2 two labels at a time */
 int oracle_set_impl(int impl) {
     if (impl == 1 && !ORACLE_HAVE_SSE2) return -1;
-    if (impl != 0 && impl != 1) return -1;
+    if (impl == 2 && !ORACLE_HAVE_AVX2) return -1;
+    if (impl < 0 || impl > 2) return -1;
     g_oracle_impl = impl;
     return 0;
 }
@@ -626,12 +690,29 @@ static void label32_r1(const uint8_t commitment[32], uint64_t index, uint64_t N,
     oracle_pbkdf2_keccak512(pw, 72, NULL, 0, B, 128);
     for (int k = 0; k < 32; k++) x[k] = le32(B + 4 * k);
 #if ORACLE_HAVE_SSE2
-    if (g_oracle_impl == 1) romix_r1_sse(x, v, N); else
+    if (g_oracle_impl >= 1) romix_r1_sse(x, v, N); else
 #endif
     romix(x, v, y, N, 1, oracle_chacha20_8);
     for (int k = 0; k < 32; k++) put_le32(B + 4 * k, x[k]);
     oracle_pbkdf2_keccak512(pw, 72, B, 128, out, 32);
 }
+
+#if ORACLE_HAVE_AVX2
+/* two labels at once (AVX2 lanes); va / vb = two scratchpads of 128*N bytes */
+static void label32_r1_x2(const uint8_t ca[32], uint64_t ia, const uint8_t cb[32], uint64_t ib, uint64_t N,
+                          uint32_t *va, uint32_t *vb, uint8_t outa[32], uint8_t outb[32]) {
+    uint8_t pwa[72], pwb[72], Ba[128], Bb[128];
+    uint32_t xa[32], xb[32];
+    label_password(ca, ia, pwa); label_password(cb, ib, pwb);
+    oracle_pbkdf2_keccak512(pwa, 72, NULL, 0, Ba, 128);
+    oracle_pbkdf2_keccak512(pwb, 72, NULL, 0, Bb, 128);
+    for (int k = 0; k < 32; k++) { xa[k] = le32(Ba + 4 * k); xb[k] = le32(Bb + 4 * k); }
+    romix_r1_avx2_x2(xa, xb, va, vb, N);
+    for (int k = 0; k < 32; k++) { put_le32(Ba + 4 * k, xa[k]); put_le32(Bb + 4 * k, xb[k]); }
+    oracle_pbkdf2_keccak512(pwa, 72, Ba, 128, outa, 32);
+    oracle_pbkdf2_keccak512(pwb, 72, Bb, 128, outb, 32);
+}
+#endif
 
 int oracle_label32(const uint8_t commitment[32], uint64_t index, uint64_t N, uint32_t r, uint32_t p,
                    uint8_t out[32]) {
@@ -665,7 +746,7 @@ typedef struct {
 
 static void *worker(void *p) {
     worker_arg *a = (worker_arg *)p;
-    uint32_t *v = (uint32_t *)malloc(128 * (size_t)a->N);
+    uint32_t *v = (uint32_t *)malloc(2 * 128 * (size_t)a->N);   /* two scratchpads: the AVX2 path does two labels at a time */
     if (!v) { a->rc = -1; return NULL; }
     /* contiguous sub-range per thread so that "first index wins ties" is easy to merge */
     uint64_t per = (a->count + a->nthreads - 1) / a->nthreads;
@@ -674,13 +755,25 @@ static void *worker(void *p) {
     a->found = 0;
     if (a->vrf_difficulty) memcpy(a->best, a->vrf_difficulty, 32);
     for (uint64_t k = lo; k < hi; k++) {
-        uint8_t l32[32];
-        if (a->gather) label32_r1(a->commitment + 32 * k, a->indices[k], a->N, v, l32);
-        else label32_r1(a->commitment, a->start + k, a->N, v, l32);
-        if (a->out16) memcpy(a->out16 + 16 * k, l32, 16);
-        if (a->vrf_difficulty && memcmp(l32, a->best, 32) < 0) {
-            memcpy(a->best, l32, 32); a->best_index = a->start + k; a->found = 1;
+        uint8_t l32[2][32];
+        int n = 1;
+#if ORACLE_HAVE_AVX2
+        if (g_oracle_impl == 2 && k + 1 < hi) {
+            n = 2;
+            if (a->gather) label32_r1_x2(a->commitment + 32 * k, a->indices[k], a->commitment + 32 * (k + 1), a->indices[k + 1], a->N,
+                                         v, v + 32 * a->N, l32[0], l32[1]);
+            else label32_r1_x2(a->commitment, a->start + k, a->commitment, a->start + k + 1, a->N, v, v + 32 * a->N, l32[0], l32[1]);
+        } else
+#endif
+        if (a->gather) label32_r1(a->commitment + 32 * k, a->indices[k], a->N, v, l32[0]);
+        else label32_r1(a->commitment, a->start + k, a->N, v, l32[0]);
+        for (int q = 0; q < n; q++) {
+            if (a->out16) memcpy(a->out16 + 16 * (k + q), l32[q], 16);
+            if (a->vrf_difficulty && memcmp(l32[q], a->best, 32) < 0) {
+                memcpy(a->best, l32[q], 32); a->best_index = a->start + k + q; a->found = 1;
+            }
         }
+        k += n - 1;
     }
     free(v);
     a->rc = 0;

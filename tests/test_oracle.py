@@ -173,20 +173,25 @@ def test_bad_parameters_rejected(orc):
     assert labels.shape == (0, 16) and not found
 
 
-def test_sse2_and_scalar_romix_agree(orc):
-    """The vectorised ROMix used for the timed CPU baseline is the same function as the scalar restatement."""
+def test_simd_and_scalar_romix_agree(orc):
+    """The vectorised ROMix paths used for the timed CPU baseline (1 = SSE2, 2 = AVX2 with two labels per thread in
+    lock-step) are the same function as the scalar restatement, odd counts and the VRF scan included."""
     L = orc.lib()
-    if L.oracle_set_impl(1) != 0:
-        pytest.skip("no SSE2")
+    default = L.oracle_get_impl()
     try:
         rng = np.random.default_rng(31)
         for n in (2, 4, 64, 1024, 8192):
             c = bytes(rng.integers(0, 256, 32, dtype=np.uint8))
             d = orc.py_vrf_difficulty(8)
             L.oracle_set_impl(0)
-            a = orc.c_labels_range(c, n, 2**32 - 3, 24, d, threads=2)
-            L.oracle_set_impl(1)
-            b = orc.c_labels_range(c, n, 2**32 - 3, 24, d, threads=2)
-            assert (a[0] == b[0]).all() and a[1:] == b[1:], n
+            a = orc.c_labels_range(c, n, 2**32 - 3, 25, d, threads=2)
+            comms = rng.integers(0, 256, (9, 32), dtype=np.uint8); idx = rng.integers(0, 2**40, 9, dtype=np.uint64)
+            ga = orc.c_labels_gather(comms, idx, n, threads=2)
+            for impl in (1, 2):
+                if L.oracle_set_impl(impl) != 0:
+                    continue
+                b = orc.c_labels_range(c, n, 2**32 - 3, 25, d, threads=2)
+                assert (a[0] == b[0]).all() and a[1:] == b[1:], (n, impl)
+                assert (orc.c_labels_gather(comms, idx, n, threads=2) == ga).all(), (n, impl)
     finally:
-        L.oracle_set_impl(1)
+        L.oracle_set_impl(default)
