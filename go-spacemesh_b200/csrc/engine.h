@@ -19,7 +19,7 @@ struct Options {
     std::atomic<int64_t> romix_variant{ROMIX_PIPELINED};
     std::atomic<int64_t> rotate_mask{0};
     std::atomic<int64_t> tpb{512};             // pipelined default: one 16-warp CTA per SM (measured best)
-    std::atomic<int64_t> dr_unroll{4};         // pipelined kernel: Salsa double-rounds unrolled (4) or rolled (1)
+    std::atomic<int64_t> dr_unroll{4};         // pipelined kernel: ChaCha double-rounds unrolled (4) or rolled (1)
     std::atomic<int64_t> ctas_per_sm{0};       // 0 = occupancy maximum
     std::atomic<int64_t> max_scratch_mib{0};   // 0 = 90 % of free HBM
     std::atomic<int64_t> speculate_next{1};    // pipelined range jobs of >= 4 layers pre-fill the next range's first layer
@@ -77,7 +77,7 @@ private:
     void release();
     int run_job(const Job &job);
     // b = buffer parity of the layer (layer index + parity offset of the call)
-    int stage_layer(const Job &job, uint64_t layer, int b, uint32_t n_valid, LabelJob *lj);          // inputs + K0 + K1
+    int stage_layer(const Job &job, uint64_t layer, int b, uint32_t n_valid, LabelJob *lj);          // inputs + K1
     int finish_layer(const Job &job, uint64_t layer, int b, uint32_t n_valid, const LabelJob &lj);   // K3 (+K4) + D2H + event
     int retire(const Job &job, int buf);
     void harvest(int buf);
