@@ -54,6 +54,27 @@ def test_golden_gather_vectors(b2, golden):
             assert row.tobytes().hex() == it["label32"][:32]
 
 
+def test_real_vrf_nonces_of_the_reference_checkpoint_fixture(b2, golden):
+    """REAL DATA through the product path: the 42 identities of the reference's checkpoint/checkpointdata.json.  The GPU's
+    label at each identity's VRF nonce is the committed label32 (an arg-min label: within a small factor of
+    2^256/numLabels), `b200post_verify_vrf_nonce` judges it as the threshold says, and for two identities the fused VRF
+    scan over a 4096-label window of their POST returns exactly that nonce as the minimum."""
+    items = golden["checkpoint_vrf"]["items"]
+    comms = np.frombuffer(b"".join(bytes.fromhex(it["commitment"]) for it in items), dtype=np.uint8).reshape(-1, 32)
+    idx = np.array([it["vrf_nonce"] for it in items], dtype=np.uint64)
+    got = b2.labels_gather(comms, idx, 8192)
+    for row, it in zip(got, items):
+        assert row.tobytes().hex() == it["label32"][:32]
+        num_labels = it["num_units"] * it["labels_per_unit"]
+        below = bytes.fromhex(it["label32"]) < b2.vrf_difficulty(num_labels)
+        assert b2.verify_vrf_nonce(it["vrf_nonce"], bytes.fromhex(it["node_id"]), bytes.fromhex(it["commitment_atx"]),
+                                   it["num_units"], it["labels_per_unit"], 8192) == below
+    for it in (items[1], items[-1]):
+        start = max(0, it["vrf_nonce"] - 2048)
+        _, vrf = b2.labels_range(bytes.fromhex(it["commitment"]), 8192, start, 4096, vrf_difficulty_=b"\xff" * 32, discard=True)
+        assert vrf == (it["vrf_nonce"], bytes.fromhex(it["label32"]))
+
+
 @pytest.mark.parametrize("n,start,count", [
     (2, 0, 1024),                 # BASELINE.json configs[0] shape
     (2, 2**32 - 100, 333),        # 64-bit salt, ragged
