@@ -58,7 +58,7 @@ void DeviceEngine::release() {
         cudaFreeHost(h_commit_[b]); h_commit_[b] = nullptr;
         cudaFreeHost(h_idx_[b]); h_idx_[b] = nullptr;
         cudaFree(d_cidx_[b]); d_cidx_[b] = nullptr; cudaFreeHost(h_cidx_[b]); h_cidx_[b] = nullptr;
-        cudaEvent_t *evs[] = {&ev_done_[b], &ev_in_[b], &ev_k2a_[b], &ev_k2b_[b], &ev_call_[b]};
+        cudaEvent_t *evs[] = {&ev_done_[b], &ev_in_[b], &ev_k3_[b], &ev_k2a_[b], &ev_k2b_[b], &ev_call_[b]};
         for (cudaEvent_t *e : evs) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
         k2_pending_[b] = false; in_pending_[b] = false; pend_[b].live = false;
     }
@@ -70,6 +70,8 @@ void DeviceEngine::release() {
     cudaFree(d_running_); d_running_ = nullptr;
     cudaFreeHost(h_running_); h_running_ = nullptr;
     if (stream_) cudaStreamDestroy(stream_);
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
+    copy_stream_ = nullptr;
     stream_ = nullptr;
     alloc_slots_ = 0;
     wave_slots_ = 0;
@@ -84,9 +86,11 @@ int DeviceEngine::ensure(uint64_t N, uint64_t want_slots) {
     const int dr = (int)o.dr_unroll.load();
     if (!stream_) {
         CU_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
         for (int b = 0; b < 2; b++) {
             CU_TRY(cudaEventCreateWithFlags(&ev_done_[b], cudaEventDisableTiming));
             CU_TRY(cudaEventCreateWithFlags(&ev_in_[b], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&ev_k3_[b], cudaEventDisableTiming));
             CU_TRY(cudaEventCreate(&ev_k2a_[b]));
             CU_TRY(cudaEventCreate(&ev_k2b_[b]));
             CU_TRY(cudaEventCreate(&ev_call_[b]));
@@ -217,8 +221,15 @@ int DeviceEngine::finish_layer(const Job &job, uint64_t layer, int b, uint32_t n
         CU_TRY(launch_vrf_merge(d_cta_cand_, pbkdf2_final_ctas(n_slots), d_running_, stream_));
         g_launches += 1;
     }
-    if (job.out_host) CU_TRY(cudaMemcpyAsync(h_out_[b], d_out_[b], (size_t)n_valid * 16, cudaMemcpyDeviceToHost, stream_));
-    CU_TRY(cudaEventRecord(ev_done_[b], stream_));
+    if (job.out_host) {
+        // the copy runs on its own stream: the next layers' kernels do not queue behind PCIe
+        CU_TRY(cudaEventRecord(ev_k3_[b], stream_));
+        CU_TRY(cudaStreamWaitEvent(copy_stream_, ev_k3_[b], 0));
+        CU_TRY(cudaMemcpyAsync(h_out_[b], d_out_[b], (size_t)n_valid * 16, cudaMemcpyDeviceToHost, copy_stream_));
+        CU_TRY(cudaEventRecord(ev_done_[b], copy_stream_));
+    } else {
+        CU_TRY(cudaEventRecord(ev_done_[b], stream_));
+    }
     pend_[b] = Pending{off, n_valid, true};
     return B200POST_OK;
 }
@@ -267,7 +278,6 @@ int DeviceEngine::run_job(const Job &job) {
             bool fill = false;
             uint32_t n_fill = 0;
             if (m < M) {
-                if ((rc_ = retire(job, b))) return rc_;   // layer m-2 used this parity's buffers
                 nv[b] = layer_count(m);
                 if (m == 0 && resume) {
                     lj[b] = LabelJob{d_range_commit_, 0, nullptr, job.start, nv[b], nullptr};   // already filled: X_[b] holds its mid-state
@@ -277,7 +287,6 @@ int DeviceEngine::run_job(const Job &job) {
                 }
             } else if (speculate && status == B200POST_OK) {
                 // one layer past the end of this call: the next initialize() batch, if it comes
-                if ((rc_ = retire(job, b))) return rc_;
                 LabelJob next;
                 Job after = job;                       // the range that would follow this call: [start + total, ...)
                 after.start = job.start + job.total;
@@ -318,7 +327,13 @@ int DeviceEngine::run_job(const Job &job) {
                     fclose(f);
                 }
             }
-            if (m >= 1 && (rc_ = finish_layer(job, m - 1, b ^ 1, nv[b ^ 1], lj[b ^ 1]))) return rc_;
+            if (m >= 1) {
+                // layer m-3 used the output buffers of this parity.  Waiting for it HERE, after launch m is queued,
+                // keeps one whole launch ahead of the host: a slow wake-up, host copy or PCIe transfer does not
+                // leave the GPU idle between layers.
+                if ((rc_ = retire(job, b ^ 1))) return rc_;
+                if ((rc_ = finish_layer(job, m - 1, b ^ 1, nv[b ^ 1], lj[b ^ 1]))) return rc_;
+            }
         }
         if (spec_filled && status == B200POST_OK) {
             spec_.valid = true; spec_.N = job.N; spec_.next_start = job.start + job.total; spec_.parity = par(M);
@@ -408,6 +423,7 @@ int DeviceEngine::labels_gather(size_t n_items, const uint8_t *commitments, cons
 void DeviceEngine::quiesce() {
     const std::string keep = last_error();
     if (stream_) cudaStreamSynchronize(stream_);
+    if (copy_stream_) cudaStreamSynchronize(copy_stream_);
     cudaGetLastError();
     for (int b = 0; b < 2; b++) { pend_[b].live = false; k2_pending_[b] = false; in_pending_[b] = false; }
     spec_.valid = false;

@@ -109,6 +109,8 @@ private:
     VrfCandidate *d_running_ = nullptr;
     VrfCandidate *h_running_ = nullptr;            // pinned
     cudaEvent_t ev_done_[2] = {nullptr, nullptr};  // layer outputs are in h_out_[b]
+    cudaEvent_t ev_k3_[2] = {nullptr, nullptr};    // K3 of the layer has written d_out_[b] (the copy stream waits on it)
+    cudaStream_t copy_stream_ = nullptr;           // D2H of finished labels, off the kernels' stream
     cudaEvent_t ev_in_[2] = {nullptr, nullptr};    // layer inputs have left h_commit_/h_idx_[b]
     bool in_pending_[2] = {false, false};
     cudaEvent_t ev_k2a_[2] = {nullptr, nullptr}, ev_k2b_[2] = {nullptr, nullptr};
