@@ -190,7 +190,7 @@ def run_reference(args, rank: int, world: int) -> None:
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "labels/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "4-SU POST init (2^34 labels), scrypt N=8192 r=1 p=1, labels discarded",
+            "config": {"workload": "4-SU POST init (2^34 labels), scrypt-jane (ChaCha20/8 + Keccak-512) N=8192 r=1 p=1, labels discarded",
                        "step": f"bounded sample: {per_step} labels per step on {cores} host threads"},
             "cpu_baseline": {"value": value, "unit": "labels/s", "cores": cores, "kind": "port",
                              "sample": f"{per_step} labels/step x {args.steps} steps, oracle/post_oracle.c"},
@@ -365,7 +365,7 @@ def main() -> None:
             "metric": METRIC, "value": value, "unit": "labels/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "4-SU POST init (2^34 labels/GPU), scrypt N=8192 r=1 p=1, labels discarded (/dev/null sink)",
+            "config": {"workload": "4-SU POST init (2^34 labels/GPU), scrypt-jane (ChaCha20/8 + Keccak-512) N=8192 r=1 p=1, labels discarded (/dev/null sink)",
                        "labels_per_step_per_gpu": batch, "wave_slots": wave, "provider": prov["model"],
                        "romix_variant": b2.get_option("romix_variant"), "rotate_mask": b2.get_option("rotate_mask"),
                        "tpb": tpb, "l2": "working set = wave_slots x 1 MiB scratch >> 126 MB L2; every step uses fresh indices",
