@@ -4,9 +4,10 @@
 // batches of ComputeBatchSize labels, cancellable, progress observable) but sized for a B200.  A *layer*
 // is one label per resident slot (threads x SMs that fit the registers and the HBM scratch).  With the
 // pipelined ROMix kernel the stream carries, for layer m:
-//     K1(m)  ->  K2p{ mix layer m-1 | fill layer m }  ->  K3(m-1) -> D2H(m-1)
+//     K1(m)  ->  K2p{ mix layer m-1 | fill layer m }  ->  K3(m-1)        (and on the copy stream: D2H(m-1))
 // so every launch keeps half of each thread's work latency-free, and the 16-byte labels of layer m-1
-// leave the device while layer m computes.  Buffers are double-buffered by layer parity.
+// leave the device while layer m computes.  Buffers are double-buffered by layer parity; the host thread
+// stays one launch ahead of the GPU.
 #include "engine.h"
 
 #include <algorithm>
@@ -48,6 +49,7 @@ DeviceEngine::~DeviceEngine() {
 
 void DeviceEngine::release() {
     if (stream_) cudaStreamSynchronize(stream_);
+    if (copy_stream_) cudaStreamSynchronize(copy_stream_);
     cudaFree(V_raw_); V_raw_ = nullptr; V_ = nullptr; v_bytes_ = 0; v_align_ = 0;
     for (int b = 0; b < 2; b++) {
         cudaFree(X_[b]); X_[b] = nullptr;
