@@ -1,5 +1,6 @@
 """CPU tier: the product's host-side logic and the kernels' arithmetic (compiled for the host)."""
 import ctypes
+import importlib
 import re
 from pathlib import Path
 
@@ -73,8 +74,21 @@ def test_no_cpu_fallback(b2):
         b2.labels_gather(np.zeros((1, 32), np.uint8), np.zeros(1, np.uint64), 2)
     assert e.value.code == b2.ERR_NO_DEVICE
     with pytest.raises(b2.B200PostError) as e:
+        b2.labels_gather_indexed(np.zeros((1, 32), np.uint8), np.zeros(1, np.uint32), np.zeros(1, np.uint64), 2)
+    assert e.value.code == b2.ERR_NO_DEVICE
+    with pytest.raises(b2.B200PostError) as e:
         b2.labels_range(bytes(32), 2, 0, 8, provider=b2.CPU_PROVIDER_ID)
     assert e.value.code == b2.ERR_UNSUPPORTED
+    vf = importlib.import_module("go-spacemesh_b200.verify")
+    proof, meta = vf.Proof(0, vf.pack_indices([1, 2], 11), 0), vf.ProofMetadata(bytes(32), bytes(32), bytes(32), 4, 256)
+    params = vf.VerifyParams(k1=200, k2=2, scrypt_n=2)
+    for kw in ({"provider": 0}, {"providers": [0, 1]}):
+        with pytest.raises(b2.B200PostError) as e:
+            vf.verify_batch([proof, proof], [meta, meta], params, **kw)
+        assert e.value.code == b2.ERR_NO_DEVICE
+    with pytest.raises(b2.B200PostError) as e:
+        vf.PostVerifier(providers=[0, 1])
+    assert e.value.code == b2.ERR_NO_DEVICE
 
 
 def test_argument_validation(b2):
@@ -85,8 +99,13 @@ def test_argument_validation(b2):
     with pytest.raises(b2.B200PostError) as e:
         b2.labels_range(bytes(32), 2, 2**64 - 4, 8)   # index overflow: last index would be 2^64 + 3
     assert e.value.code == b2.ERR_INVALID_ARGUMENT
+    with pytest.raises(b2.B200PostError) as e:     # a row past the end of the commitment table
+        b2.labels_gather_indexed(np.zeros((2, 32), np.uint8), np.array([2], np.uint32), np.zeros(1, np.uint64), 2)
+    assert e.value.code == b2.ERR_INVALID_ARGUMENT
     with pytest.raises(b2.B200PostError):
         b2.set_option("romix_variant", 9)
+    with pytest.raises(b2.B200PostError):
+        b2.set_option("rotate_mask", 2)
     with pytest.raises(b2.B200PostError):
         b2.set_option("no_such_option", 1)
 
