@@ -73,6 +73,11 @@ def test_real_vrf_nonces_of_the_reference_checkpoint_fixture(b2, golden):
         start = max(0, it["vrf_nonce"] - 2048)
         _, vrf = b2.labels_range(bytes.fromhex(it["commitment"]), 8192, start, 4096, vrf_difficulty_=b"\xff" * 32, discard=True)
         assert vrf == (it["vrf_nonce"], bytes.fromhex(it["label32"]))
+    # the whole POST of three identities (33 and 100 units: one and two layers): the recorded nonce is the arg-min
+    for it in (items[0], items[15], next(x for x in items if x["num_units"] == 100)):
+        _, vrf = b2.labels_range(bytes.fromhex(it["commitment"]), 8192, 0, it["num_units"] * it["labels_per_unit"],
+                                 vrf_difficulty_=b"\xff" * 32, discard=True)
+        assert vrf == (it["vrf_nonce"], bytes.fromhex(it["label32"]))
 
 
 @pytest.mark.parametrize("n,start,count", [
