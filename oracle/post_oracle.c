@@ -648,19 +648,87 @@ static void romix_r1_avx2_x2(uint32_t xa[32], uint32_t xb[32], void *va, void *v
         _mm_storeu_si128((__m128i *)(xb + 4 * k), _mm256_extracti128_si256(X[k], 1));
     }
 }
+
+/* Four labels per thread in the four 128-bit lanes of AVX-512 registers (compiled per function, chosen at run time) */
+#define T512 __attribute__((target("avx512f")))
+T512 static inline void chacha20_8_avx512(__m512i B[4]) {
+    __m512i a = B[0], b = B[1], c = B[2], d = B[3];
+#define HALF4 \
+    a = _mm512_add_epi32(a, b); d = _mm512_rol_epi32(_mm512_xor_si512(d, a), 16); \
+    c = _mm512_add_epi32(c, d); b = _mm512_rol_epi32(_mm512_xor_si512(b, c), 12); \
+    a = _mm512_add_epi32(a, b); d = _mm512_rol_epi32(_mm512_xor_si512(d, a), 8);  \
+    c = _mm512_add_epi32(c, d); b = _mm512_rol_epi32(_mm512_xor_si512(b, c), 7);
+    for (int i = 0; i < 4; i++) {
+        HALF4
+        b = _mm512_shuffle_epi32(b, 0x39); c = _mm512_shuffle_epi32(c, 0x4E); d = _mm512_shuffle_epi32(d, 0x93);
+        HALF4
+        b = _mm512_shuffle_epi32(b, 0x93); c = _mm512_shuffle_epi32(c, 0x4E); d = _mm512_shuffle_epi32(d, 0x39);
+    }
+#undef HALF4
+    B[0] = _mm512_add_epi32(B[0], a); B[1] = _mm512_add_epi32(B[1], b);
+    B[2] = _mm512_add_epi32(B[2], c); B[3] = _mm512_add_epi32(B[3], d);
+}
+T512 static inline void blockmix_r1_avx512(__m512i X[8]) {
+    __m512i T[4];
+    for (int k = 0; k < 4; k++) T[k] = _mm512_xor_si512(X[k], X[4 + k]);
+    chacha20_8_avx512(T);
+    for (int k = 0; k < 4; k++) { X[k] = T[k]; T[k] = _mm512_xor_si512(T[k], X[4 + k]); }
+    chacha20_8_avx512(T);
+    for (int k = 0; k < 4; k++) X[4 + k] = T[k];
+}
+T512 static inline __m512i gather4(const __m128i *p0, const __m128i *p1, const __m128i *p2, const __m128i *p3) {
+    __m512i v = _mm512_castsi128_si512(_mm_loadu_si128(p0));
+    v = _mm512_inserti32x4(v, _mm_loadu_si128(p1), 1);
+    v = _mm512_inserti32x4(v, _mm_loadu_si128(p2), 2);
+    return _mm512_inserti32x4(v, _mm_loadu_si128(p3), 3);
+}
+/* ROMix of four labels in lock-step; v[q] = label q's private 128*N-byte scratchpad */
+T512 static void romix_r1_avx512_x4(uint32_t *x[4], void *v[4], uint64_t N) {
+    __m512i X[8];
+    __m128i *V0 = (__m128i *)v[0], *V1 = (__m128i *)v[1], *V2 = (__m128i *)v[2], *V3 = (__m128i *)v[3];
+    for (int k = 0; k < 8; k++)
+        X[k] = gather4((const __m128i *)(x[0] + 4 * k), (const __m128i *)(x[1] + 4 * k), (const __m128i *)(x[2] + 4 * k), (const __m128i *)(x[3] + 4 * k));
+    for (uint64_t i = 0; i < N; i++) {
+        for (int k = 0; k < 8; k++) {
+            _mm_storeu_si128(V0 + 8 * i + k, _mm512_castsi512_si128(X[k]));
+            _mm_storeu_si128(V1 + 8 * i + k, _mm512_extracti32x4_epi32(X[k], 1));
+            _mm_storeu_si128(V2 + 8 * i + k, _mm512_extracti32x4_epi32(X[k], 2));
+            _mm_storeu_si128(V3 + 8 * i + k, _mm512_extracti32x4_epi32(X[k], 3));
+        }
+        blockmix_r1_avx512(X);
+    }
+    for (uint64_t i = 0; i < N; i++) {
+        const uint64_t j0 = (uint32_t)_mm_cvtsi128_si32(_mm512_castsi512_si128(X[4])) & (N - 1);
+        const uint64_t j1 = (uint32_t)_mm_cvtsi128_si32(_mm512_extracti32x4_epi32(X[4], 1)) & (N - 1);
+        const uint64_t j2 = (uint32_t)_mm_cvtsi128_si32(_mm512_extracti32x4_epi32(X[4], 2)) & (N - 1);
+        const uint64_t j3 = (uint32_t)_mm_cvtsi128_si32(_mm512_extracti32x4_epi32(X[4], 3)) & (N - 1);
+        for (int k = 0; k < 8; k++)
+            X[k] = _mm512_xor_si512(X[k], gather4(V0 + 8 * j0 + k, V1 + 8 * j1 + k, V2 + 8 * j2 + k, V3 + 8 * j3 + k));
+        blockmix_r1_avx512(X);
+    }
+    for (int k = 0; k < 8; k++) {
+        _mm_storeu_si128((__m128i *)(x[0] + 4 * k), _mm512_castsi512_si128(X[k]));
+        _mm_storeu_si128((__m128i *)(x[1] + 4 * k), _mm512_extracti32x4_epi32(X[k], 1));
+        _mm_storeu_si128((__m128i *)(x[2] + 4 * k), _mm512_extracti32x4_epi32(X[k], 2));
+        _mm_storeu_si128((__m128i *)(x[3] + 4 * k), _mm512_extracti32x4_epi32(X[k], 3));
+    }
+}
+static int have_avx512(void) { return __builtin_cpu_supports("avx512f"); }
 #else
 #define ORACLE_HAVE_AVX2 0
+static int have_avx512(void) { return 0; }
 #endif
 #else
 #define ORACLE_HAVE_SSE2 0
 #define ORACLE_HAVE_AVX2 0
 #endif
 
-static int g_oracle_impl = ORACLE_HAVE_AVX2 ? 2 : ORACLE_HAVE_SSE2;   /* 0 = scalar restatement, 1 = SSE2, 2 = AVX2 two labels at a time */
+static int g_oracle_impl = ORACLE_HAVE_AVX2 ? 2 : ORACLE_HAVE_SSE2;   /* 0 = scalar restatement, 1 = SSE2, 2 = AVX2 two labels at a time, 3 = AVX-512 four at a time (opt-in) */
 int oracle_set_impl(int impl) {
     if (impl == 1 && !ORACLE_HAVE_SSE2) return -1;
     if (impl == 2 && !ORACLE_HAVE_AVX2) return -1;
-    if (impl < 0 || impl > 2) return -1;
+    if (impl == 3 && !(ORACLE_HAVE_AVX2 && have_avx512())) return -1;
+    if (impl < 0 || impl > 3) return -1;
     g_oracle_impl = impl;
     return 0;
 }
@@ -714,6 +782,25 @@ static void label32_r1_x2(const uint8_t ca[32], uint64_t ia, const uint8_t cb[32
 }
 #endif
 
+#if ORACLE_HAVE_AVX2
+T512 static void label32_r1_x4(const uint8_t *c[4], const uint64_t idx[4], uint64_t N, uint32_t *v, uint8_t out[4][32]) {
+    uint8_t pw[4][72], B[4][128];
+    uint32_t x[4][32];
+    uint32_t *xp[4]; void *vp[4];
+    for (int q = 0; q < 4; q++) {
+        label_password(c[q], idx[q], pw[q]);
+        oracle_pbkdf2_keccak512(pw[q], 72, NULL, 0, B[q], 128);
+        for (int k = 0; k < 32; k++) x[q][k] = le32(B[q] + 4 * k);
+        xp[q] = x[q]; vp[q] = v + (size_t)q * 32 * N;
+    }
+    romix_r1_avx512_x4(xp, vp, N);
+    for (int q = 0; q < 4; q++) {
+        for (int k = 0; k < 32; k++) put_le32(B[q] + 4 * k, x[q][k]);
+        oracle_pbkdf2_keccak512(pw[q], 72, B[q], 128, out[q], 32);
+    }
+}
+#endif
+
 int oracle_label32(const uint8_t commitment[32], uint64_t index, uint64_t N, uint32_t r, uint32_t p,
                    uint8_t out[32]) {
     uint8_t pw[72];
@@ -746,7 +833,7 @@ typedef struct {
 
 static void *worker(void *p) {
     worker_arg *a = (worker_arg *)p;
-    uint32_t *v = (uint32_t *)malloc(2 * 128 * (size_t)a->N);   /* two scratchpads: the AVX2 path does two labels at a time */
+    uint32_t *v = (uint32_t *)malloc(4 * 128 * (size_t)a->N);   /* up to four scratchpads: the SIMD paths do 2 / 4 labels at a time */
     if (!v) { a->rc = -1; return NULL; }
     /* contiguous sub-range per thread so that "first index wins ties" is easy to merge */
     uint64_t per = (a->count + a->nthreads - 1) / a->nthreads;
@@ -755,10 +842,18 @@ static void *worker(void *p) {
     a->found = 0;
     if (a->vrf_difficulty) memcpy(a->best, a->vrf_difficulty, 32);
     for (uint64_t k = lo; k < hi; k++) {
-        uint8_t l32[2][32];
+        uint8_t l32[4][32];
         int n = 1;
 #if ORACLE_HAVE_AVX2
-        if (g_oracle_impl == 2 && k + 1 < hi) {
+        if (g_oracle_impl == 3 && k + 3 < hi) {
+            const uint8_t *c4[4]; uint64_t i4[4];
+            for (int q = 0; q < 4; q++) {
+                c4[q] = a->gather ? a->commitment + 32 * (k + q) : a->commitment;
+                i4[q] = a->gather ? a->indices[k + q] : a->start + k + q;
+            }
+            n = 4;
+            label32_r1_x4(c4, i4, a->N, v, l32);
+        } else if (g_oracle_impl >= 2 && k + 1 < hi) {
             n = 2;
             if (a->gather) label32_r1_x2(a->commitment + 32 * k, a->indices[k], a->commitment + 32 * (k + 1), a->indices[k + 1], a->N,
                                          v, v + 32 * a->N, l32[0], l32[1]);

@@ -87,8 +87,9 @@ void oracle_vrf_difficulty(uint64_t num_labels, uint8_t out[32]);
 /* timing helper for bench.py's cpu_baseline: computes `count`
  * labels starting at `start` on `threads` threads, returns elapsed seconds. */
 /* ROMix implementation used by the label functions: 0 = scalar restatement, 1 = SSE2, 2 = AVX2 with two labels
- * per thread in lock-step (the default where available; all cross-checked against 0 in tests/).  Returns 0, or -1
- * if unsupported. */
+ * per thread in lock-step (the default where available), 3 = AVX-512 with four labels per thread (run-time CPU check;
+ * opt-in: bench.py times both and reports the faster).  All cross-checked against 0 in tests/.  Returns 0, or -1 if
+ * unsupported. */
 int oracle_set_impl(int impl);
 int oracle_get_impl(void);
 

@@ -181,7 +181,8 @@ def test_bad_parameters_rejected(orc):
 
 def test_simd_and_scalar_romix_agree(orc):
     """The vectorised ROMix paths used for the timed CPU baseline (1 = SSE2, 2 = AVX2 with two labels per thread in
-    lock-step) are the same function as the scalar restatement, odd counts and the VRF scan included."""
+    lock-step, 3 = AVX-512 with four, where the CPU has it) are the same function as the scalar restatement, ragged
+    counts and the VRF scan included."""
     L = orc.lib()
     default = L.oracle_get_impl()
     try:
@@ -190,13 +191,13 @@ def test_simd_and_scalar_romix_agree(orc):
             c = bytes(rng.integers(0, 256, 32, dtype=np.uint8))
             d = orc.py_vrf_difficulty(8)
             L.oracle_set_impl(0)
-            a = orc.c_labels_range(c, n, 2**32 - 3, 25, d, threads=2)
-            comms = rng.integers(0, 256, (9, 32), dtype=np.uint8); idx = rng.integers(0, 2**40, 9, dtype=np.uint64)
+            a = orc.c_labels_range(c, n, 2**32 - 3, 27, d, threads=2)
+            comms = rng.integers(0, 256, (11, 32), dtype=np.uint8); idx = rng.integers(0, 2**40, 11, dtype=np.uint64)
             ga = orc.c_labels_gather(comms, idx, n, threads=2)
-            for impl in (1, 2):
+            for impl in (1, 2, 3):
                 if L.oracle_set_impl(impl) != 0:
                     continue
-                b = orc.c_labels_range(c, n, 2**32 - 3, 25, d, threads=2)
+                b = orc.c_labels_range(c, n, 2**32 - 3, 27, d, threads=2)
                 assert (a[0] == b[0]).all() and a[1:] == b[1:], (n, impl)
                 assert (orc.c_labels_gather(comms, idx, n, threads=2) == ga).all(), (n, impl)
     finally:
