@@ -188,8 +188,9 @@ def run_reference(args, rank: int, world: int) -> None:
     from oracle import pyoracle as orc
     orc.build()
     commitment = bytes(range(32))
-    cores, _ = best_thread_count(orc, commitment)
-    per_step = max(cores * 64, 256)      # bounded sample per step (~0.2 s per 64 labels per core)
+    cores, rate = best_thread_count(orc, commitment)
+    # bounded sample per step: ~2 s of work at the probed rate, a whole number of 4-label groups per thread
+    per_step = max(cores * 64, int(rate * 2.0) // (4 * cores) * (4 * cores), 256)
     for w in range(args.warmup):
         orc.c_time_labels(commitment, N_SCRYPT, w * per_step, min(per_step, cores * 8), cores)
     t_total = 0.0
@@ -202,7 +203,8 @@ def run_reference(args, rank: int, world: int) -> None:
             "config": {"workload": "4-SU POST init (2^34 labels), scrypt-jane (ChaCha20/8 + Keccak-512) N=8192 r=1 p=1, labels discarded",
                        "step": f"bounded sample: {per_step} labels per step on {cores} host threads"},
             "cpu_baseline": {"value": value, "unit": "labels/s", "cores": cores, "kind": "port",
-                             "sample": f"{per_step} labels/step x {args.steps} steps, oracle/post_oracle.c"},
+                             "sample": f"{per_step} labels/step x {args.steps} steps, oracle/post_oracle.c, ROMix impl "
+                                       f"{orc.lib().oracle_get_impl()} [2 = AVX2 x2 labels, 3 = AVX-512 x4]"},
             "e2e": {"value": value, "unit": "labels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
