@@ -401,7 +401,7 @@ def main() -> None:
         }
         if verify_extra:
             line["verify"] = verify_extra
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is an N = 1 measurement
             from oracle import pyoracle as orc
             orc.build()
             line["cpu_baseline"] = cpu_baseline(orc)
