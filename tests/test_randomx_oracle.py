@@ -1,0 +1,159 @@
+"""Pins oracle/randomx_oracle.c (the k2pow checker) stage by stage; CPU only.
+
+Blake2b vs hashlib, Argon2d vs OpenSSL (cryptography), AES rounds vs AES-NI, generator constants vs their published
+derivation, and RandomX's own known-answer vectors (tevador/RandomX src/tests/tests.cpp): reciprocals, cache words,
+SuperscalarHash program hashes, dataset items and five full hashes.  The product never loads this library."""
+import ctypes
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import pyrandomx as rx
+
+
+@pytest.fixture(scope="module")
+def cache000():
+    c = rx.Cache(b"test key 000")
+    yield c
+    c.close()
+
+
+def test_blake2b_vs_hashlib():
+    msg = bytes(range(256)) * 5
+    for n in (0, 1, 63, 64, 65, 127, 128, 129, 255, 256, 1000, 1280):
+        for ol in (1, 32, 64):
+            assert rx.blake2b(msg[:n], ol) == hashlib.blake2b(msg[:n], digest_size=ol).digest()
+
+
+def test_argon2d_vs_openssl():
+    argon2 = pytest.importorskip("cryptography.hazmat.primitives.kdf.argon2")
+    L = rx.lib()
+    for m, t in ((8, 1), (64, 3), (1024, 3), (4096, 2)):
+        mem = (ctypes.c_uint64 * (m * 128))()
+        tag = ctypes.create_string_buffer(32)
+        assert L.rxo_argon2d_fill(mem, m, t, b"test key 000", 12, b"RandomX\x03", 8, 32, tag) == 0
+        exp = argon2.Argon2d(salt=b"RandomX\x03", length=32, iterations=t, lanes=1, memory_cost=m).derive(b"test key 000")
+        assert tag.raw == exp
+
+
+def test_aes_constants_follow_their_derivation():
+    L = rx.lib()
+    g1, g4, hs, hx = (ctypes.create_string_buffer(n) for n in (64, 128, 64, 32))
+    L.rxo_aes_constants(g1, g4, hs, hx)
+    # spec 3.2: key0 = 53 a5 ac 6d 09 66 71 62 2b 55 b5 db 17 49 f4 b4 ... (Blake2b-512 of the ASCII name)
+    assert g1.raw[:16].hex() == "53a5ac6d096671622b55b5db1749f4b4"
+    assert g1.raw[48:].hex() == "3581ef6a7c31bab1884c311654911649"
+    assert g1.raw == hashlib.blake2b(b"RandomX AesGenerator1R keys", digest_size=64).digest()
+    assert g4.raw[:64] == hashlib.blake2b(b"RandomX AesGenerator4R keys 0-3", digest_size=64).digest()
+    assert hs.raw == hashlib.blake2b(b"RandomX AesHash1R state", digest_size=64).digest()
+    assert hx.raw == hashlib.blake2b(b"RandomX AesHash1R xkeys", digest_size=32).digest()
+
+
+def test_soft_aes_rounds_match_fips197_and_aesni():
+    L = rx.lib()
+    # FIPS-197 appendix B, round 1: start-of-round state + round key 1 -> state after round 1
+    st = ctypes.create_string_buffer(bytes.fromhex("193de3bea0f4e22b9ac68d2ae9f84808"), 16)
+    L.rxo_soft_aesenc(st, bytes.fromhex("a0fafe1788542cb123a339392a6c7605"))
+    assert st.raw.hex() == "a49c7ff2689f352b6b5bea43026a5049"
+    rng = np.random.default_rng(5)
+    seed = bytes(rng.integers(0, 256, 64, dtype=np.uint8))
+    outs = []
+    for soft in (1, 0):
+        L.rxo_set_soft_aes(soft)
+        s = ctypes.create_string_buffer(seed, 64)
+        o = ctypes.create_string_buffer(4096)
+        L.rxo_fill_aes_1rx4(s, 4096, o)
+        o4 = ctypes.create_string_buffer(2176)
+        L.rxo_fill_aes_4rx4(seed, 2176, o4)
+        h = ctypes.create_string_buffer(64)
+        L.rxo_hash_aes_1rx4(o.raw, 4096, h)
+        outs.append((o.raw, s.raw, o4.raw, h.raw))
+    L.rxo_set_soft_aes(0)
+    if L.rxo_has_aesni():
+        assert outs[0] == outs[1]
+    # dec is the inverse direction of enc up to the key: aesdec(aesenc(x, 0) ...) is not an identity, so check the
+    # x86 identity instead: aesdec(x, k) == InvMixColumns(InvSubBytes(InvShiftRows(x))) ^ k  via a double round trip
+    assert len(set(outs[0][0][i:i + 64] for i in range(0, 4096, 64))) == 64
+
+
+def test_reciprocal_vectors():
+    L = rx.lib()
+    for d, e in ((3, 12297829382473034410), (13, 11351842506898185609), (33, 17887751829051686415),
+                 (65537, 18446462603027742720), (15000001, 10316166306300415204), (3845182035, 10302264209224146340),
+                 (0xffffffff, 9223372039002259456)):
+        assert L.rxo_reciprocal(d) == e
+
+
+def test_opcode_map_matches_frequency_table():
+    m = ctypes.create_string_buffer(256)
+    rx.lib().rxo_opcode_map(m)
+    counts = np.bincount(np.frombuffer(m.raw, dtype=np.uint8), minlength=30)
+    assert list(counts) == [16, 7, 16, 7, 16, 4, 4, 1, 4, 1, 8, 2, 15, 5, 8, 2, 4, 4, 16, 5, 16, 5, 6, 32, 4, 6, 25, 1, 16, 0]
+
+
+def test_cache_words(cache000):
+    mem = cache000.memory()
+    assert int(mem[0]) == 0x191e0e1d23c02186
+    assert int(mem[1568413]) == 0xf1b62fe6210bf8b1
+    assert int(mem[33554431]) == 0x1f47f056d05cd99b
+
+
+SUPERSCALAR_REFERENCES = [
+    "d3a4a6623738756f77e6104469102f082eff2a3e60be7ad696285ef7dfc72a61",
+    "f5e7e0bbc7e93c609003d6359208688070afb4a77165a552ff7be63b38dfbc86",
+    "85ed8b11734de5b3e9836641413a8f36e99e89694f419c8cd25c3f3f16c40c5a",
+    "5dd956292cf5d5704ad99e362d70098b2777b2a1730520be52f772ca48cd3bc0",
+    "6f14018ca7d519e9b48d91af094c0f2d7e12e93af0228782671a8640092af9e5",
+    "134be097c92e2c45a92f23208cacd89e4ce51f1009a0b900dbe83b38de11d791",
+    "268f9392c20c6e31371a5131f82bd7713d3910075f2f0468baafaa1abd2f3187",
+    "c668a05fd909714ed4a91e8d96d67b17e44329e88bc71e0672b529a3fc16be47",
+]
+
+
+def test_superscalar_program_hashes(cache000):
+    for i, ref in enumerate(SUPERSCALAR_REFERENCES):
+        assert hashlib.blake2b(cache000.program_bytes(i), digest_size=32).hexdigest() == ref, i
+
+
+def test_dataset_items(cache000):
+    for n, e in ((0, 0x680588a85ae222db), (10000000, 0x7943a1f6186ffb72), (20000000, 0x9035244d718095e1),
+                 (30000000, 0x145a5091f7853099)):
+        assert int(cache000.dataset_item(n)[0]) == e
+
+
+def test_hash_known_answers(cache000):
+    kats = [
+        (b"This is a test", "639183aae1bf4c9a35884cb46b09cad9175f04efd7684e7262a0ac1c2f0b4e3f"),
+        (b"Lorem ipsum dolor sit amet", "300a0adb47603dedb42228ccb2b211104f4da45af709cd7547cd049e9489c969"),
+        (b"sed do eiusmod tempor incididunt ut labore et dolore magna aliqua",
+         "c36d4ed4191e617309867ed66a443be4075014e2b061bcdaf9ce7b721d2b77a8"),
+    ]
+    for msg, ref in kats:
+        assert cache000.hash(msg).hex() == ref
+
+
+def test_hash_known_answers_second_key():
+    c = rx.Cache(b"test key 001")
+    try:
+        assert c.hash(b"sed do eiusmod tempor incididunt ut labore et dolore magna aliqua").hex() == \
+            "e9ff4503201c0c2cca26d285c93ae883f9b1d30c9eb240b820756f2d5a7905fc"
+        blob = bytes.fromhex("0b0b98bea7e805e0010a2126d287a2a0cc833d312cb786385a7c2f9de69d25537f584a9bc9977b00000000666fd8753bf61a"
+                             "8631f12984e3fd44f4014eca629276817b56f32e9b68bd82f416")
+        assert c.hash(blob).hex() == "c56414121acda1713c2f2a819d8ae38aed7c80c35c2a769298d34f03833cd5f1"
+    finally:
+        c.close()
+
+
+def test_k2pow_input_layout_and_scan(cache000):
+    ch, node = bytes(range(8)), bytes(range(32))
+    inp = rx.k2pow_input(0x0123456789abcdef, 7, ch, node)
+    assert inp == bytes.fromhex("efcdab89674523") + b"\x07" + ch + node   # pow[0:7] LE, nonce group, challenge[0:8], node id
+    hashes, found, _ = cache000.k2pow_scan(7, ch, node, 100, 6, difficulty=b"\xff" * 32, threads=3)
+    assert found == 100
+    for i in range(6):
+        assert bytes(hashes[i]) == cache000.hash(rx.k2pow_input(100 + i, 7, ch, node))
+    thr = bytes(sorted(bytes(h) for h in hashes)[1])      # second-smallest hash as the threshold: exactly one pow passes
+    _, found, _ = cache000.k2pow_scan(7, ch, node, 100, 6, difficulty=thr, threads=2)
+    assert found == 100 + int(np.argmin([int.from_bytes(bytes(h), "big") for h in hashes]))
+    assert rx.scale_pow_difficulty(b"\x00\x0d" + b"\xff" * 30, 4) == ((int.from_bytes(b"\x00\x0d" + b"\xff" * 30, "big")) // 4).to_bytes(32, "big")
