@@ -1,0 +1,665 @@
+// randomx_kernels.cu — RandomX (k2pow) on sm_100a.  go-spacemesh reaches this function only through an RPC to the
+// external post-service (activation/nipost.go:171) and through libpost's verifier (activation/post_verifier.go:159);
+// the arithmetic is tevador/RandomX v1.1.x (doc/specs.md), restated here for the GPU:
+//
+//   dataset      one thread per 64-byte item: 8 SuperscalarHash programs (identical for every item, so a warp never
+//                diverges) over registers held in shared memory, 8 random 64-byte reads of the 256 MiB cache (spec §7.3)
+//   seed         Blake2b-512 of the 48-byte k2pow input (or of caller-supplied inputs), one thread per VM
+//   fill         AesGenerator1R: four lanes per VM (one per AES column), 32768 chained rounds each, T-tables in smem
+//   program      AesGenerator4R -> configuration + 256 instructions, decoded to an 8-byte form (spec §4.5, §5)
+//   execute      the VM.  One thread per VM, its 256-byte register file in shared memory ([slot][thread], conflict
+//                free), its decoded program in HBM as [pc][vm] (a warp in step reads 256 contiguous bytes), its 2 MiB
+//                scratchpad private in HBM.  Operand fetch, the one scratchpad load and the write-back are common code;
+//                only the ALU step of each instruction sits in the divergent switch.  FP rounding modes are per VM:
+//                add/mul use the hardware's static-rounding instructions, div/sqrt round to nearest and are corrected
+//                by the sign of the exact FMA residual (no 4-way divergence over ~100-instruction software routines).
+//   chain seed   Blake2b-512 of the register file;  finalize: AesHash1R over the scratchpad + Blake2b-256.
+//
+// Throughput is bounded by dependent scratchpad accesses (one 8-byte access per ~5 instructions, each a random HBM
+// sector) and by SIMT divergence across VMs — RandomX is built to be that — so the lever a B200 offers is capacity:
+// tens of thousands of 2 MiB scratchpads resident in 180 GB of HBM and the full 2080 MiB dataset next to them.
+#include "randomx_kernels.cuh"
+
+#include <cstring>
+
+namespace b200post {
+namespace rx {
+namespace {
+
+using u64 = uint64_t;
+using u32 = uint32_t;
+
+// ---------------------------------------------------------------------------------------------- tables
+__device__ u32 g_te0[256], g_td0[256];      // AES round tables (enc: {2s, s, s, 3s}; dec: {14i, 9i, 13i, 11i}), byte 0 = row 0
+__device__ uint8_t g_opmap[256];            // opcode byte -> instruction type (spec table 5.1 frequencies)
+__constant__ uint8_t c_sigma[12][16] = {
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+    {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+    {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+    {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+    {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0},
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3}};
+__constant__ u64 c_b2iv[8] = {0x6a09e667f3bcc908ull, 0xbb67ae8584caa73bull, 0x3c6ef372fe94f82bull, 0xa54ff53a5f1d36f1ull,
+                              0x510e527fade682d1ull, 0x9b05688c2b3e6c1full, 0x1f83d9abfb41bd6bull, 0x5be0cd19137e2179ull};
+// generator keys / hash state: Blake2b of fixed strings (spec §3.2-3.4), derived on the host at upload time
+__constant__ u32 c_gen1_keys[16], c_gen4_keys[32], c_hash_state[16], c_hash_xkeys[8];
+
+// ---------------------------------------------------------------------------------------------- Blake2b
+__device__ __forceinline__ u64 ror64(u64 v, int n) { return (v >> n) | (v << (64 - n)); }
+
+__device__ void b2_compress(u64 h[8], const u64 m[16], u64 t, bool last) {
+    u64 v[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { v[i] = h[i]; v[i + 8] = c_b2iv[i]; }
+    v[12] ^= t;
+    if (last) v[14] = ~v[14];
+#define B2G(r, i, a, b, c, d)                                             \
+    a = a + b + m[c_sigma[r][2 * i]];     d = ror64(d ^ a, 32);           \
+    c = c + d;                            b = ror64(b ^ c, 24);           \
+    a = a + b + m[c_sigma[r][2 * i + 1]]; d = ror64(d ^ a, 16);           \
+    c = c + d;                            b = ror64(b ^ c, 63);
+    for (int r = 0; r < 12; r++) {
+        B2G(r, 0, v[0], v[4], v[8], v[12]) B2G(r, 1, v[1], v[5], v[9], v[13])
+        B2G(r, 2, v[2], v[6], v[10], v[14]) B2G(r, 3, v[3], v[7], v[11], v[15])
+        B2G(r, 4, v[0], v[5], v[10], v[15]) B2G(r, 5, v[1], v[6], v[11], v[12])
+        B2G(r, 6, v[2], v[7], v[8], v[13]) B2G(r, 7, v[3], v[4], v[9], v[14])
+    }
+#undef B2G
+#pragma unroll
+    for (int i = 0; i < 8; i++) h[i] ^= v[i] ^ v[i + 8];
+}
+__device__ __forceinline__ void b2_init(u64 h[8], u32 outlen) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) h[i] = c_b2iv[i];
+    h[0] ^= 0x01010000ull ^ outlen;
+}
+
+// ---------------------------------------------------------------------------------------------- AES rounds
+struct AesSmem { u32 te[256], td[256]; };
+__device__ __forceinline__ void aes_load(AesSmem &sm) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { sm.te[i] = g_te0[i]; sm.td[i] = g_td0[i]; }
+    __syncthreads();
+}
+__device__ __forceinline__ u32 rl8(u32 v) { return __byte_perm(v, 0, 0x2103); }
+__device__ __forceinline__ u32 rl16(u32 v) { return __byte_perm(v, 0, 0x1032); }
+__device__ __forceinline__ u32 rl24(u32 v) { return __byte_perm(v, 0, 0x0321); }
+// x86 AESENC: ShiftRows, SubBytes, MixColumns, xor key.  s = 4 little-endian column words.
+__device__ __forceinline__ void aes_enc(const AesSmem &sm, u32 s[4], const u32 k[4]) {
+    const u32 t0 = sm.te[s[0] & 255] ^ rl8(sm.te[(s[1] >> 8) & 255]) ^ rl16(sm.te[(s[2] >> 16) & 255]) ^ rl24(sm.te[s[3] >> 24]);
+    const u32 t1 = sm.te[s[1] & 255] ^ rl8(sm.te[(s[2] >> 8) & 255]) ^ rl16(sm.te[(s[3] >> 16) & 255]) ^ rl24(sm.te[s[0] >> 24]);
+    const u32 t2 = sm.te[s[2] & 255] ^ rl8(sm.te[(s[3] >> 8) & 255]) ^ rl16(sm.te[(s[0] >> 16) & 255]) ^ rl24(sm.te[s[1] >> 24]);
+    const u32 t3 = sm.te[s[3] & 255] ^ rl8(sm.te[(s[0] >> 8) & 255]) ^ rl16(sm.te[(s[1] >> 16) & 255]) ^ rl24(sm.te[s[2] >> 24]);
+    s[0] = t0 ^ k[0]; s[1] = t1 ^ k[1]; s[2] = t2 ^ k[2]; s[3] = t3 ^ k[3];
+}
+// x86 AESDEC: InvShiftRows, InvSubBytes, InvMixColumns, xor key
+__device__ __forceinline__ void aes_dec(const AesSmem &sm, u32 s[4], const u32 k[4]) {
+    const u32 t0 = sm.td[s[0] & 255] ^ rl8(sm.td[(s[3] >> 8) & 255]) ^ rl16(sm.td[(s[2] >> 16) & 255]) ^ rl24(sm.td[s[1] >> 24]);
+    const u32 t1 = sm.td[s[1] & 255] ^ rl8(sm.td[(s[0] >> 8) & 255]) ^ rl16(sm.td[(s[3] >> 16) & 255]) ^ rl24(sm.td[s[2] >> 24]);
+    const u32 t2 = sm.td[s[2] & 255] ^ rl8(sm.td[(s[1] >> 8) & 255]) ^ rl16(sm.td[(s[0] >> 16) & 255]) ^ rl24(sm.td[s[3] >> 24]);
+    const u32 t3 = sm.td[s[3] & 255] ^ rl8(sm.td[(s[2] >> 8) & 255]) ^ rl16(sm.td[(s[1] >> 16) & 255]) ^ rl24(sm.td[s[0] >> 24]);
+    s[0] = t0 ^ k[0]; s[1] = t1 ^ k[1]; s[2] = t2 ^ k[2]; s[3] = t3 ^ k[3];
+}
+
+// ---------------------------------------------------------------------------------------------- dataset
+__device__ __forceinline__ u64 mulh_u(u64 a, u64 b) { return __umul64hi(a, b); }
+__device__ __forceinline__ u64 mulh_s(u64 a, u64 b) { return (u64)__mul64hi((long long)a, (long long)b); }
+__device__ __forceinline__ u64 sext(u32 v) { return (u64)(long long)(int)v; }
+
+constexpr int kDatasetThreads = 256;
+struct SsArgs { const SsOp *ops; u32 first[kCacheAccesses + 1]; u32 address_reg[kCacheAccesses]; };
+
+__global__ void __launch_bounds__(kDatasetThreads) dataset_kernel(const u64 *__restrict__ cache, SsArgs ss, u64 *__restrict__ dataset,
+                                                                   u64 first_item, u64 count) {
+    __shared__ u64 regs[8][kDatasetThreads];
+    const u64 idx = (u64)blockIdx.x * kDatasetThreads + threadIdx.x;
+    if (idx >= count) return;
+    const u64 item = first_item + idx;
+    const int t = threadIdx.x;
+    const u64 r0 = (item + 1) * 6364136223846793005ull;
+    regs[0][t] = r0;
+    regs[1][t] = r0 ^ 9298411001130361340ull;  regs[2][t] = r0 ^ 12065312585734608966ull;
+    regs[3][t] = r0 ^ 9306329213124626780ull;  regs[4][t] = r0 ^ 5281919268842080866ull;
+    regs[5][t] = r0 ^ 10536153434571861004ull; regs[6][t] = r0 ^ 3398623926847679864ull;
+    regs[7][t] = r0 ^ 9549104520008361294ull;
+    u64 line = item;
+    constexpr u64 kLineMask = (u64)kCacheKiB * 1024 / 64 - 1;
+    for (int p = 0; p < (int)kCacheAccesses; p++) {
+        const ulonglong2 *mix = reinterpret_cast<const ulonglong2 *>(cache + (line & kLineMask) * 8);
+        ulonglong2 m0 = __ldg(mix), m1 = __ldg(mix + 1), m2 = __ldg(mix + 2), m3 = __ldg(mix + 3);   // in flight under the program
+        for (u32 j = ss.first[p]; j < ss.first[p + 1]; j++) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(ss.ops + j));   // warp-uniform address: one broadcast
+            const u32 op = raw.x & 255, dst = (raw.x >> 8) & 255, src = (raw.x >> 16) & 255, shift = raw.x >> 24;
+            const u64 d = regs[dst][t], s = regs[src][t];
+            u64 res;
+            switch (op) {
+                case SS_ISUB_R: res = d - s; break;
+                case SS_IXOR_R: res = d ^ s; break;
+                case SS_IADD_RS: res = d + (s << shift); break;
+                case SS_IMUL_R: res = d * s; break;
+                case SS_IROR_C: res = ror64(d, raw.y & 63); break;   // imm is 1..63
+                case SS_IADD_C: res = d + sext(raw.y); break;
+                case SS_IXOR_C: res = d ^ sext(raw.y); break;
+                case SS_IMULH_R: res = mulh_u(d, s); break;
+                case SS_ISMULH_R: res = mulh_s(d, s); break;
+                default: res = d * (((u64)raw.w << 32) | raw.z); break;   // SS_IMUL_RCP
+            }
+            regs[dst][t] = res;
+        }
+        regs[0][t] ^= m0.x; regs[1][t] ^= m0.y; regs[2][t] ^= m1.x; regs[3][t] ^= m1.y;
+        regs[4][t] ^= m2.x; regs[5][t] ^= m2.y; regs[6][t] ^= m3.x; regs[7][t] ^= m3.y;
+        line = regs[ss.address_reg[p]][t];
+    }
+    ulonglong2 *out = reinterpret_cast<ulonglong2 *>(dataset + item * 8);
+    out[0] = make_ulonglong2(regs[0][t], regs[1][t]); out[1] = make_ulonglong2(regs[2][t], regs[3][t]);
+    out[2] = make_ulonglong2(regs[4][t], regs[5][t]); out[3] = make_ulonglong2(regs[6][t], regs[7][t]);
+}
+
+// ---------------------------------------------------------------------------------------------- seeds
+__global__ void seed_inputs_kernel(u64 *__restrict__ seed, u32 stride, u32 n, const uint8_t *__restrict__ inputs, u32 len) {
+    const u32 vm = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vm >= n) return;
+    const uint8_t *in = inputs + (size_t)vm * len;
+    u64 h[8], m[16];
+    b2_init(h, 64);
+    u32 off = 0;
+    while (len - off > 128) {
+        for (int i = 0; i < 16; i++) { u64 w = 0; for (int b = 0; b < 8; b++) w |= (u64)in[off + 8 * i + b] << (8 * b); m[i] = w; }
+        off += 128;
+        b2_compress(h, m, off, false);
+    }
+    for (int i = 0; i < 16; i++) { u64 w = 0; for (int b = 0; b < 8; b++) { const u32 p = off + 8 * i + b; if (p < len) w |= (u64)in[p] << (8 * b); } m[i] = w; }
+    b2_compress(h, m, len, true);
+    for (int i = 0; i < 8; i++) seed[(size_t)i * stride + vm] = h[i];
+}
+__global__ void seed_k2pow_kernel(u64 *__restrict__ seed, u32 stride, u32 n, K2powTemplate t) {
+    const u32 vm = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vm >= n) return;
+    uint8_t in[48];
+    const u64 pow = t.start + vm;
+    for (int i = 0; i < 7; i++) in[i] = (uint8_t)(pow >> (8 * i));
+    for (int i = 0; i < 41; i++) in[7 + i] = t.tail[i];
+    u64 h[8], m[16];
+    b2_init(h, 64);
+    for (int i = 0; i < 16; i++) { u64 w = 0; if (i < 6) for (int b = 0; b < 8; b++) w |= (u64)in[8 * i + b] << (8 * b); m[i] = w; }
+    b2_compress(h, m, 48, true);
+    for (int i = 0; i < 8; i++) seed[(size_t)i * stride + vm] = h[i];
+}
+
+// ---------------------------------------------------------------------------------------------- scratchpad fill / hash
+// 4 lanes per VM: lane c owns AES column c of the 64-byte generator state (columns 0,2 decrypt, 1,3 encrypt)
+__global__ void __launch_bounds__(256) fill_kernel(u64 *__restrict__ seed, u32 stride, u32 n, uint8_t *__restrict__ scratchpads) {
+    __shared__ AesSmem sm;
+    aes_load(sm);
+    const u32 gid = blockIdx.x * blockDim.x + threadIdx.x, vm = gid >> 2, col = gid & 3;
+    if (vm >= n) return;
+    u32 s[4], k[4];
+    { const u64 a = seed[(size_t)(2 * col) * stride + vm], b = seed[(size_t)(2 * col + 1) * stride + vm];
+      s[0] = (u32)a; s[1] = (u32)(a >> 32); s[2] = (u32)b; s[3] = (u32)(b >> 32); }
+#pragma unroll
+    for (int i = 0; i < 4; i++) k[i] = c_gen1_keys[4 * col + i];
+    uint4 *out = reinterpret_cast<uint4 *>(scratchpads + (size_t)vm * kScratchpadL3) + col;
+    const bool dec = (col & 1) == 0;
+    for (u32 i = 0; i < kScratchpadL3 / 64; i++) {
+        if (dec) aes_dec(sm, s, k); else aes_enc(sm, s, k);
+        out[4 * (size_t)i] = make_uint4(s[0], s[1], s[2], s[3]);
+    }
+    seed[(size_t)(2 * col) * stride + vm] = (u64)s[0] | ((u64)s[1] << 32);
+    seed[(size_t)(2 * col + 1) * stride + vm] = (u64)s[2] | ((u64)s[3] << 32);
+}
+// AesHash1R: the scratchpad is the key stream (columns 0,2 encrypt, 1,3 decrypt), two fixed finishing rounds -> a0..a3
+__global__ void __launch_bounds__(256) hash_scratchpad_kernel(u64 *__restrict__ regfile, u32 stride, u32 n, const uint8_t *__restrict__ scratchpads) {
+    __shared__ AesSmem sm;
+    aes_load(sm);
+    const u32 gid = blockIdx.x * blockDim.x + threadIdx.x, vm = gid >> 2, col = gid & 3;
+    if (vm >= n) return;
+    u32 s[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) s[i] = c_hash_state[4 * col + i];
+    const uint4 *in = reinterpret_cast<const uint4 *>(scratchpads + (size_t)vm * kScratchpadL3) + col;
+    const bool enc = (col & 1) == 0;
+    constexpr u32 kRounds = kScratchpadL3 / 64;
+    uint4 nxt[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) nxt[j] = in[4 * (size_t)j];
+    for (u32 i = 0; i < kRounds; i += 4) {
+        uint4 cur[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { cur[j] = nxt[j]; if (i + 4 + j < kRounds) nxt[j] = in[4 * (size_t)(i + 4 + j)]; }   // keys do not depend on the state: prefetch
+#pragma unroll
+        for (int j = 0; j < 4; j++) { const u32 k[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w}; if (enc) aes_enc(sm, s, k); else aes_dec(sm, s, k); }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++) { const u32 k[4] = {c_hash_xkeys[4 * r], c_hash_xkeys[4 * r + 1], c_hash_xkeys[4 * r + 2], c_hash_xkeys[4 * r + 3]}; if (enc) aes_enc(sm, s, k); else aes_dec(sm, s, k); }
+    regfile[(size_t)(24 + 2 * col) * stride + vm] = (u64)s[0] | ((u64)s[1] << 32);
+    regfile[(size_t)(25 + 2 * col) * stride + vm] = (u64)s[2] | ((u64)s[3] << 32);
+}
+
+// ---------------------------------------------------------------------------------------------- program generation + decode
+// instruction types in opcode order (spec table 5.1)
+enum : uint8_t { T_IADD_RS, T_IADD_M, T_ISUB_R, T_ISUB_M, T_IMUL_R, T_IMUL_M, T_IMULH_R, T_IMULH_M, T_ISMULH_R, T_ISMULH_M, T_IMUL_RCP,
+                 T_INEG_R, T_IXOR_R, T_IXOR_M, T_IROR_R, T_IROL_R, T_ISWAP_R, T_FSWAP_R, T_FADD_R, T_FADD_M, T_FSUB_R, T_FSUB_M,
+                 T_FSCAL_R, T_FMUL_R, T_FDIV_M, T_FSQRT_R, T_CBRANCH, T_CFROUND, T_ISTORE, T_NOP, T_COUNT };
+// decoded form: word0 = op | dst slot << 8 | src << 16 | aux << 24, word1 = imm32.
+//   op bit 7 = reads the scratchpad at (src + imm) & mask(aux); bit 6 = floating point (two 64-bit slots written back)
+//   dst slot / src slot index the register file: 0-7 r, 8-15 f (lo,hi), 16-23 e, 24-31 a;  src 32 = the immediate, 33 = zero
+enum : uint8_t { X_NOP, X_IADD_RS, X_IADD, X_ISUB, X_IMUL, X_IMULH, X_ISMULH, X_IXOR, X_IROR, X_IROL, X_INEG, X_ISWAP, X_IMUL_RCP,
+                 X_IMUL_RCP_SLOW, X_CBRANCH, X_CFROUND, X_ISTORE,
+                 X_FSWAP = 0x40, X_FADD, X_FSUB, X_FSCAL, X_FMUL, X_FDIV, X_FSQRT, X_MEM = 0x80 };
+constexpr u32 kSrcImm = 32, kSrcZero = 33;
+constexpr u32 kL1Mask = (kScratchpadL1 - 1) & ~7u, kL2Mask = (kScratchpadL2 - 1) & ~7u, kL3Mask = (kScratchpadL3 - 1) & ~7u;
+constexpr u32 kL3Mask64 = (kScratchpadL3 - 1) & ~63u;
+constexpr u32 kDatasetAlignMask = (u32)((kDatasetBase - 1) & ~63ull);
+
+__device__ u64 device_reciprocal(u32 divisor) {
+    u64 q = (1ull << 63) / divisor, r = (1ull << 63) % divisor;
+    const int bits = 32 - __clz(divisor);
+    for (int i = 0; i < bits; i++) {
+        if (r >= divisor - r) { q = 2 * q + 1; r = 2 * r - divisor; }
+        else { q = 2 * q; r = 2 * r; }
+    }
+    return q;
+}
+
+__device__ __forceinline__ u32 pack(u32 op, u32 dst, u32 src, u32 aux) { return op | (dst << 8) | (src << 16) | (aux << 24); }
+
+__global__ void __launch_bounds__(128) program_kernel(BatchBuffers b, u32 n, bool first_program) {
+    __shared__ AesSmem sm;
+    __shared__ uint8_t opmap[256];
+    __shared__ short usage[8][128];     // CBRANCH targets: last instruction that wrote each integer register
+    aes_load(sm);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) opmap[i] = g_opmap[i];
+    __syncthreads();
+    const u32 vm = blockIdx.x * blockDim.x + threadIdx.x, t = threadIdx.x;
+    if (vm >= n) return;
+    const u32 stride = b.stride;
+    u32 st[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const u64 lo = b.seed[(size_t)(2 * c) * stride + vm], hi = b.seed[(size_t)(2 * c + 1) * stride + vm];
+        st[c][0] = (u32)lo; st[c][1] = (u32)(lo >> 32); st[c][2] = (u32)hi; st[c][3] = (u32)(hi >> 32);
+    }
+    auto next64 = [&](u64 out[8]) {   // AesGenerator4R: columns 0,1 keys 0-3, columns 2,3 keys 4-7; 0,2 decrypt, 1,3 encrypt
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const u32 ka[4] = {c_gen4_keys[4 * k], c_gen4_keys[4 * k + 1], c_gen4_keys[4 * k + 2], c_gen4_keys[4 * k + 3]};
+            const u32 kb[4] = {c_gen4_keys[16 + 4 * k], c_gen4_keys[17 + 4 * k], c_gen4_keys[18 + 4 * k], c_gen4_keys[19 + 4 * k]};
+            aes_dec(sm, st[0], ka); aes_enc(sm, st[1], ka); aes_dec(sm, st[2], kb); aes_enc(sm, st[3], kb);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) { out[2 * c] = (u64)st[c][0] | ((u64)st[c][1] << 32); out[2 * c + 1] = (u64)st[c][2] | ((u64)st[c][3] << 32); }
+    };
+    u64 ent[16];
+    next64(ent); next64(ent + 8);
+    // configuration (spec §4.5): a0-3 = small positive doubles, ma/mx, address registers, dataset offset, e masks
+    constexpr u64 kMant = (1ull << 52) - 1;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const u64 e = ent[i];
+        b.regfile[(size_t)(24 + i) * stride + vm] = ((((e >> 59) + 1023) & 2047) << 52) | (e & kMant);
+    }
+    const u32 ma = (u32)ent[8] & kDatasetAlignMask, mx = (u32)ent[10];
+    b.config[(size_t)0 * stride + vm] = (u64)ma | ((u64)mx << 32);
+    const u64 ds_off = (ent[13] % (kDatasetExtra / 64 + 1)) * 64;
+    b.config[(size_t)1 * stride + vm] = ds_off | ((ent[12] & 15) << 60);
+    auto fmask = [](u64 e) { return (e & ((1ull << 22) - 1)) | ((0x300ull | ((e >> 60) << 4)) << 52); };
+    b.config[(size_t)2 * stride + vm] = fmask(ent[14]);
+    b.config[(size_t)3 * stride + vm] = fmask(ent[15]);
+    if (first_program) b.fprc[vm] = 0;
+
+#pragma unroll
+    for (int i = 0; i < 8; i++) usage[i][t] = -1;
+    u32 n_rcp = 0;
+    for (int chunk = 0; chunk < kProgramSize / 8; chunk++) {
+        u64 raw[8];
+        next64(raw);
+        for (int j = 0; j < 8; j++) {
+            const int i = chunk * 8 + j;
+            const u32 lo = (u32)raw[j], imm = (u32)(raw[j] >> 32);
+            const u32 type = opmap[lo & 255], dst = (lo >> 8) & 7, src = (lo >> 16) & 7, mod = lo >> 24;
+            const u32 lvl12 = (mod & 3) ? 0 : 1;    // mod.mem != 0 -> L1, else L2
+            u32 w0 = X_NOP, w1 = imm;
+            switch (type) {
+                case T_IADD_RS: w0 = pack(X_IADD_RS, dst, src, (mod >> 2) & 3); w1 = dst == 5 ? imm : 0; usage[dst][t] = (short)i; break;
+                case T_IADD_M: case T_ISUB_M: case T_IMUL_M: case T_IMULH_M: case T_ISMULH_M: case T_IXOR_M: {
+                    const u32 alu = type == T_IADD_M ? X_IADD : type == T_ISUB_M ? X_ISUB : type == T_IMUL_M ? X_IMUL : type == T_IMULH_M ? X_IMULH
+                                  : type == T_ISMULH_M ? X_ISMULH : X_IXOR;
+                    w0 = src != dst ? pack(alu | X_MEM, dst, src, lvl12) : pack(alu | X_MEM, dst, kSrcZero, 2);
+                    usage[dst][t] = (short)i;
+                } break;
+                case T_ISUB_R: case T_IMUL_R: case T_IXOR_R: {
+                    const u32 alu = type == T_ISUB_R ? X_ISUB : type == T_IMUL_R ? X_IMUL : X_IXOR;
+                    w0 = pack(alu, dst, src != dst ? src : kSrcImm, 0);
+                    usage[dst][t] = (short)i;
+                } break;
+                case T_IMULH_R: w0 = pack(X_IMULH, dst, src, 0); usage[dst][t] = (short)i; break;
+                case T_ISMULH_R: w0 = pack(X_ISMULH, dst, src, 0); usage[dst][t] = (short)i; break;
+                case T_IMUL_RCP:
+                    if (imm & (imm - 1)) {
+                        if (n_rcp < (u32)kRcpSlots) { b.rcp[(size_t)n_rcp * stride + vm] = device_reciprocal(imm); w0 = pack(X_IMUL_RCP, dst, 0, n_rcp); n_rcp++; }
+                        else w0 = pack(X_IMUL_RCP_SLOW, dst, 0, 0);
+                        usage[dst][t] = (short)i;
+                    }
+                    break;
+                case T_INEG_R: w0 = pack(X_INEG, dst, 0, 0); usage[dst][t] = (short)i; break;
+                case T_IROR_R: w0 = pack(X_IROR, dst, src != dst ? src : kSrcImm, 0); usage[dst][t] = (short)i; break;
+                case T_IROL_R: w0 = pack(X_IROL, dst, src != dst ? src : kSrcImm, 0); usage[dst][t] = (short)i; break;
+                case T_ISWAP_R: if (src != dst) { w0 = pack(X_ISWAP, dst, src, 0); usage[dst][t] = (short)i; usage[src][t] = (short)i; } break;
+                case T_FSWAP_R: w0 = pack(X_FSWAP, 8 + 2 * dst, 0, 0); break;               // dst 0-3 = f, 4-7 = e: slots 8.. and 16.. are contiguous
+                case T_FADD_R: w0 = pack(X_FADD, 8 + 2 * (dst & 3), 24 + 2 * (src & 3), 0); break;
+                case T_FADD_M: w0 = pack(X_FADD | X_MEM, 8 + 2 * (dst & 3), src, lvl12); break;
+                case T_FSUB_R: w0 = pack(X_FSUB, 8 + 2 * (dst & 3), 24 + 2 * (src & 3), 0); break;
+                case T_FSUB_M: w0 = pack(X_FSUB | X_MEM, 8 + 2 * (dst & 3), src, lvl12); break;
+                case T_FSCAL_R: w0 = pack(X_FSCAL, 8 + 2 * (dst & 3), 0, 0); break;
+                case T_FMUL_R: w0 = pack(X_FMUL, 16 + 2 * (dst & 3), 24 + 2 * (src & 3), 0); break;
+                case T_FDIV_M: w0 = pack(X_FDIV | X_MEM, 16 + 2 * (dst & 3), src, lvl12); break;
+                case T_FSQRT_R: w0 = pack(X_FSQRT, 16 + 2 * (dst & 3), 0, 0); break;
+                case T_CBRANCH: {
+                    const u32 shift = (mod >> 4) + 8;
+                    w0 = pack(X_CBRANCH, dst, (u32)(usage[dst][t] + 1), shift);      // target + 1 (0 = restart at instruction 0)
+                    w1 = (imm | (1u << shift)) & ~(1u << (shift - 1));               // both bits lie below bit 31: sign extension unaffected
+#pragma unroll
+                    for (int r = 0; r < 8; r++) usage[r][t] = (short)i;
+                } break;
+                case T_CFROUND: w0 = pack(X_CFROUND, 0, src, imm & 63); break;
+                case T_ISTORE: w0 = pack(X_ISTORE, dst, src, (mod >> 4) < 14 ? lvl12 : 2); break;
+                default: break;
+            }
+            b.program[(size_t)i * stride + vm] = make_uint2(w0, w1);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- the VM
+__device__ __forceinline__ double add_rm(double a, double c, u32 mode) {
+    switch (mode) {
+        case 0: return __dadd_rn(a, c);
+        case 1: return __dadd_rd(a, c);
+        case 2: return __dadd_ru(a, c);
+        default: return __dadd_rz(a, c);
+    }
+}
+__device__ __forceinline__ double mul_rm(double a, double c, u32 mode) {
+    switch (mode) {
+        case 0: return __dmul_rn(a, c);
+        case 1: return __dmul_rd(a, c);
+        case 2: return __dmul_ru(a, c);
+        default: return __dmul_rz(a, c);
+    }
+}
+// e-group values are positive and finite (spec §4.3.2): directed rounding = round-to-nearest, then step one ulp against
+// the sign of the exact residual.  residual = fma(-q, b, a) is exact for a correctly rounded quotient / root.
+__device__ __forceinline__ double fix_positive(double q, double residual, u32 mode) {
+    long long bits = __double_as_longlong(q);
+    const bool down = (mode == 1 || mode == 3) && residual < 0.0, up = mode == 2 && residual > 0.0;
+    bits += up ? 1 : 0;
+    bits -= down ? 1 : 0;
+    return __longlong_as_double(bits);
+}
+__device__ __forceinline__ double div_rm(double a, double c, u32 mode) {
+    const double q = __ddiv_rn(a, c);
+    return fix_positive(q, __fma_rn(-q, c, a), mode);
+}
+__device__ __forceinline__ double sqrt_rm(double a, u32 mode) {
+    const double s = __dsqrt_rn(a);
+    return fix_positive(s, __fma_rn(-s, s, a), mode);
+}
+__device__ __forceinline__ u64 d2u(double v) { return (u64)__double_as_longlong(v); }
+__device__ __forceinline__ double u2d(u64 v) { return __longlong_as_double((long long)v); }
+
+template <int BS>
+__global__ void __launch_bounds__(BS) execute_kernel(BatchBuffers b, u32 n, const uint8_t *__restrict__ dataset) {
+    extern __shared__ u64 sm[];                  // [32][BS]: slot s of this thread's VM at sm[s * BS + tid]
+    const u32 tid = threadIdx.x, vm = blockIdx.x * BS + tid;
+    if (vm >= n) return;
+    const u32 stride = b.stride;
+#define REG(s) sm[(s) * BS + tid]
+#pragma unroll
+    for (int i = 0; i < 8; i++) REG(i) = 0;
+#pragma unroll
+    for (int i = 24; i < 32; i++) REG(i) = b.regfile[(size_t)i * stride + vm];
+    const u64 c0 = b.config[vm], c1 = b.config[(size_t)stride + vm];
+    const u64 emask_lo = b.config[(size_t)2 * stride + vm], emask_hi = b.config[(size_t)3 * stride + vm];
+    u32 ma = (u32)c0, mx = (u32)(c0 >> 32);
+    const u32 rr = (u32)(c1 >> 60);
+    const u32 rr0 = rr & 1, rr1 = 2 + ((rr >> 1) & 1), rr2 = 4 + ((rr >> 2) & 1), rr3 = 6 + ((rr >> 3) & 1);
+    const uint8_t *ds = dataset + (c1 & ((1ull << 60) - 1));
+    u32 mode = b.fprc[vm];
+    uint8_t *sp = b.scratchpads + (size_t)vm * kScratchpadL3;
+    const uint2 *prog = b.program + vm;
+    const u64 *rcp = b.rcp + vm;
+    constexpr u64 kEMant = (1ull << 56) - 1;
+
+    u32 sp0 = mx, sp1 = ma;
+    for (int it = 0; it < kProgramIterations; it++) {
+        const u64 mix = REG(rr0) ^ REG(rr1);
+        sp0 = (sp0 ^ (u32)mix) & kL3Mask64;
+        sp1 = (sp1 ^ (u32)(mix >> 32)) & kL3Mask64;
+        {
+            const ulonglong2 *p0 = reinterpret_cast<const ulonglong2 *>(sp + sp0);
+            const int4 *p1 = reinterpret_cast<const int4 *>(sp + sp1);
+            const ulonglong2 a0 = p0[0], a1 = p0[1], a2 = p0[2], a3 = p0[3];
+            const int4 f01 = p1[0], f23 = p1[1], e01 = p1[2], e23 = p1[3];
+            REG(0) ^= a0.x; REG(1) ^= a0.y; REG(2) ^= a1.x; REG(3) ^= a1.y; REG(4) ^= a2.x; REG(5) ^= a2.y; REG(6) ^= a3.x; REG(7) ^= a3.y;
+            REG(8) = d2u((double)f01.x);  REG(9) = d2u((double)f01.y);  REG(10) = d2u((double)f01.z); REG(11) = d2u((double)f01.w);
+            REG(12) = d2u((double)f23.x); REG(13) = d2u((double)f23.y); REG(14) = d2u((double)f23.z); REG(15) = d2u((double)f23.w);
+            REG(16) = (d2u((double)e01.x) & kEMant) | emask_lo; REG(17) = (d2u((double)e01.y) & kEMant) | emask_hi;
+            REG(18) = (d2u((double)e01.z) & kEMant) | emask_lo; REG(19) = (d2u((double)e01.w) & kEMant) | emask_hi;
+            REG(20) = (d2u((double)e23.x) & kEMant) | emask_lo; REG(21) = (d2u((double)e23.y) & kEMant) | emask_hi;
+            REG(22) = (d2u((double)e23.z) & kEMant) | emask_lo; REG(23) = (d2u((double)e23.w) & kEMant) | emask_hi;
+        }
+
+        uint2 ins = prog[0];
+        for (int pc = 0; pc < kProgramSize; pc++) {
+            const uint2 cur = ins;
+            if (pc + 1 < kProgramSize) ins = prog[(size_t)(pc + 1) * stride];     // fetched under this instruction's work
+            const u32 op = cur.x & 255, dslot = (cur.x >> 8) & 255, src = (cur.x >> 16) & 255, aux = cur.x >> 24;
+            const u64 simm = sext(cur.y);
+            // common operand fetch
+            const u64 d0 = REG(dslot), d1 = REG(dslot + 1);
+            const u32 sidx = src & 31;
+            u64 s0 = REG(sidx);
+            const u64 s1 = REG(sidx | 1);           // a-register high lane for FADD_R / FSUB_R / FMUL_R (src slot is even there)
+            s0 = src < 32 ? s0 : (src == kSrcImm ? simm : 0);
+            u64 v = s0;
+            if (op & X_MEM) {                       // the one scratchpad read of the instruction set
+                const u32 mask = aux == 0 ? kL1Mask : (aux == 1 ? kL2Mask : kL3Mask);
+                v = *reinterpret_cast<const u64 *>(sp + ((u32)(s0 + simm) & mask));
+            }
+            u64 r0 = d0, r1 = d1;
+            switch (op & 0x7f) {
+                case X_NOP: break;
+                case X_IADD_RS: r0 = d0 + (s0 << aux) + simm; break;
+                case X_IADD: r0 = d0 + v; break;
+                case X_ISUB: r0 = d0 - v; break;
+                case X_IMUL: r0 = d0 * v; break;
+                case X_IMULH: r0 = mulh_u(d0, v); break;
+                case X_ISMULH: r0 = mulh_s(d0, v); break;
+                case X_IXOR: r0 = d0 ^ v; break;
+                case X_IROR: { const u32 c = (u32)v & 63; r0 = (d0 >> c) | (d0 << ((64 - c) & 63)); } break;
+                case X_IROL: { const u32 c = (u32)v & 63; r0 = (d0 << c) | (d0 >> ((64 - c) & 63)); } break;
+                case X_INEG: r0 = 0 - d0; break;
+                case X_ISWAP: r0 = s0; REG(sidx) = d0; break;
+                case X_IMUL_RCP: r0 = d0 * rcp[(size_t)aux * stride]; break;
+                case X_IMUL_RCP_SLOW: r0 = d0 * device_reciprocal(cur.y); break;
+                case X_CBRANCH:
+                    r0 = d0 + simm;
+                    if ((r0 & (255ull << aux)) == 0) { pc = (int)src - 1; ins = prog[(size_t)src * stride]; }   // src = target + 1: the loop's pc++ lands there
+                    break;
+                case X_CFROUND: { const u32 c = aux; mode = (u32)((s0 >> c) | (s0 << ((64 - c) & 63))) & 3; } break;
+                case X_ISTORE: {
+                    const u32 mask = aux == 0 ? kL1Mask : (aux == 1 ? kL2Mask : kL3Mask);
+                    *reinterpret_cast<u64 *>(sp + ((u32)(d0 + simm) & mask)) = s0;
+                } break;
+                case X_FSWAP: r0 = d1; r1 = d0; break;
+                case X_FADD: case X_FSUB: {
+                    double lo, hi;
+                    if (op & X_MEM) { lo = (double)(int)(u32)v; hi = (double)(int)(u32)(v >> 32); }
+                    else { lo = u2d(s0); hi = u2d(s1); }
+                    if ((op & 0x7f) == X_FSUB) { lo = -lo; hi = -hi; }
+                    r0 = d2u(add_rm(u2d(d0), lo, mode)); r1 = d2u(add_rm(u2d(d1), hi, mode));
+                } break;
+                case X_FSCAL: r0 = d0 ^ 0x80F0000000000000ull; r1 = d1 ^ 0x80F0000000000000ull; break;
+                case X_FMUL: r0 = d2u(mul_rm(u2d(d0), u2d(s0), mode)); r1 = d2u(mul_rm(u2d(d1), u2d(s1), mode)); break;
+                case X_FDIV: {
+                    const u64 lo = (d2u((double)(int)(u32)v) & kEMant) | emask_lo, hi = (d2u((double)(int)(u32)(v >> 32)) & kEMant) | emask_hi;
+                    r0 = d2u(div_rm(u2d(d0), u2d(lo), mode)); r1 = d2u(div_rm(u2d(d1), u2d(hi), mode));
+                } break;
+                case X_FSQRT: r0 = d2u(sqrt_rm(u2d(d0), mode)); r1 = d2u(sqrt_rm(u2d(d1), mode)); break;
+                default: break;
+            }
+            REG(dslot) = r0;
+            if (op & 0x40) REG(dslot + 1) = r1;
+        }
+
+        mx = (mx ^ (u32)(REG(rr2) ^ REG(rr3))) & kDatasetAlignMask;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ds + mx));     // the line the NEXT iteration reads
+        {
+            const ulonglong2 *line = reinterpret_cast<const ulonglong2 *>(ds + ma);
+            const ulonglong2 l0 = __ldg(line), l1 = __ldg(line + 1), l2 = __ldg(line + 2), l3 = __ldg(line + 3);
+            const u64 n0 = REG(0) ^ l0.x, n1 = REG(1) ^ l0.y, n2 = REG(2) ^ l1.x, n3 = REG(3) ^ l1.y;
+            const u64 n4 = REG(4) ^ l2.x, n5 = REG(5) ^ l2.y, n6 = REG(6) ^ l3.x, n7 = REG(7) ^ l3.y;
+            REG(0) = n0; REG(1) = n1; REG(2) = n2; REG(3) = n3; REG(4) = n4; REG(5) = n5; REG(6) = n6; REG(7) = n7;
+            ulonglong2 *o1 = reinterpret_cast<ulonglong2 *>(sp + sp1);
+            o1[0] = make_ulonglong2(n0, n1); o1[1] = make_ulonglong2(n2, n3); o1[2] = make_ulonglong2(n4, n5); o1[3] = make_ulonglong2(n6, n7);
+        }
+        { const u32 tmp = mx; mx = ma; ma = tmp; }
+        {
+            ulonglong2 *o0 = reinterpret_cast<ulonglong2 *>(sp + sp0);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const u64 lo = REG(8 + 2 * i) ^ REG(16 + 2 * i), hi = REG(9 + 2 * i) ^ REG(17 + 2 * i);
+                REG(8 + 2 * i) = lo; REG(9 + 2 * i) = hi;
+                o0[i] = make_ulonglong2(lo, hi);
+            }
+        }
+        sp0 = 0; sp1 = 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 24; i++) b.regfile[(size_t)i * stride + vm] = REG(i);
+    b.fprc[vm] = (uint8_t)mode;
+#undef REG
+}
+
+// ---------------------------------------------------------------------------------------------- chain seed / final hash
+__global__ void chain_seed_kernel(BatchBuffers b, u32 n, bool final_hash) {
+    const u32 vm = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vm >= n) return;
+    u64 h[8], m[16];
+    b2_init(h, final_hash ? 32 : 64);
+    for (int i = 0; i < 16; i++) m[i] = b.regfile[(size_t)i * b.stride + vm];
+    b2_compress(h, m, 128, false);
+    for (int i = 0; i < 16; i++) m[i] = b.regfile[(size_t)(16 + i) * b.stride + vm];
+    b2_compress(h, m, 256, true);
+    if (final_hash) { u64 *out = reinterpret_cast<u64 *>(b.hashes + (size_t)vm * 32); for (int i = 0; i < 4; i++) out[i] = h[i]; }
+    else for (int i = 0; i < 8; i++) b.seed[(size_t)i * b.stride + vm] = h[i];
+}
+
+__global__ void find_below_kernel(const uint8_t *__restrict__ hashes, u32 n, const uint8_t *__restrict__ difficulty, u32 *found) {
+    const u32 vm = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vm >= n) return;
+    const uint8_t *h = hashes + (size_t)vm * 32;
+    for (int i = 0; i < 32; i++) {               // big-endian byte order: the first differing byte decides
+        const uint8_t a = h[i], d = difficulty[i];
+        if (a != d) { if (a < d) atomicMin(found, vm); return; }
+    }
+}
+
+inline u32 blocks_for(u64 n, u32 per) { return (u32)((n + per - 1) / per); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ host-side launchers
+cudaError_t upload_tables() {
+    // AES: S-box from the field inverse + affine map (FIPS-197 §5.1.1), then the MixColumns-folded round tables
+    uint8_t sbox[256], inv[256];
+    auto xt = [](uint8_t a) { return (uint8_t)((a << 1) ^ ((a & 0x80) ? 0x1b : 0)); };
+    auto gm = [&](uint8_t a, uint8_t c) { uint8_t p = 0; for (int i = 0; i < 8; i++) { if (c & 1) p ^= a; a = xt(a); c >>= 1; } return p; };
+    uint8_t ex[256], lg[256], x = 1;
+    for (int i = 0; i < 255; i++) { ex[i] = x; lg[x] = (uint8_t)i; x = (uint8_t)(x ^ xt(x)); }
+    for (int v = 0; v < 256; v++) {
+        const uint8_t iv = v ? ex[(255 - lg[v]) % 255] : 0;
+        uint8_t s = iv, r = iv;
+        for (int k = 0; k < 4; k++) { r = (uint8_t)((r << 1) | (r >> 7)); s ^= r; }
+        sbox[v] = s ^ 0x63;
+    }
+    for (int v = 0; v < 256; v++) inv[sbox[v]] = (uint8_t)v;
+    u32 te[256], td[256];
+    for (int v = 0; v < 256; v++) {
+        const uint8_t s = sbox[v], i = inv[v];
+        te[v] = (u32)gm(s, 2) | ((u32)s << 8) | ((u32)s << 16) | ((u32)gm(s, 3) << 24);
+        td[v] = (u32)gm(i, 14) | ((u32)gm(i, 9) << 8) | ((u32)gm(i, 13) << 16) | ((u32)gm(i, 11) << 24);
+    }
+    cudaError_t e;
+    if ((e = cudaMemcpyToSymbol(g_te0, te, sizeof te)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(g_td0, td, sizeof td)) != cudaSuccess) return e;
+    static const uint8_t freq[T_COUNT] = {16, 7, 16, 7, 16, 4, 4, 1, 4, 1, 8, 2, 15, 5, 8, 2, 4, 4, 16, 5, 16, 5, 6, 32, 4, 6, 25, 1, 16, 0};
+    uint8_t opmap[256]; int k = 0;
+    for (int t = 0; t < T_COUNT; t++) for (int j = 0; j < freq[t]; j++) opmap[k++] = (uint8_t)t;
+    if ((e = cudaMemcpyToSymbol(g_opmap, opmap, sizeof opmap)) != cudaSuccess) return e;
+    uint8_t g1[64], g4[128], hs[64], hx[32];
+    blake2b(g1, 64, "RandomX AesGenerator1R keys", 27);
+    blake2b(g4, 64, "RandomX AesGenerator4R keys 0-3", 31);
+    blake2b(g4 + 64, 64, "RandomX AesGenerator4R keys 4-7", 31);
+    blake2b(hs, 64, "RandomX AesHash1R state", 23);
+    blake2b(hx, 32, "RandomX AesHash1R xkeys", 23);
+    if ((e = cudaMemcpyToSymbol(c_gen1_keys, g1, 64)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_gen4_keys, g4, 128)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_hash_state, hs, 64)) != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_hash_xkeys, hx, 32);
+}
+
+cudaError_t launch_dataset(const uint64_t *d_cache, const SuperscalarImage &ss, uint64_t *d_dataset, uint64_t first, uint64_t count, cudaStream_t s) {
+    SsArgs a;
+    a.ops = ss.ops;
+    memcpy(a.first, ss.first, sizeof a.first);
+    memcpy(a.address_reg, ss.address_reg, sizeof a.address_reg);
+    dataset_kernel<<<blocks_for(count, kDatasetThreads), kDatasetThreads, 0, s>>>(reinterpret_cast<const u64 *>(d_cache), a, reinterpret_cast<u64 *>(d_dataset), first, count);
+    return cudaGetLastError();
+}
+cudaError_t launch_seed_inputs(const BatchBuffers &b, uint32_t n, const uint8_t *d_inputs, uint32_t input_len, cudaStream_t s) {
+    seed_inputs_kernel<<<blocks_for(n, 128), 128, 0, s>>>(reinterpret_cast<u64 *>(b.seed), b.stride, n, d_inputs, input_len);
+    return cudaGetLastError();
+}
+cudaError_t launch_seed_k2pow(const BatchBuffers &b, uint32_t n, const K2powTemplate &t, cudaStream_t s) {
+    seed_k2pow_kernel<<<blocks_for(n, 128), 128, 0, s>>>(reinterpret_cast<u64 *>(b.seed), b.stride, n, t);
+    return cudaGetLastError();
+}
+cudaError_t launch_fill_scratchpads(const BatchBuffers &b, uint32_t n, cudaStream_t s) {
+    fill_kernel<<<blocks_for((u64)n * 4, 256), 256, 0, s>>>(reinterpret_cast<u64 *>(b.seed), b.stride, n, b.scratchpads);
+    return cudaGetLastError();
+}
+cudaError_t launch_program(const BatchBuffers &b, uint32_t n, bool first_program, cudaStream_t s) {
+    program_kernel<<<blocks_for(n, 128), 128, 0, s>>>(b, n, first_program);
+    return cudaGetLastError();
+}
+int execute_max_ctas_per_sm() {
+    int ctas = 0;
+    cudaFuncSetAttribute(execute_kernel<kExecThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kExecThreads * 8);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, execute_kernel<kExecThreads>, kExecThreads, 32 * kExecThreads * 8) != cudaSuccess) return 0;
+    return ctas;
+}
+cudaError_t launch_execute(const BatchBuffers &b, uint32_t n, const uint64_t *d_dataset, cudaStream_t s) {
+    constexpr size_t smem = 32 * kExecThreads * 8;
+    cudaError_t e = cudaFuncSetAttribute(execute_kernel<kExecThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    execute_kernel<kExecThreads><<<blocks_for(n, kExecThreads), kExecThreads, smem, s>>>(b, n, reinterpret_cast<const uint8_t *>(d_dataset));
+    return cudaGetLastError();
+}
+cudaError_t launch_chain_seed(const BatchBuffers &b, uint32_t n, cudaStream_t s) {
+    chain_seed_kernel<<<blocks_for(n, 128), 128, 0, s>>>(b, n, false);
+    return cudaGetLastError();
+}
+cudaError_t launch_finalize(const BatchBuffers &b, uint32_t n, cudaStream_t s) {
+    hash_scratchpad_kernel<<<blocks_for((u64)n * 4, 256), 256, 0, s>>>(reinterpret_cast<u64 *>(b.regfile), b.stride, n, b.scratchpads);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    chain_seed_kernel<<<blocks_for(n, 128), 128, 0, s>>>(b, n, true);
+    return cudaGetLastError();
+}
+cudaError_t launch_find_below(const BatchBuffers &b, uint32_t n, const uint8_t *d_difficulty, uint32_t *d_found, cudaStream_t s) {
+    find_below_kernel<<<blocks_for(n, 256), 256, 0, s>>>(b.hashes, n, d_difficulty, d_found);
+    return cudaGetLastError();
+}
+
+}  // namespace rx
+}  // namespace b200post
