@@ -262,7 +262,7 @@ __device__ u64 device_reciprocal(u32 divisor) {
 
 __device__ __forceinline__ u32 pack(u32 op, u32 dst, u32 src, u32 aux) { return op | (dst << 8) | (src << 16) | (aux << 24); }
 
-__global__ void __launch_bounds__(128) program_kernel(BatchBuffers b, u32 n, bool first_program) {
+__global__ void __launch_bounds__(128) program_kernel(BatchBuffers b, u32 n, bool first_program, bool vm_major) {
     __shared__ AesSmem sm;
     __shared__ uint8_t opmap[256];
     __shared__ short usage[8][128];     // CBRANCH targets: last instruction that wrote each integer register
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(128) program_kernel(BatchBuffers b, u32 n, boo
                 case T_ISMULH_R: w0 = pack(X_ISMULH, dst, src, 0); usage[dst][t] = (short)i; break;
                 case T_IMUL_RCP:
                     if (imm & (imm - 1)) {
-                        if (n_rcp < (u32)kRcpSlots) { b.rcp[(size_t)n_rcp * stride + vm] = device_reciprocal(imm); w0 = pack(X_IMUL_RCP, dst, 0, n_rcp); n_rcp++; }
+                        if (n_rcp < (u32)kRcpSlots) { b.rcp[vm_major ? (size_t)vm * kRcpSlots + n_rcp : (size_t)n_rcp * stride + vm] = device_reciprocal(imm); w0 = pack(X_IMUL_RCP, dst, 0, n_rcp); n_rcp++; }
                         else w0 = pack(X_IMUL_RCP_SLOW, dst, 0, 0);
                         usage[dst][t] = (short)i;
                     }
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(128) program_kernel(BatchBuffers b, u32 n, boo
                 case T_ISTORE: w0 = pack(X_ISTORE, dst, src, (mod >> 4) < 14 ? lvl12 : 2); break;
                 default: break;
             }
-            b.program[(size_t)i * stride + vm] = make_uint2(w0, w1);
+            b.program[vm_major ? (size_t)vm * kProgramSize + i : (size_t)i * stride + vm] = make_uint2(w0, w1);
         }
     }
 }
@@ -540,6 +540,138 @@ __global__ void __launch_bounds__(BS) execute_kernel(BatchBuffers b, u32 n, cons
 #undef REG
 }
 
+// ---------------------------------------------------------------------------------------------- the VM, one warp per VM
+// All 32 lanes run the same VM, so the interpreter never diverges: the branch on the opcode is warp-uniform and a step
+// costs its own latency, not the worst latency among 32 unrelated programs.  The register file IS the warp: lane l
+// holds slot l (r0-7 | f0-3 lo,hi | e0-3 lo,hi | a0-3 lo,hi), an operand is one shuffle, the two halves of an FP
+// register are processed by their two lanes at once, and the 64-byte scratchpad / dataset lines of the loop prologue
+// and epilogue are single coalesced accesses by lanes 0-7 / 8-15 / 16-23.  The decoded program (2 KiB) and the
+// reciprocals (256 B) sit in shared memory.  A batch is SMs x warps-per-SM VMs: ~10 GB of scratchpads instead of
+// ~150 GB, and a hash takes a fraction of a second instead of many seconds (the verifier's pow check needs that).
+constexpr unsigned kFull = 0xffffffffu;
+__device__ __forceinline__ u64 shfl64(u64 v, int src) { return __shfl_sync(kFull, (unsigned long long)v, src); }
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) execute_warp_kernel(BatchBuffers b, u32 n, const uint8_t *__restrict__ dataset) {
+    extern __shared__ uint2 wsm[];               // per warp: 256 instructions + kRcpSlots reciprocals
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, vm = blockIdx.x * WARPS + warp;
+    if (vm >= n) return;                         // whole warp leaves together
+    uint2 *prog = wsm + warp * (kProgramSize + kRcpSlots);
+    const u64 *rcp = reinterpret_cast<const u64 *>(prog + kProgramSize);
+    for (int i = lane; i < kProgramSize; i += 32) prog[i] = b.program[(size_t)vm * kProgramSize + i];
+    reinterpret_cast<u64 *>(prog + kProgramSize)[lane] = b.rcp[(size_t)vm * kRcpSlots + lane];
+    __syncwarp();
+    const u32 stride = b.stride;
+    u64 reg = lane >= 24 ? b.regfile[(size_t)lane * stride + vm] : 0;
+    const u64 c0 = b.config[vm], c1 = b.config[(size_t)stride + vm];
+    const u64 emask = b.config[(size_t)(2 + (lane & 1)) * stride + vm];      // lo for even lanes, hi for odd ones
+    u32 ma = (u32)c0, mx = (u32)(c0 >> 32);
+    const u32 rr = (u32)(c1 >> 60);
+    const int rr0 = rr & 1, rr1 = 2 + ((rr >> 1) & 1), rr2 = 4 + ((rr >> 2) & 1), rr3 = 6 + ((rr >> 3) & 1);
+    const uint8_t *ds = dataset + (c1 & ((1ull << 60) - 1));
+    u32 mode = b.fprc[vm];
+    uint8_t *sp = b.scratchpads + (size_t)vm * kScratchpadL3;
+    constexpr u64 kEMant = (1ull << 56) - 1;
+    const bool is_r = lane < 8, is_f = lane >= 8 && lane < 16, is_e = lane >= 16 && lane < 24;
+
+    u32 sp0 = mx, sp1 = ma;
+    for (int it = 0; it < kProgramIterations; it++) {
+        const u64 mix = shfl64(reg, rr0) ^ shfl64(reg, rr1);
+        sp0 = (sp0 ^ (u32)mix) & kL3Mask64;
+        sp1 = (sp1 ^ (u32)(mix >> 32)) & kL3Mask64;
+        if (is_r) reg ^= *reinterpret_cast<const u64 *>(sp + sp0 + 8 * lane);
+        else if (lane < 24) {
+            const int x = *reinterpret_cast<const int *>(sp + sp1 + 4 * (lane - 8));     // f: bytes 0-31, e: bytes 32-63 of the line
+            const u64 bits = d2u((double)x);
+            reg = is_e ? ((bits & kEMant) | emask) : bits;
+        }
+
+        for (int pc = 0; pc < kProgramSize; pc++) {
+            const uint2 ins = prog[pc];
+            const u32 op = ins.x & 255, dslot = (ins.x >> 8) & 255, src = (ins.x >> 16) & 255, aux = ins.x >> 24;
+            const u64 simm = sext(ins.y);
+            if (op < 0x40 || (op & X_MEM)) {
+                // integer instruction, or an FP one with a memory operand: d = r[dst], s = r[src] | imm | 0
+                u64 s0 = shfl64(reg, (int)(src & 31));
+                s0 = src < 32 ? s0 : (src == kSrcImm ? simm : 0);
+                u64 v = s0;
+                if (op & X_MEM) {
+                    const u32 mask = aux == 0 ? kL1Mask : (aux == 1 ? kL2Mask : kL3Mask);
+                    v = *reinterpret_cast<const u64 *>(sp + ((u32)(s0 + simm) & mask));    // same address in every lane: one broadcast
+                }
+                if (op & 0x40) {        // FADD_M / FSUB_M / FDIV_M: each of the two destination lanes takes its int32 half
+                    const double m = (double)(int)(u32)((lane & 1) ? (v >> 32) : v);
+                    if ((lane & ~1u) == dslot) {
+                        const u32 k = op & 0x3f;
+                        if (k == (X_FDIV & 0x3f)) reg = d2u(div_rm(u2d(reg), u2d((d2u(m) & kEMant) | emask), mode));
+                        else reg = d2u(add_rm(u2d(reg), k == (X_FSUB & 0x3f) ? -m : m, mode));
+                    }
+                    continue;
+                }
+                const u64 d0 = shfl64(reg, (int)dslot);
+                u64 r0 = d0;
+                switch (op & 0x3f) {
+                    case X_IADD_RS: r0 = d0 + (s0 << aux) + simm; break;
+                    case X_IADD: r0 = d0 + v; break;
+                    case X_ISUB: r0 = d0 - v; break;
+                    case X_IMUL: r0 = d0 * v; break;
+                    case X_IMULH: r0 = mulh_u(d0, v); break;
+                    case X_ISMULH: r0 = mulh_s(d0, v); break;
+                    case X_IXOR: r0 = d0 ^ v; break;
+                    case X_IROR: { const u32 c = (u32)v & 63; r0 = (d0 >> c) | (d0 << ((64 - c) & 63)); } break;
+                    case X_IROL: { const u32 c = (u32)v & 63; r0 = (d0 << c) | (d0 >> ((64 - c) & 63)); } break;
+                    case X_INEG: r0 = 0 - d0; break;
+                    case X_ISWAP: r0 = s0; if (lane == src) reg = d0; break;
+                    case X_IMUL_RCP: r0 = d0 * rcp[aux]; break;
+                    case X_IMUL_RCP_SLOW: r0 = d0 * device_reciprocal(ins.y); break;
+                    case X_CBRANCH:
+                        r0 = d0 + simm;
+                        if ((r0 & (255ull << aux)) == 0) pc = (int)src - 1;      // src = target + 1
+                        break;
+                    case X_CFROUND: mode = (u32)((s0 >> aux) | (s0 << ((64 - aux) & 63))) & 3; break;
+                    case X_ISTORE: {
+                        const u32 mask = aux == 0 ? kL1Mask : (aux == 1 ? kL2Mask : kL3Mask);
+                        if (lane == 0) *reinterpret_cast<u64 *>(sp + ((u32)(d0 + simm) & mask)) = s0;
+                        __syncwarp();                                             // orders the store before later loads of other lanes
+                    } break;
+                    default: break;
+                }
+                if (lane == dslot) reg = r0;
+            } else {
+                // register-only FP instruction: the two lanes of the destination work on their halves
+                const bool mine = (lane & ~1u) == dslot;
+                switch (op) {
+                    case X_FSWAP: { const u64 o = __shfl_xor_sync(kFull, (unsigned long long)reg, 1); if (mine) reg = o; } break;
+                    case X_FADD: { const u64 a = shfl64(reg, (int)(src | (lane & 1))); if (mine) reg = d2u(add_rm(u2d(reg), u2d(a), mode)); } break;
+                    case X_FSUB: { const u64 a = shfl64(reg, (int)(src | (lane & 1))); if (mine) reg = d2u(add_rm(u2d(reg), -u2d(a), mode)); } break;
+                    case X_FSCAL: if (mine) reg ^= 0x80F0000000000000ull; break;
+                    case X_FMUL: { const u64 a = shfl64(reg, (int)(src | (lane & 1))); if (mine) reg = d2u(mul_rm(u2d(reg), u2d(a), mode)); } break;
+                    case X_FSQRT: if (mine) reg = d2u(sqrt_rm(u2d(reg), mode)); break;
+                    default: break;
+                }
+            }
+        }
+
+        mx = (mx ^ (u32)(shfl64(reg, rr2) ^ shfl64(reg, rr3))) & kDatasetAlignMask;
+        if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(ds + mx));
+        if (is_r) {
+            reg ^= __ldg(reinterpret_cast<const u64 *>(ds + ma) + lane);
+            *reinterpret_cast<u64 *>(sp + sp1 + 8 * lane) = reg;
+        }
+        { const u32 tmp = mx; mx = ma; ma = tmp; }
+        const u64 e_of_f = __shfl_down_sync(kFull, (unsigned long long)reg, 8);   // lane 8+k receives e's slot 16+k
+        __syncwarp();                                                              // r stored before f (they may share a line)
+        if (is_f) {
+            reg ^= e_of_f;
+            *reinterpret_cast<u64 *>(sp + sp0 + 8 * (lane - 8)) = reg;
+        }
+        __syncwarp();
+        sp0 = 0; sp1 = 0;
+    }
+    if (lane < 24) b.regfile[(size_t)lane * stride + vm] = reg;
+    if (lane == 0) b.fprc[vm] = (uint8_t)mode;
+}
+
 // ---------------------------------------------------------------------------------------------- chain seed / final hash
 __global__ void chain_seed_kernel(BatchBuffers b, u32 n, bool final_hash) {
     const u32 vm = blockIdx.x * blockDim.x + threadIdx.x;
@@ -628,8 +760,8 @@ cudaError_t launch_fill_scratchpads(const BatchBuffers &b, uint32_t n, cudaStrea
     fill_kernel<<<blocks_for((u64)n * 4, 256), 256, 0, s>>>(reinterpret_cast<u64 *>(b.seed), b.stride, n, b.scratchpads);
     return cudaGetLastError();
 }
-cudaError_t launch_program(const BatchBuffers &b, uint32_t n, bool first_program, cudaStream_t s) {
-    program_kernel<<<blocks_for(n, 128), 128, 0, s>>>(b, n, first_program);
+cudaError_t launch_program(const BatchBuffers &b, uint32_t n, bool first_program, bool vm_major, cudaStream_t s) {
+    program_kernel<<<blocks_for(n, 128), 128, 0, s>>>(b, n, first_program, vm_major);
     return cudaGetLastError();
 }
 int execute_max_ctas_per_sm() {
@@ -643,6 +775,11 @@ cudaError_t launch_execute(const BatchBuffers &b, uint32_t n, const uint64_t *d_
     cudaError_t e = cudaFuncSetAttribute(execute_kernel<kExecThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     execute_kernel<kExecThreads><<<blocks_for(n, kExecThreads), kExecThreads, smem, s>>>(b, n, reinterpret_cast<const uint8_t *>(d_dataset));
+    return cudaGetLastError();
+}
+cudaError_t launch_execute_warp(const BatchBuffers &b, uint32_t n, const uint64_t *d_dataset, cudaStream_t s) {
+    constexpr size_t smem = (size_t)kWarpsPerCta * (kProgramSize + kRcpSlots) * sizeof(uint2);
+    execute_warp_kernel<kWarpsPerCta><<<blocks_for(n, kWarpsPerCta), kWarpsPerCta * 32, smem, s>>>(b, n, reinterpret_cast<const uint8_t *>(d_dataset));
     return cudaGetLastError();
 }
 cudaError_t launch_chain_seed(const BatchBuffers &b, uint32_t n, cudaStream_t s) {

@@ -10,6 +10,7 @@ namespace b200post {
 namespace rx {
 
 constexpr int kExecThreads = 128;          // VMs per CTA of the VM kernel (register files live in its shared memory)
+constexpr int kWarpsPerCta = 4;             // warp-per-VM kernel: VMs per CTA
 constexpr int kRcpSlots = 32;              // resolved IMUL_RCP reciprocals kept per VM and program
 
 // Device-resident state of one batch of VMs.  All per-VM arrays are [field][vm] (field-major) so that a warp of 32
@@ -45,9 +46,11 @@ cudaError_t launch_seed_k2pow(const BatchBuffers &b, uint32_t n, const K2powTemp
 // AesGenerator1R: 2 MiB scratchpad per VM from its seed; the seed advances to the generator's final state
 cudaError_t launch_fill_scratchpads(const BatchBuffers &b, uint32_t n, cudaStream_t s);
 // AesGenerator4R -> 128 bytes of configuration + 256 instructions, decoded into the VM kernel's format
-cudaError_t launch_program(const BatchBuffers &b, uint32_t n, bool first_program, cudaStream_t s);
+cudaError_t launch_program(const BatchBuffers &b, uint32_t n, bool first_program, bool vm_major, cudaStream_t s);
 // the VM: 2048 iterations of the 256-instruction program against scratchpad and dataset
 cudaError_t launch_execute(const BatchBuffers &b, uint32_t n, const uint64_t *d_dataset, cudaStream_t s);
+// the same VM with one WARP per VM (program layout vm_major): no divergence, low latency, 1/16 of the memory
+cudaError_t launch_execute_warp(const BatchBuffers &b, uint32_t n, const uint64_t *d_dataset, cudaStream_t s);
 // seed = Blake2b-512(register file) for the next program of the chain
 cudaError_t launch_chain_seed(const BatchBuffers &b, uint32_t n, cudaStream_t s);
 // AesHash1R over the scratchpad into a0-3, then Blake2b-256(register file) -> hashes

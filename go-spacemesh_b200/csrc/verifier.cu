@@ -21,6 +21,8 @@
 #include "host_hash.h"
 #include "metrics.h"
 #include "proof_common.h"
+#include "randomx_engine.h"
+#include "../../include/b200post_k2pow.h"
 
 namespace b200post {
 namespace {
@@ -54,6 +56,10 @@ struct Job {
     bool done = false;
     // filled by prepare()
     std::vector<uint64_t> check;   // label indices to recompute, in verification order
+    std::vector<uint32_t> pos;     // position of each of them in the proof's K2 index list (what ErrInvalidIndex reports)
+    uint64_t bad_label = 0;        // the label index stored at the failing position
+    uint8_t pow_input[48];         // k2pow input of this proof (builtin pow check)
+    uint8_t pow_target[32];        // pow_difficulty / num_units
     uint8_t commitment[32];
     uint8_t key[16], lazy_key[16];
     uint8_t diff_msb = 0;
@@ -143,29 +149,42 @@ void prepare(Job &j, const b200post_verifier_opts &vo) {
     j.status = B200POST_OK;
     if (!p.indices || p.indices_len == 0) { j.status = B200POST_ERR_EMPTY_PROOF; return; }   // "proof indices are empty"
     const unsigned __int128 nl = (unsigned __int128)m.num_units * m.labels_per_unit;
-    if (nl == 0 || nl > ~0ull || q.k2 == 0 || q.k1 == 0 || m.num_units == 0) { j.status = B200POST_ERR_INVALID_ARGUMENT; return; }
+    // k2 <= 65535: the Subset shuffle draws 16-bit values (and the wire format caps a proof at 800 bytes anyway,
+    // activation/wire/wire_v1.go:41-45)
+    if (nl == 0 || nl > ~0ull || q.k2 == 0 || q.k2 > 0xffffu || q.k1 == 0 || m.num_units == 0) { j.status = B200POST_ERR_INVALID_ARGUMENT; return; }
     const uint64_t num_labels = (uint64_t)nl;
     const uint32_t bits = b200post_bits_per_index(num_labels);
     const size_t expect_len = ((size_t)q.k2 * bits + 7) / 8;
     if (p.indices_len != expect_len) { j.status = B200POST_ERR_INVALID_ARGUMENT; return; }   // wrong number of indices
     const uint32_t nonce_group = p.nonce / 16;
-    if (vo.pow_verify) {
+    if (vo.pow_mode != B200POST_POW_SKIP) {
         if (nonce_group > 255) { j.status = B200POST_ERR_INVALID_ARGUMENT; return; }
-        uint8_t scaled[32];
-        div256_u32(q.pow_difficulty, m.num_units, scaled);
-        if (vo.pow_verify(vo.pow_ctx, p.pow, (uint8_t)nonce_group, m.challenge, scaled, m.node_id) != 0) {
-            j.status = B200POST_ERR_INVALID_PROOF;
-            j.bad_index = ~0ull;   // the pow, not a label, is invalid
-            return;
+        div256_u32(q.pow_difficulty, m.num_units, j.pow_target);
+        if (vo.pow_mode == B200POST_POW_CALLBACK) {
+            if (vo.pow_verify(vo.pow_ctx, p.pow, (uint8_t)nonce_group, m.challenge, j.pow_target, m.node_id) != 0) {
+                j.status = B200POST_ERR_INVALID_PROOF;
+                j.bad_index = ~0ull;   // the pow, not a label, is invalid
+                return;
+            }
+        } else {
+            // builtin: the RandomX hashes of the whole batch are computed together on the device (process())
+            if (p.pow >> 56) { j.status = B200POST_ERR_INVALID_PROOF; j.bad_index = ~0ull; return; }   // more than the 7 bytes the prover hashes
+            for (int b = 0; b < 7; b++) j.pow_input[b] = (uint8_t)(p.pow >> (8 * b));
+            j.pow_input[7] = (uint8_t)nonce_group;
+            memcpy(j.pow_input + 8, m.challenge, 8);
+            memcpy(j.pow_input + 16, m.node_id, 32);
         }
     }
     std::vector<uint64_t> all(q.k2);
+    std::vector<uint32_t> where(q.k2);
+    for (uint32_t i = 0; i < q.k2; i++) where[i] = i;
     if (b200post_unpack_indices(p.indices, p.indices_len, bits, all.data(), all.size()) != q.k2) { j.status = B200POST_ERR_INVALID_ARGUMENT; return; }
     switch (j.opt.mode) {
-        case B200POST_VERIFY_ALL: j.check = std::move(all); break;
+        case B200POST_VERIFY_ALL: j.check = std::move(all); j.pos = std::move(where); break;
         case B200POST_VERIFY_SELECTED_INDEX:
             if (j.opt.selected_index >= q.k2) { j.status = B200POST_ERR_INVALID_ARGUMENT; return; }
             j.check.assign(1, all[j.opt.selected_index]);
+            j.pos.assign(1, j.opt.selected_index);
             break;
         case B200POST_VERIFY_SUBSET: {
             const uint32_t k3 = std::min(j.opt.k3, q.k2);
@@ -187,7 +206,10 @@ void prepare(Job &j, const b200post_verifier_opts &vo) {
                 do { r = rng.next_u16(); } while (r >= max_allowed && rng.ok);
                 if (!rng.ok) { j.status = B200POST_ERR_INVALID_ARGUMENT; return; }
                 std::swap(all[idx], all[idx + r % remaining]);
-                j.check.push_back(all[idx++]);
+                std::swap(where[idx], where[idx + r % remaining]);
+                j.check.push_back(all[idx]);
+                j.pos.push_back(where[idx]);
+                idx++;
             }
             break;
         }
@@ -345,8 +367,26 @@ int gather_and_judge(uint32_t provider, std::vector<Job *> &jobs, uint64_t n, co
 // One GPU batch: jobs may use different scrypt N; group by N (in practice a single value).
 int process(uint32_t provider, std::vector<Job *> &jobs, const b200post_verifier_opts &vo) {
     const auto t0 = std::chrono::steady_clock::now();
-    if (vo.pow_verify) { for (Job *j : jobs) prepare(*j, vo); }   // the callback's thread-safety is the caller's business
+    if (vo.pow_mode == B200POST_POW_CALLBACK) { for (Job *j : jobs) prepare(*j, vo); }   // the callback's thread-safety is the caller's business
     else parallel_for(jobs.size(), [&](size_t i) { prepare(*jobs[i], vo); });
+    if (vo.pow_mode == B200POST_POW_BUILTIN) {
+        // the k2pow check of verifying.ProofVerifier.Verify (activation/post_verifier.go:150-160): one RandomX hash per
+        // proof, all proofs of the batch in one device batch
+        std::vector<Job *> live;
+        for (Job *j : jobs) if (j->status == B200POST_OK) live.push_back(j);
+        if (!live.empty()) {
+            std::vector<uint8_t> in(live.size() * 48), out(live.size() * 32);
+            for (size_t i = 0; i < live.size(); i++) memcpy(&in[i * 48], live[i]->pow_input, 48);
+            RandomxEngine *rxe = randomx_engine_for(provider);
+            const std::string key = vo.pow_cache_key ? std::string(reinterpret_cast<const char *>(vo.pow_cache_key), vo.pow_cache_key_len)
+                                                     : std::string(B200POST_K2POW_DEFAULT_KEY);
+            const int rc = rxe ? rxe->hash_inputs(key, in.data(), 48, live.size(), out.data()) : B200POST_ERR_NO_DEVICE;
+            for (size_t i = 0; i < live.size(); i++) {
+                if (rc != B200POST_OK) live[i]->status = rc;
+                else if (memcmp(&out[i * 32], live[i]->pow_target, 32) >= 0) { live[i]->status = B200POST_ERR_INVALID_PROOF; live[i]->bad_index = ~0ull; }
+            }
+        }
+    }
     const auto t1 = std::chrono::steady_clock::now();
     metrics().verify_prepare_us_total += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
     struct Stage { std::chrono::steady_clock::time_point from; ~Stage() {
@@ -371,7 +411,11 @@ int process(uint32_t provider, std::vector<Job *> &jobs, const b200post_verifier
         for (Job *j : jobs) {
             if (j->status != B200POST_OK || j->params->scrypt_n != n) continue;
             if (rc != B200POST_OK) j->status = rc;
-            else if (first_bad[k] != 0xffffffffu) { j->status = B200POST_ERR_INVALID_PROOF; j->bad_index = j->check[first_bad[k]]; }
+            else if (first_bad[k] != 0xffffffffu) {
+                // verifying.ErrInvalidIndex{Index}: the POSITION in the proof's K2 list (activation/handler_v1.go:248 stores it as
+                // InvalidPostIndexProof.InvalidIdx, activation/malfeasance.go:165 re-verifies it with SelectedIndex(InvalidIdx))
+                j->status = B200POST_ERR_INVALID_PROOF; j->bad_index = j->pos[first_bad[k]]; j->bad_label = j->check[first_bad[k]];
+            }
             k++;
         }
     }
@@ -439,6 +483,10 @@ int b200post_verifier_new_multi(const uint32_t *providers, int n_providers, cons
     *out = nullptr;
     for (int d = 0; d < n_providers; d++)
         if (!engine_for(providers[d])) return providers[d] == B200POST_CPU_PROVIDER_ID ? B200POST_ERR_UNSUPPORTED : B200POST_ERR_NO_DEVICE;
+    if (opts && (opts->pow_mode > B200POST_POW_SKIP || (opts->pow_mode == B200POST_POW_CALLBACK && !opts->pow_verify))) {
+        set_error("pow_mode CALLBACK needs a pow_verify function; to run without the k2pow check ask for B200POST_POW_SKIP explicitly");
+        return B200POST_ERR_UNSUPPORTED;
+    }
     b200post_verifier *v = new b200post_verifier;
     v->provider = providers[0];
     if (opts) v->opts = *opts;
@@ -514,6 +562,10 @@ int b200post_verify_batch(uint32_t provider, size_t n, const b200post_proof *pro
     if (!engine_for(provider)) return provider == B200POST_CPU_PROVIDER_ID ? B200POST_ERR_UNSUPPORTED : B200POST_ERR_NO_DEVICE;
     b200post_verifier_opts vo{};
     if (opts) vo = *opts;
+    if (vo.pow_mode > B200POST_POW_SKIP || (vo.pow_mode == B200POST_POW_CALLBACK && !vo.pow_verify)) {
+        set_error("pow_mode CALLBACK needs a pow_verify function; to run without the k2pow check ask for B200POST_POW_SKIP explicitly");
+        return B200POST_ERR_UNSUPPORTED;
+    }
     std::vector<Job> jobs(n);
     std::vector<Job *> ptrs(n);
     for (size_t i = 0; i < n; i++) {

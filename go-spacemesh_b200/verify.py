@@ -42,11 +42,27 @@ POW_VERIFY_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64,
 
 
 class _VerifierOpts(ctypes.Structure):
-    _fields_ = [("pow_verify", POW_VERIFY_FN), ("pow_ctx", ctypes.c_void_p), ("max_batch_proofs", ctypes.c_uint32)]
+    _fields_ = [("pow_verify", POW_VERIFY_FN), ("pow_ctx", ctypes.c_void_p), ("max_batch_proofs", ctypes.c_uint32),
+                ("pow_mode", ctypes.c_uint32), ("pow_cache_key", ctypes.c_char_p), ("pow_cache_key_len", ctypes.c_size_t)]
+
+
+POW_BUILTIN, POW_CALLBACK, POW_SKIP = 0, 1, 2
+POW_INVALID = 2**64 - 1     # invalid_index value when the k2pow, not a label, is what failed
+
+
+def _verifier_opts(pow, max_batch_proofs: int = 0, pow_cache_key: bytes | None = None):
+    """pow: "builtin" (RandomX on the device, the library default), "skip" (explicit opt-out) or a callable
+    (pow, nonce_group, challenge8, difficulty32, node_id32) -> 0 if valid."""
+    if callable(pow):
+        cb = POW_VERIFY_FN(pow)
+        return _VerifierOpts(cb, None, max_batch_proofs, POW_CALLBACK, None, 0), cb
+    mode = {"builtin": POW_BUILTIN, "skip": POW_SKIP, "callback-missing": POW_CALLBACK}[pow]
+    return _VerifierOpts(ctypes.cast(None, POW_VERIFY_FN), None, max_batch_proofs, mode, pow_cache_key,
+                         len(pow_cache_key) if pow_cache_key else 0), None
 
 
 class ErrInvalidIndex(Exception):
-    """verifying.ErrInvalidIndex{Index}."""
+    """verifying.ErrInvalidIndex{Index}: Index = position in the proof's K2 index list (POW_INVALID: the k2pow failed)."""
     def __init__(self, index: int):
         super().__init__(f"invalid index: {index}")
         self.index = index
@@ -174,10 +190,10 @@ def _raise(rc: int, bad: int):
 class PostVerifier:
     """activation.PostVerifier: Verify(ctx, proof, metadata, opts...) error; Close() error."""
 
-    def __init__(self, provider: int = 0, pow_verify=None, max_batch_proofs: int = 0, providers: list[int] | None = None):
+    def __init__(self, provider: int = 0, pow="builtin", max_batch_proofs: int = 0, providers: list[int] | None = None,
+                 pow_cache_key: bytes | None = None):
         L = _bind()
-        self._cb = POW_VERIFY_FN(pow_verify) if pow_verify else ctypes.cast(None, POW_VERIFY_FN)
-        opts = _VerifierOpts(self._cb, None, max_batch_proofs)
+        opts, self._cb = _verifier_opts(pow, max_batch_proofs, pow_cache_key)
         self._h = ctypes.c_void_p()
         if providers:     # one dispatcher, a worker per device
             ids = (ctypes.c_uint32 * len(providers))(*providers)
@@ -226,26 +242,28 @@ class PreparedBatch:
         self.st = (ctypes.c_int * max(n, 1))()
         self.bad = (ctypes.c_uint64 * max(n, 1))()
 
-    def run(self, provider: int = 0):
-        rc = _bind().b200post_verify_batch(provider, self.n, self.cps, self.cms, ctypes.byref(self.cq), self.cos, None,
+    def run(self, provider: int = 0, pow="builtin"):
+        opts, _cb = _verifier_opts(pow)
+        rc = _bind().b200post_verify_batch(provider, self.n, self.cps, self.cms, ctypes.byref(self.cq), self.cos, ctypes.byref(opts),
                                            self.st, self.bad)
         if rc != OK:
             raise B200PostError(rc, lib().b200post_last_error().decode(errors="replace"))
         return list(self.st[:self.n]), list(self.bad[:self.n])
 
-    def run_multi(self, providers: list[int]):
+    def run_multi(self, providers: list[int], pow="builtin"):
         """The batch split over several B200s (contiguous runs of proofs, one host thread per device)."""
         ids = (ctypes.c_uint32 * len(providers))(*providers)
+        opts, _cb = _verifier_opts(pow)
         rc = _bind().b200post_verify_batch_multi(ids, len(providers), self.n, self.cps, self.cms, ctypes.byref(self.cq),
-                                                 self.cos, None, self.st, self.bad)
+                                                 self.cos, ctypes.byref(opts), self.st, self.bad)
         if rc != OK:
             raise B200PostError(rc, lib().b200post_last_error().decode(errors="replace"))
         return list(self.st[:self.n]), list(self.bad[:self.n])
 
 
 def verify_batch(proofs: list[Proof], metas: list[ProofMetadata], params: VerifyParams, *, provider: int = 0,
-                 providers: list[int] | None = None, options: list[dict] | None = None):
+                 providers: list[int] | None = None, options: list[dict] | None = None, pow="builtin"):
     """One synchronous GPU batch (BASELINE.json configs[2]).  Returns (statuses, invalid_indices).  With
     `providers` the batch is split over those devices."""
     batch = PreparedBatch(proofs, metas, params, options)
-    return batch.run_multi(providers) if providers else batch.run(provider)
+    return batch.run_multi(providers, pow) if providers else batch.run(provider, pow)

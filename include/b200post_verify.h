@@ -13,13 +13,17 @@
  * the verdicts.  Semantics kept: safe for concurrent use; "verifier is closed" after Close (B200POST_ERR_CLOSED,
  * activation/post_verifier_test.go:61,90,102); an empty index list is an error (B200POST_ERR_EMPTY_PROOF,
  * activation/e2e/validation_test.go:102); a label that fails the difficulty yields
- * B200POST_ERR_INVALID_PROOF + the offending index value (verifying.ErrInvalidIndex, activation/handler_v1.go:228).
+ * B200POST_ERR_INVALID_PROOF + the POSITION of the offending index in the proof's K2 list (verifying.ErrInvalidIndex{Index}:
+ * activation/handler_v1.go:228,248 stores it as InvalidPostIndexProof.InvalidIdx and activation/malfeasance.go:165
+ * re-verifies it with verifying.SelectedIndex(InvalidIdx), so it must be a position, also under SUBSET).
  *
  * PARITY NOTE.  Everything outside label recomputation — index bit-packing, the BLAKE3-derived AES-128 keys,
  * the 8/56-bit difficulty compare, Subset(K3, seed) selection — follows the published post-rs v0.7.x
  * behaviour from memory; none of it is pinned by a vector in the reference tree ("parity unpinned",
- * DESIGN.md §2).  The k2pow check is RandomX (cmd/root.go:254-259) and is NOT implemented here: pass a
- * callback (e.g. libpost's RandomX verifier) or leave it NULL to skip it explicitly.
+ * DESIGN.md §2).  The k2pow check is RandomX (cmd/root.go:254-259): by default the verifier computes one RandomX hash
+ * per proof on the device (include/b200post_k2pow.h; the RandomX function itself is pinned on its official vectors).
+ * A caller-supplied callback or an explicit skip are opt-in (b200post_verifier_opts.pow_mode); a NULL callback no
+ * longer means "skip".
  */
 #ifndef B200POST_VERIFY_H
 #define B200POST_VERIFY_H
@@ -69,19 +73,27 @@ typedef struct b200post_verify_options {
 typedef int (*b200post_pow_verify_fn)(void *ctx, uint64_t pow, uint8_t nonce_group, const uint8_t challenge8[8],
                                       const uint8_t difficulty[32], const uint8_t node_id[32]);
 
+enum { B200POST_POW_BUILTIN = 0, B200POST_POW_CALLBACK = 1, B200POST_POW_SKIP = 2 };
+
 typedef struct b200post_verifier_opts {
-    b200post_pow_verify_fn pow_verify;     /* NULL = the k2pow check is skipped (explicitly, see PARITY NOTE)          */
+    b200post_pow_verify_fn pow_verify;     /* used when pow_mode == B200POST_POW_CALLBACK (must be non-NULL then)        */
     void *pow_ctx;
     uint32_t max_batch_proofs;             /* 0 = 16384; cap on proofs coalesced into one GPU batch                    */
+    uint32_t pow_mode;                     /* BUILTIN (default, also with opts == NULL): RandomX on the device;
+                                              CALLBACK: pow_verify; SKIP: no k2pow check — must be asked for explicitly  */
+    const uint8_t *pow_cache_key;          /* BUILTIN: RandomX cache key, NULL = B200POST_K2POW_DEFAULT_KEY              */
+    size_t pow_cache_key_len;
 } b200post_verifier_opts;
 
 typedef struct b200post_verifier b200post_verifier;
 
-/* NewPostVerifier (activation/post_verifier.go:191-221).  opts may be NULL. */
+/* NewPostVerifier (activation/post_verifier.go:191-221).  opts may be NULL (= builtin k2pow check).
+ * B200POST_ERR_UNSUPPORTED if pow_mode is CALLBACK without a function. */
 int b200post_verifier_new(uint32_t provider, const b200post_verifier_opts *opts, b200post_verifier **out);
 
 /* PostVerifier.Verify: blocking, safe for concurrent use.  options may be NULL (= ALL, not prioritised).
- * Returns B200POST_OK, B200POST_ERR_INVALID_PROOF (*invalid_index = the label index that failed, if non-NULL),
+ * Returns B200POST_OK, B200POST_ERR_INVALID_PROOF (*invalid_index = position 0..K2-1 of the failing index in the proof's
+ * index list, or UINT64_MAX when the k2pow — not a label — is invalid),
  * B200POST_ERR_EMPTY_PROOF, B200POST_ERR_INVALID_ARGUMENT, B200POST_ERR_CLOSED, or an engine error. */
 int b200post_verifier_verify(b200post_verifier *v, const b200post_proof *proof, const b200post_proof_metadata *meta,
                              const b200post_verify_params *params, const b200post_verify_options *options,
@@ -100,7 +112,7 @@ void b200post_verifier_free(b200post_verifier *v);
 int b200post_verifier_stats(b200post_verifier *v, uint64_t *batches, uint64_t *proofs);
 
 /* Synchronous batch form (BASELINE.json configs[2]: 10 000 proofs x K2 = 37): verifies n proofs in one GPU
- * batch on the calling thread.  statuses[i] gets the per-proof code, invalid_indices[i] the failing index. */
+ * batch on the calling thread.  statuses[i] gets the per-proof code, invalid_indices[i] the failing position. */
 int b200post_verify_batch(uint32_t provider, size_t n, const b200post_proof *proofs, const b200post_proof_metadata *metas,
                           const b200post_verify_params *params, const b200post_verify_options *options /* n or NULL */,
                           const b200post_verifier_opts *opts, int *statuses, uint64_t *invalid_indices);

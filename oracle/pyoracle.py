@@ -393,11 +393,13 @@ def py_label_passes(label16: bytes, challenge: bytes, nonce: int, pow_: int, dif
     return (int.from_bytes(out[:8], "little") & ((1 << 56) - 1)) < (difficulty & ((1 << 56) - 1))
 
 
-def py_subset_positions(values, seed: bytes, nonce: int, packed: bytes, pow_: int, k3: int):
-    """RandomValuesIterator: BLAKE3-XOF driven partial Fisher-Yates; returns the first k3 selected values."""
+def py_subset_positions(values, seed: bytes, nonce: int, packed: bytes, pow_: int, k3: int, with_positions: bool = False):
+    """RandomValuesIterator: BLAKE3-XOF driven partial Fisher-Yates; returns the first k3 selected values
+    (with_positions: pairs (value, position in `values`))."""
     import blake3
     stream = blake3.blake3(seed + nonce.to_bytes(4, "little") + packed + pow_.to_bytes(8, "little")).digest(8192)
     vals, pos, out, idx = list(values), 0, [], 0
+    where = list(range(len(vals)))
     while len(out) < min(k3, len(vals)):
         remaining = len(vals) - idx
         max_allowed = 0xFFFF - 0xFFFF % remaining
@@ -407,7 +409,8 @@ def py_subset_positions(values, seed: bytes, nonce: int, packed: bytes, pow_: in
             if r < max_allowed:
                 break
         vals[idx], vals[idx + r % remaining] = vals[idx + r % remaining], vals[idx]
-        out.append(vals[idx])
+        where[idx], where[idx + r % remaining] = where[idx + r % remaining], where[idx]
+        out.append((vals[idx], where[idx]) if with_positions else vals[idx])
         idx += 1
     return out
 
@@ -415,7 +418,8 @@ def py_subset_positions(values, seed: bytes, nonce: int, packed: bytes, pow_: in
 def py_verify(nonce: int, packed: bytes, pow_: int, node_id: bytes, atx: bytes, challenge: bytes, num_units: int,
               labels_per_unit: int, k1: int, k2: int, n: int, mode: str = "all", k3: int = 0, seed: bytes = b"",
               selected: int = 0):
-    """Returns (ok, failing_label_index or None).  Labels come from the C oracle."""
+    """Returns (ok, position of the failing index in the proof's K2 list or None) — the position is what
+    verifying.ErrInvalidIndex carries (activation/handler_v1.go:248, activation/malfeasance.go:165).  Labels come from the C oracle."""
     if not packed:
         raise ValueError("proof indices are empty")
     num_labels = num_units * labels_per_unit
@@ -423,17 +427,19 @@ def py_verify(nonce: int, packed: bytes, pow_: int, node_id: bytes, atx: bytes, 
     if len(packed) != (k2 * bits + 7) // 8:
         raise ValueError("wrong indices length")
     idx = py_unpack_indices(packed, bits, k2)
+    where = list(range(k2))
     if mode == "subset":
-        idx = py_subset_positions(idx, seed, nonce, packed, pow_, k3)
+        pairs = py_subset_positions(idx, seed, nonce, packed, pow_, k3, with_positions=True)
+        idx, where = [p[0] for p in pairs], [p[1] for p in pairs]
     elif mode == "selected":
-        idx = [idx[selected]]
+        idx, where = [idx[selected]], [selected]
     c = py_commitment(node_id, atx)
     comms = np.tile(np.frombuffer(c, dtype=np.uint8), (len(idx), 1))
     labels = c_labels_gather(comms, np.array(idx, dtype=np.uint64), n, threads=4)
     diff = py_proving_difficulty(k1, num_labels)
-    for i, lab in zip(idx, labels):
+    for w, lab in zip(where, labels):
         if not py_label_passes(lab.tobytes(), challenge, nonce, pow_, diff):
-            return False, i
+            return False, w
     return True, None
 
 

@@ -64,7 +64,7 @@ def test_init_prove_verify_roundtrip(mods, tmp_path, orc, n, lpu, units, k1, k2,
     # the oracle's verifier accepts it ...
     assert orc.py_verify(proof.nonce, proof.indices, proof.pow, NODE, ATX, challenge, units, lpu, k1, k2, n) == (True, None)
     # ... and so does the batched GPU verifier, in every mode
-    v = vf.PostVerifier()
+    v = vf.PostVerifier(pow="skip")
     try:
         v.verify(proof, meta, params)
         v.verify(proof, meta, params, mode=vf.MODE_SUBSET, k3=3, seed=b"peer")
@@ -118,7 +118,7 @@ def test_mainnet_shaped_lifecycle_at_n8192(mods, tmp_path, orc, b2):
     proof, meta, scanned = pr.generate_proof(o.data_dir, challenge, cfg, nonces=288)
     assert len(proof.indices) == (k2 * vf.bits_per_index(units * lpu) + 7) // 8 and scanned <= units * lpu
     params = vf.VerifyParams(k1=k1, k2=k2, scrypt_n=8192)
-    v = vf.PostVerifier()
+    v = vf.PostVerifier(pow="skip")
     try:
         v.verify(proof, meta, params)                                       # all K2 indices
         v.verify(proof, meta, params, mode=vf.MODE_SUBSET, k3=1, seed=b"peer")

@@ -39,7 +39,7 @@ def _oracle_verdict(orc, proof, meta, params, **kw):
 
 def test_valid_proofs_pass_in_every_mode(vf, orc, small_space):
     meta, params, proofs = small_space
-    v = vf.PostVerifier()
+    v = vf.PostVerifier(pow="skip")
     try:
         for nonce, (proof, hits) in proofs.items():
             assert _oracle_verdict(orc, proof, meta, params) == (True, None)
@@ -52,11 +52,11 @@ def test_valid_proofs_pass_in_every_mode(vf, orc, small_space):
 
 
 def test_tampered_indices_are_reported(vf, orc, small_space):
-    """Indices[i] += 1 for every position: verdict and failing index must equal the oracle's."""
+    """Indices[i] += 1 for every position: verdict and failing POSITION (ErrInvalidIndex.Index) must equal the oracle's."""
     meta, params, proofs = small_space
     proof, hits = proofs[5]
     bits = vf.bits_per_index(meta.num_units * meta.labels_per_unit)
-    v = vf.PostVerifier()
+    v = vf.PostVerifier(pow="skip")
     try:
         seen_invalid = 0
         for pos in range(params.k2):
@@ -74,7 +74,7 @@ def test_tampered_indices_are_reported(vf, orc, small_space):
                 # SelectedIndex on the tampered position (activation/malfeasance.go:161-166)
                 with pytest.raises(vf.ErrInvalidIndex) as e:
                     v.verify(tampered, meta, params, mode=vf.MODE_SELECTED_INDEX, selected_index=pos)
-                assert e.value.index == bad[pos]
+                assert e.value.index == pos
         assert seen_invalid >= params.k2 // 2
     finally:
         v.close()
@@ -86,7 +86,7 @@ def test_subset_selection_matches_oracle(vf, orc, small_space):
     proof, hits = proofs[17]
     bits = vf.bits_per_index(meta.num_units * meta.labels_per_unit)
     garbage = vf.Proof(proof.nonce, vf.pack_indices([(h * 7 + 3) % 1024 for h in hits], bits), proof.pow)
-    v = vf.PostVerifier()
+    v = vf.PostVerifier(pow="skip")
     try:
         for seed in (b"", b"peer-A", b"peer-B" * 5):
             for k3 in (1, 2, 5, 8, 20):
@@ -104,7 +104,7 @@ def test_subset_selection_matches_oracle(vf, orc, small_space):
 def test_malformed_proofs(vf, b2, small_space):
     meta, params, proofs = small_space
     proof, _ = proofs[0]
-    v = vf.PostVerifier()
+    v = vf.PostVerifier(pow="skip")
     try:
         with pytest.raises(vf.ErrEmptyProof):                       # "proof indices are empty"
             v.verify(vf.Proof(0, b"", 0), meta, params)
@@ -123,7 +123,7 @@ def test_closed_verifier(vf, small_space):
     """post_verifier_test.go:37-62,64-91: Verify after Close -> "verifier is closed"; Close is idempotent."""
     meta, params, proofs = small_space
     proof, _ = proofs[0]
-    v = vf.PostVerifier()
+    v = vf.PostVerifier(pow="skip")
     v.verify(proof, meta, params)
     v.close()
     v.close()
@@ -139,7 +139,7 @@ def test_concurrent_callers_are_coalesced(vf, orc, b2, small_space, multi):
     meta, params, proofs = small_space
     bits = vf.bits_per_index(1024)
     gpus = [p["id"] for p in b2.providers() if p["id"] != b2.CPU_PROVIDER_ID]
-    v = vf.PostVerifier(providers=gpus if len(gpus) > 1 else gpus * 2) if multi else vf.PostVerifier()
+    v = vf.PostVerifier(pow="skip", providers=gpus if len(gpus) > 1 else gpus * 2) if multi else vf.PostVerifier(pow="skip")
     work = []
     for nonce, (proof, hits) in proofs.items():
         work.append((proof, None))
@@ -182,12 +182,12 @@ def test_pow_callback_contract(vf, small_space):
         return 0
 
     q = vf.VerifyParams(params.k1, params.k2, params.scrypt_n, pow_difficulty=bytes([0, 0x0d, 0xfb, 0x23]) + b"\xff" * 28)
-    v = vf.PostVerifier(pow_verify=pow_ok)
+    v = vf.PostVerifier(pow=pow_ok)
     v.verify(proof, meta, q)
     v.close()
     scaled = (int.from_bytes(q.pow_difficulty, "big") // meta.num_units).to_bytes(32, "big")
     assert seen == [(proof.pow, proof.nonce // 16, meta.challenge[:8], scaled, meta.node_id)]
-    v = vf.PostVerifier(pow_verify=lambda *a: 1)
+    v = vf.PostVerifier(pow=lambda *a: 1)
     with pytest.raises(vf.ErrInvalidIndex) as e:
         v.verify(proof, meta, q)
     assert e.value.index == 2**64 - 1          # the pow, not a label, was rejected
@@ -210,11 +210,11 @@ def test_batch_at_mainnet_shape(vf, orc, b2):
         proofs.append(vf.Proof(int(rng.integers(0, 288)), vf.pack_indices(ix, bits), int(rng.integers(0, 2**56))))
         metas.append(vf.ProofMetadata(node_id, atx, ch, 4, 2**32))
     opts = [dict(mode=vf.MODE_SUBSET, k3=4, seed=b"p") if i % 3 == 0 else dict() for i in range(n_proofs)]
-    st, bad = vf.verify_batch(proofs, metas, params, options=opts)
+    st, bad = vf.verify_batch(proofs, metas, params, options=opts, pow="skip")
     assert set(st) <= {b2.OK, b2.ERR_INVALID_PROOF}
     for i in range(n_proofs):
         if st[i] == b2.ERR_INVALID_PROOF:
-            assert bad[i] in idxs[i]
+            assert 0 <= bad[i] < k2          # a position in the K2 list (ErrInvalidIndex.Index), not a label index
     for i in list(range(0, n_proofs, 16)):
         kw = dict(mode="subset", k3=4, seed=b"p") if i % 3 == 0 else {}
         ok, idx = _oracle_verdict(orc, proofs[i], metas[i], params, **kw)
@@ -235,7 +235,7 @@ def test_device_epilogue_against_oracle_densely(vf, orc, b2):
         ix = [int(x) for x in rng.integers(0, num_units * lpu, k2)]
         proofs.append(vf.Proof(int(rng.integers(0, 320)), vf.pack_indices(ix, bits), int(rng.integers(0, 2**60))))
         metas.append(vf.ProofMetadata(node_id, atx, ch, num_units, lpu))
-    st, bad = vf.verify_batch(proofs, metas, params)
+    st, bad = vf.verify_batch(proofs, metas, params, pow="skip")
     n_ok = 0
     for i in range(n_proofs):
         ok, idx = _oracle_verdict(orc, proofs[i], metas[i], params)
@@ -259,12 +259,12 @@ def test_batch_split_over_devices(vf, b2):
         metas.append(vf.ProofMetadata(ident[:32], ident[32:64], ident[64:], num_units, lpu))
     gpus = [p["id"] for p in b2.providers() if p["id"] != b2.CPU_PROVIDER_ID]
     devs = gpus if len(gpus) > 1 else [gpus[0], gpus[0]]
-    one = vf.verify_batch(proofs, metas, params, provider=gpus[0])
-    many = vf.verify_batch(proofs, metas, params, providers=devs)
+    one = vf.verify_batch(proofs, metas, params, provider=gpus[0], pow="skip")
+    many = vf.verify_batch(proofs, metas, params, providers=devs, pow="skip")
     assert one == many and one[0][300] == b2.ERR_EMPTY_PROOF and 0 < sum(1 for s in one[0] if s == b2.OK) < n_proofs
-    assert vf.verify_batch(proofs[:1], metas[:1], params, providers=devs) == ([one[0][0]], [one[1][0]])
+    assert vf.verify_batch(proofs[:1], metas[:1], params, providers=devs, pow="skip") == ([one[0][0]], [one[1][0]])
     with pytest.raises(b2.B200PostError):
-        vf.verify_batch(proofs, metas, params, providers=[gpus[0], 12345])
+        vf.verify_batch(proofs, metas, params, providers=[gpus[0], 12345], pow="skip")
 
 
 def test_metrics_follow_the_work(vf, b2, small_space):
@@ -278,7 +278,7 @@ def test_metrics_follow_the_work(vf, b2, small_space):
 
     before = {k: val(k) for k in ("b200post_verify_proofs_total", "b200post_labels_gather_total",
                                   "b200post_post_verification_seconds_count")}
-    v = vf.PostVerifier()
+    v = vf.PostVerifier(pow="skip")
     for _ in range(3):
         v.verify(proof, meta, params)
     v.close()
@@ -301,7 +301,7 @@ def test_prioritized_calls_jump_the_queue(vf, orc):
     def mk():
         return vf.Proof(0, vf.pack_indices([int(x) for x in rng.integers(0, num_labels, k2)], bits), 0)
 
-    v = vf.PostVerifier(max_batch_proofs=1)
+    v = vf.PostVerifier(pow="skip", max_batch_proofs=1)
     order, lock = [], threading.Lock()
 
     def call(tag, prioritized):
@@ -324,3 +324,55 @@ def test_prioritized_calls_jump_the_queue(vf, orc):
     v.close()
     assert n == 11 and batches == 11
     assert order.index("PRIO") <= 5, order
+
+
+def test_builtin_k2pow_check(vf, b2, small_space):
+    """Default verifier = the RandomX pow check on the device (activation/post_verifier.go:150-160): a mined pow passes,
+    any other fails with the 'k2pow, not a label' marker; the difficulty is pow_difficulty / num_units."""
+    k2 = importlib.import_module("go-spacemesh_b200.k2pow")
+    meta, params, proofs = small_space
+    proof, hits = proofs[17]
+    easy = bytes([0x20]) + b"\x00" * 31                        # 1/8 of all hashes pass before scaling, 1/32 after / 4 units
+    q = vf.VerifyParams(params.k1, params.k2, params.scrypt_n, pow_difficulty=easy)
+    scaled = k2.scale_difficulty(easy, meta.num_units)
+    found, _ = k2.search(proof.nonce // 16, meta.challenge[:8], meta.node_id, scaled, 0, 4096)
+    assert found is not None
+    # the labels of `proof` were proven under pow = proof.pow: keep the label check out of it (SELECTED_INDEX would still
+    # bind to the pow through the AES key), so this test drives verify_batch on statuses only
+    good = vf.Proof(proof.nonce, proof.indices, found)
+    wrong = vf.Proof(proof.nonce, proof.indices, found + 1 if not k2.verify(found + 1, proof.nonce // 16, meta.challenge[:8], meta.node_id, scaled) else found + 2)
+    st, bad = vf.verify_batch([good, wrong, wrong], [meta] * 3, q, pow="builtin")
+    assert st[1] == st[2] == b2.ERR_INVALID_PROOF and bad[1] == bad[2] == vf.POW_INVALID
+    assert st[0] in (b2.OK, b2.ERR_INVALID_PROOF) and bad[0] != vf.POW_INVALID   # pow accepted; labels judged under the new key
+    st2, _ = vf.verify_batch([good], [meta], q, pow="skip")
+    assert st2[0] == st[0]
+    # through the queueing verifier (opts == builtin by default)
+    v = vf.PostVerifier()
+    try:
+        with pytest.raises(vf.ErrInvalidIndex) as e:
+            v.verify(wrong, meta, q)
+        assert e.value.index == vf.POW_INVALID
+        big = vf.Proof(proof.nonce, proof.indices, 2**56 + 5)     # does not fit the 7 hashed bytes
+        with pytest.raises(vf.ErrInvalidIndex) as e:
+            v.verify(big, meta, q)
+        assert e.value.index == vf.POW_INVALID
+    finally:
+        v.close()
+
+
+def test_pow_policy_is_explicit(vf, b2):
+    """A NULL callback no longer means 'skip': CALLBACK without a function is refused, SKIP must be asked for."""
+    with pytest.raises(b2.B200PostError) as e:
+        vf.PostVerifier(pow="callback-missing")
+    assert e.value.code == b2.ERR_UNSUPPORTED
+    vf.PostVerifier(pow="skip").close()
+
+
+def test_k2_above_16_bits_is_rejected(vf, b2):
+    meta = vf.ProofMetadata(bytes(32), bytes(32), bytes(32), 1, 2**20)
+    bits = vf.bits_per_index(2**20)
+    for k2 in (65536, 70000):
+        params = vf.VerifyParams(k1=10, k2=k2, scrypt_n=2)
+        proof = vf.Proof(0, bytes((k2 * bits + 7) // 8), 0)
+        st, _ = vf.verify_batch([proof], [meta], params, options=[dict(mode=vf.MODE_SUBSET, k3=2, seed=b"s")], pow="skip")
+        assert st == [b2.ERR_INVALID_ARGUMENT]
