@@ -79,7 +79,7 @@ int b200post_set_option(const char *key, int64_t value) {
     if (k == "ctas_per_sm" && value >= 0 && value <= 32) { o.ctas_per_sm = value; return B200POST_OK; }
     if (k == "max_scratch_mib" && value >= 0) { o.max_scratch_mib = value; return B200POST_OK; }
     if (k == "speculate_next" && (value == 0 || value == 1)) { o.speculate_next = value; return B200POST_OK; }
-    if (k == "rx_vm_mode" && (value == 0 || value == 1)) { o.rx_vm_mode = value; return B200POST_OK; }
+    if (k == "rx_vm_mode" && value >= 0 && value <= 2) { o.rx_vm_mode = value; return B200POST_OK; }
     if (k == "rx_vms_per_sm" && value >= 0 && value <= 4096) { o.rx_vms_per_sm = value; return B200POST_OK; }
     if (k == "debug_skip_phase" && value >= 0 && value <= 3) { o.debug_skip_phase = value; return B200POST_OK; }
     set_error("unknown option or value out of range: " + k);

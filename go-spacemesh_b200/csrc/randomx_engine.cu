@@ -45,7 +45,7 @@ void RandomxEngine::release_batch() {
 
 uint32_t RandomxEngine::desired_batch() const {
     int64_t per_sm = options().rx_vms_per_sm.load();
-    if (per_sm <= 0) per_sm = options().rx_vm_mode.load() != 0 ? 32 : 256;   // warp-per-VM: warps per SM; thread-per-VM: threads per SM
+    if (per_sm <= 0) per_sm = options().rx_vm_mode.load() == 0 ? 32 : (options().rx_vm_mode.load() == 1 ? 48 : 64);   // = resident warps per SM of the variant
     return (uint32_t)std::min<int64_t>((int64_t)prop_.multiProcessorCount * per_sm, 1 << 20);
 }
 
@@ -125,13 +125,12 @@ int RandomxEngine::ensure_batch(uint32_t want) {
 }
 
 int RandomxEngine::run_chain(uint32_t n) {
-    const bool warp_mode = options().rx_vm_mode.load() != 0;
+    const int vm_mode = (int)options().rx_vm_mode.load();
     RX_TRY(rx::launch_fill_scratchpads(buf_, n, stream_));
     for (int p = 0; p < rx::kProgramCount; p++) {
-        RX_TRY(rx::launch_program(buf_, n, p == 0, warp_mode, stream_));
+        RX_TRY(rx::launch_program(buf_, n, p == 0, stream_));
         RX_TRY(cudaEventRecord(ev_[2], stream_));
-        if (warp_mode) RX_TRY(rx::launch_execute_warp(buf_, n, d_dataset_, stream_));
-        else RX_TRY(rx::launch_execute(buf_, n, d_dataset_, stream_));
+        RX_TRY(rx::launch_execute(buf_, n, d_dataset_, vm_mode, stream_));
         RX_TRY(cudaEventRecord(ev_[3], stream_));
         if (p + 1 < rx::kProgramCount) RX_TRY(rx::launch_chain_seed(buf_, n, stream_));
         // the VM kernel's own time: events bracket it on the launching stream; summed after the sync below

@@ -239,13 +239,17 @@ __global__ void __launch_bounds__(256) hash_scratchpad_kernel(u64 *__restrict__ 
 enum : uint8_t { T_IADD_RS, T_IADD_M, T_ISUB_R, T_ISUB_M, T_IMUL_R, T_IMUL_M, T_IMULH_R, T_IMULH_M, T_ISMULH_R, T_ISMULH_M, T_IMUL_RCP,
                  T_INEG_R, T_IXOR_R, T_IXOR_M, T_IROR_R, T_IROL_R, T_ISWAP_R, T_FSWAP_R, T_FADD_R, T_FADD_M, T_FSUB_R, T_FSUB_M,
                  T_FSCAL_R, T_FMUL_R, T_FDIV_M, T_FSQRT_R, T_CBRANCH, T_CFROUND, T_ISTORE, T_NOP, T_COUNT };
-// decoded form: word0 = op | dst slot << 8 | src << 16 | aux << 24, word1 = imm32.
-//   op bit 7 = reads the scratchpad at (src + imm) & mask(aux); bit 6 = floating point (two 64-bit slots written back)
-//   dst slot / src slot index the register file: 0-7 r, 8-15 f (lo,hi), 16-23 e, 24-31 a;  src 32 = the immediate, 33 = zero
-enum : uint8_t { X_NOP, X_IADD_RS, X_IADD, X_ISUB, X_IMUL, X_IMULH, X_ISMULH, X_IXOR, X_IROR, X_IROL, X_INEG, X_ISWAP, X_IMUL_RCP,
-                 X_IMUL_RCP_SLOW, X_CBRANCH, X_CFROUND, X_ISTORE,
-                 X_FSWAP = 0x40, X_FADD, X_FSUB, X_FSCAL, X_FMUL, X_FDIV, X_FSQRT, X_MEM = 0x80 };
-constexpr u32 kSrcImm = 32, kSrcZero = 33;
+// Decoded instruction (8 bytes): word0 = op | aux << 8 | (src slot * 8) << 16 | (dst slot * 8) << 24, word1 = imm32.
+// Dense opcodes, one per (operation, operand kind), so each handler touches only what it needs; slot fields are byte
+// offsets into the register file in shared memory (slots: 0-7 r, 8-15 f lo/hi, 16-23 e lo/hi, 24-31 a lo/hi);
+// aux = shift / rotate count / reciprocal slot / log2 of the scratchpad level size.
+enum : uint8_t { W_NOP, W_IADD_RS, W_ISUB_R, W_IMUL_R, W_IMULH_R, W_ISMULH_R, W_IXOR_R, W_IROR_R, W_IROL_R, W_ISWAP,
+                 W_ISUB_I, W_IMUL_I, W_IXOR_I, W_IROR_I, W_IROL_I, W_INEG, W_IMUL_RCP, W_IMUL_RCP_SLOW,
+                 W_IADD_M, W_ISUB_M, W_IMUL_M, W_IMULH_M, W_ISMULH_M, W_IXOR_M,
+                 W_IADD_A, W_ISUB_A, W_IMUL_A, W_IMULH_A, W_ISMULH_A, W_IXOR_A,
+                 W_CBRANCH, W_CFROUND, W_ISTORE,
+                 W_FSWAP, W_FADD_R, W_FSUB_R, W_FSCAL, W_FMUL_R, W_FSQRT, W_FADD_M, W_FSUB_M, W_FDIV_M, W_COUNT };
+__device__ __forceinline__ u32 wpack(u32 op, u32 dslot, u32 sslot, u32 aux) { return op | (aux << 8) | ((sslot * 8) << 16) | ((dslot * 8) << 24); }
 constexpr u32 kL1Mask = (kScratchpadL1 - 1) & ~7u, kL2Mask = (kScratchpadL2 - 1) & ~7u, kL3Mask = (kScratchpadL3 - 1) & ~7u;
 constexpr u32 kL3Mask64 = (kScratchpadL3 - 1) & ~63u;
 constexpr u32 kDatasetAlignMask = (u32)((kDatasetBase - 1) & ~63ull);
@@ -260,9 +264,7 @@ __device__ u64 device_reciprocal(u32 divisor) {
     return q;
 }
 
-__device__ __forceinline__ u32 pack(u32 op, u32 dst, u32 src, u32 aux) { return op | (dst << 8) | (src << 16) | (aux << 24); }
-
-__global__ void __launch_bounds__(128) program_kernel(BatchBuffers b, u32 n, bool first_program, bool vm_major) {
+__global__ void __launch_bounds__(128) program_kernel(BatchBuffers b, u32 n, bool first_program) {
     __shared__ AesSmem sm;
     __shared__ uint8_t opmap[256];
     __shared__ short usage[8][128];     // CBRANCH targets: last instruction that wrote each integer register
@@ -316,55 +318,58 @@ __global__ void __launch_bounds__(128) program_kernel(BatchBuffers b, u32 n, boo
             const int i = chunk * 8 + j;
             const u32 lo = (u32)raw[j], imm = (u32)(raw[j] >> 32);
             const u32 type = opmap[lo & 255], dst = (lo >> 8) & 7, src = (lo >> 16) & 7, mod = lo >> 24;
-            const u32 lvl12 = (mod & 3) ? 0 : 1;    // mod.mem != 0 -> L1, else L2
-            u32 w0 = X_NOP, w1 = imm;
-            switch (type) {
-                case T_IADD_RS: w0 = pack(X_IADD_RS, dst, src, (mod >> 2) & 3); w1 = dst == 5 ? imm : 0; usage[dst][t] = (short)i; break;
-                case T_IADD_M: case T_ISUB_M: case T_IMUL_M: case T_IMULH_M: case T_ISMULH_M: case T_IXOR_M: {
-                    const u32 alu = type == T_IADD_M ? X_IADD : type == T_ISUB_M ? X_ISUB : type == T_IMUL_M ? X_IMUL : type == T_IMULH_M ? X_IMULH
-                                  : type == T_ISMULH_M ? X_ISMULH : X_IXOR;
-                    w0 = src != dst ? pack(alu | X_MEM, dst, src, lvl12) : pack(alu | X_MEM, dst, kSrcZero, 2);
-                    usage[dst][t] = (short)i;
-                } break;
-                case T_ISUB_R: case T_IMUL_R: case T_IXOR_R: {
-                    const u32 alu = type == T_ISUB_R ? X_ISUB : type == T_IMUL_R ? X_IMUL : X_IXOR;
-                    w0 = pack(alu, dst, src != dst ? src : kSrcImm, 0);
-                    usage[dst][t] = (short)i;
-                } break;
-                case T_IMULH_R: w0 = pack(X_IMULH, dst, src, 0); usage[dst][t] = (short)i; break;
-                case T_ISMULH_R: w0 = pack(X_ISMULH, dst, src, 0); usage[dst][t] = (short)i; break;
-                case T_IMUL_RCP:
-                    if (imm & (imm - 1)) {
-                        if (n_rcp < (u32)kRcpSlots) { b.rcp[vm_major ? (size_t)vm * kRcpSlots + n_rcp : (size_t)n_rcp * stride + vm] = device_reciprocal(imm); w0 = pack(X_IMUL_RCP, dst, 0, n_rcp); n_rcp++; }
-                        else w0 = pack(X_IMUL_RCP_SLOW, dst, 0, 0);
+            u32 w0 = W_NOP, w1 = imm;
+            {
+                const u32 bits12 = (mod & 3) ? 14 : 18;   // log2 of the level size: L1 16 KiB, L2 256 KiB (L3 2 MiB = 21)
+                switch (type) {
+                    case T_IADD_RS: w0 = wpack(W_IADD_RS, dst, src, (mod >> 2) & 3); w1 = dst == 5 ? imm : 0; usage[dst][t] = (short)i; break;
+                    case T_IADD_M: case T_ISUB_M: case T_IMUL_M: case T_IMULH_M: case T_ISMULH_M: case T_IXOR_M: {
+                        const u32 k = type == T_IADD_M ? 0 : type == T_ISUB_M ? 1 : type == T_IMUL_M ? 2 : type == T_IMULH_M ? 3 : type == T_ISMULH_M ? 4 : 5;
+                        if (src != dst) w0 = wpack(W_IADD_M + k, dst, src, bits12);
+                        else { w0 = wpack(W_IADD_A + k, dst, 0, 0); w1 = imm & kL3Mask; }       // constant address
                         usage[dst][t] = (short)i;
-                    }
-                    break;
-                case T_INEG_R: w0 = pack(X_INEG, dst, 0, 0); usage[dst][t] = (short)i; break;
-                case T_IROR_R: w0 = pack(X_IROR, dst, src != dst ? src : kSrcImm, 0); usage[dst][t] = (short)i; break;
-                case T_IROL_R: w0 = pack(X_IROL, dst, src != dst ? src : kSrcImm, 0); usage[dst][t] = (short)i; break;
-                case T_ISWAP_R: if (src != dst) { w0 = pack(X_ISWAP, dst, src, 0); usage[dst][t] = (short)i; usage[src][t] = (short)i; } break;
-                case T_FSWAP_R: w0 = pack(X_FSWAP, 8 + 2 * dst, 0, 0); break;               // dst 0-3 = f, 4-7 = e: slots 8.. and 16.. are contiguous
-                case T_FADD_R: w0 = pack(X_FADD, 8 + 2 * (dst & 3), 24 + 2 * (src & 3), 0); break;
-                case T_FADD_M: w0 = pack(X_FADD | X_MEM, 8 + 2 * (dst & 3), src, lvl12); break;
-                case T_FSUB_R: w0 = pack(X_FSUB, 8 + 2 * (dst & 3), 24 + 2 * (src & 3), 0); break;
-                case T_FSUB_M: w0 = pack(X_FSUB | X_MEM, 8 + 2 * (dst & 3), src, lvl12); break;
-                case T_FSCAL_R: w0 = pack(X_FSCAL, 8 + 2 * (dst & 3), 0, 0); break;
-                case T_FMUL_R: w0 = pack(X_FMUL, 16 + 2 * (dst & 3), 24 + 2 * (src & 3), 0); break;
-                case T_FDIV_M: w0 = pack(X_FDIV | X_MEM, 16 + 2 * (dst & 3), src, lvl12); break;
-                case T_FSQRT_R: w0 = pack(X_FSQRT, 16 + 2 * (dst & 3), 0, 0); break;
-                case T_CBRANCH: {
-                    const u32 shift = (mod >> 4) + 8;
-                    w0 = pack(X_CBRANCH, dst, (u32)(usage[dst][t] + 1), shift);      // target + 1 (0 = restart at instruction 0)
-                    w1 = (imm | (1u << shift)) & ~(1u << (shift - 1));               // both bits lie below bit 31: sign extension unaffected
+                    } break;
+                    case T_ISUB_R: case T_IMUL_R: case T_IXOR_R: {
+                        const u32 k = type == T_ISUB_R ? 0 : type == T_IMUL_R ? 1 : 2;
+                        w0 = src != dst ? wpack((k == 0 ? W_ISUB_R : k == 1 ? W_IMUL_R : W_IXOR_R), dst, src, 0)
+                                        : wpack((k == 0 ? W_ISUB_I : k == 1 ? W_IMUL_I : W_IXOR_I), dst, 0, 0);
+                        usage[dst][t] = (short)i;
+                    } break;
+                    case T_IMULH_R: w0 = wpack(W_IMULH_R, dst, src, 0); usage[dst][t] = (short)i; break;
+                    case T_ISMULH_R: w0 = wpack(W_ISMULH_R, dst, src, 0); usage[dst][t] = (short)i; break;
+                    case T_IMUL_RCP:
+                        if (imm & (imm - 1)) {
+                            if (n_rcp < (u32)kRcpSlots) { b.rcp[(size_t)vm * kRcpSlots + n_rcp] = device_reciprocal(imm); w0 = wpack(W_IMUL_RCP, dst, 0, n_rcp); n_rcp++; }
+                            else w0 = wpack(W_IMUL_RCP_SLOW, dst, 0, 0);
+                            usage[dst][t] = (short)i;
+                        }
+                        break;
+                    case T_INEG_R: w0 = wpack(W_INEG, dst, 0, 0); usage[dst][t] = (short)i; break;
+                    case T_IROR_R: w0 = src != dst ? wpack(W_IROR_R, dst, src, 0) : wpack(W_IROR_I, dst, 0, imm & 63); usage[dst][t] = (short)i; break;
+                    case T_IROL_R: w0 = src != dst ? wpack(W_IROL_R, dst, src, 0) : wpack(W_IROL_I, dst, 0, imm & 63); usage[dst][t] = (short)i; break;
+                    case T_ISWAP_R: if (src != dst) { w0 = wpack(W_ISWAP, dst, src, 0); usage[dst][t] = (short)i; usage[src][t] = (short)i; } break;
+                    case T_FSWAP_R: w0 = wpack(W_FSWAP, 8 + 2 * dst, 0, 0); break;
+                    case T_FADD_R: w0 = wpack(W_FADD_R, 8 + 2 * (dst & 3), 24 + 2 * (src & 3), 0); break;
+                    case T_FADD_M: w0 = wpack(W_FADD_M, 8 + 2 * (dst & 3), src, bits12); break;
+                    case T_FSUB_R: w0 = wpack(W_FSUB_R, 8 + 2 * (dst & 3), 24 + 2 * (src & 3), 0); break;
+                    case T_FSUB_M: w0 = wpack(W_FSUB_M, 8 + 2 * (dst & 3), src, bits12); break;
+                    case T_FSCAL_R: w0 = wpack(W_FSCAL, 8 + 2 * (dst & 3), 0, 0); break;
+                    case T_FMUL_R: w0 = wpack(W_FMUL_R, 16 + 2 * (dst & 3), 24 + 2 * (src & 3), 0); break;
+                    case T_FDIV_M: w0 = wpack(W_FDIV_M, 16 + 2 * (dst & 3), src, bits12); break;
+                    case T_FSQRT_R: w0 = wpack(W_FSQRT, 16 + 2 * (dst & 3), 0, 0); break;
+                    case T_CBRANCH: {
+                        const u32 shift = (mod >> 4) + 8;
+                        w0 = W_CBRANCH | (shift << 8) | ((u32)(usage[dst][t] + 1) << 16) | ((dst * 8) << 24);   // src field = target + 1 (not scaled)
+                        w1 = (imm | (1u << shift)) & ~(1u << (shift - 1));
 #pragma unroll
-                    for (int r = 0; r < 8; r++) usage[r][t] = (short)i;
-                } break;
-                case T_CFROUND: w0 = pack(X_CFROUND, 0, src, imm & 63); break;
-                case T_ISTORE: w0 = pack(X_ISTORE, dst, src, (mod >> 4) < 14 ? lvl12 : 2); break;
-                default: break;
+                        for (int r = 0; r < 8; r++) usage[r][t] = (short)i;
+                    } break;
+                    case T_CFROUND: w0 = wpack(W_CFROUND, 0, src, imm & 63); break;
+                    case T_ISTORE: w0 = wpack(W_ISTORE, dst, src, (mod >> 4) < 14 ? bits12 : 21); break;
+                    default: break;
+                }
+                b.program[(size_t)vm * kProgramSize + i] = make_uint2(w0, w1);
             }
-            b.program[vm_major ? (size_t)vm * kProgramSize + i : (size_t)i * stride + vm] = make_uint2(w0, w1);
         }
     }
 }
@@ -406,165 +411,35 @@ __device__ __forceinline__ double sqrt_rm(double a, u32 mode) {
 __device__ __forceinline__ u64 d2u(double v) { return (u64)__double_as_longlong(v); }
 __device__ __forceinline__ double u2d(u64 v) { return __longlong_as_double((long long)v); }
 
-template <int BS>
-__global__ void __launch_bounds__(BS) execute_kernel(BatchBuffers b, u32 n, const uint8_t *__restrict__ dataset) {
-    extern __shared__ u64 sm[];                  // [32][BS]: slot s of this thread's VM at sm[s * BS + tid]
-    const u32 tid = threadIdx.x, vm = blockIdx.x * BS + tid;
+// ---------------------------------------------------------------------------------------------- the VM: one WARP per VM
+// All 32 lanes run the same VM, so the interpreter never diverges: a step costs its own latency, not the worst latency
+// among 32 unrelated programs, and a hash takes ~1 s instead of ~9 s (the verifier's pow check needs that) in 1/8 of
+// the memory.  Measured alternatives (profiles/r02_k2pow_variants.md): one THREAD per VM (register files in shared
+// memory, switch diverging over 32 programs) 4.2 kH/s at 256 VMs/SM = 74 GB of scratchpads and 9 s per batch, flat
+// beyond that; a first warp-per-VM kernel with the register file spread over the lanes (operands by shuffle) issued
+// 59 SASS instructions per VM instruction and stopped at 3.3 kH/s.  This kernel: the register file lives in shared
+// memory (one LDS.64 per operand instead of two shuffles and a convergence check), slot fields of the instruction
+// word are byte offsets, opcodes are dense with one opcode per (operation, operand kind) so a handler touches only
+// what it needs, and every lane executes the whole instruction redundantly (both halves of an FP register too): no
+// cross-lane dependency inside the program loop, no warp synchronisation; the lanes split up only for the 64-byte
+// scratchpad / dataset lines around it.  39 SASS instructions per VM instruction (ncu), issue-bound.
+template <int WARPS, int MIN_CTAS>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) execute_kernel(BatchBuffers b, u32 n, const uint8_t *__restrict__ dataset) {
+    __shared__ uint2 prog_all[WARPS][kProgramSize];
+    __shared__ u64 rcp_all[WARPS][kRcpSlots];
+    __shared__ u64 regs_all[WARPS][32];
+    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, vm = blockIdx.x * WARPS + wid;
     if (vm >= n) return;
+    uint2 *prog = prog_all[wid];
+    u64 *rcp = rcp_all[wid], *regs = regs_all[wid];
+    for (int i = lane; i < kProgramSize; i += 32) prog[i] = b.program[(size_t)vm * kProgramSize + i];
+    rcp[lane] = b.rcp[(size_t)vm * kRcpSlots + lane];
     const u32 stride = b.stride;
-#define REG(s) sm[(s) * BS + tid]
-#pragma unroll
-    for (int i = 0; i < 8; i++) REG(i) = 0;
-#pragma unroll
-    for (int i = 24; i < 32; i++) REG(i) = b.regfile[(size_t)i * stride + vm];
+    regs[lane] = lane >= 24 ? b.regfile[(size_t)lane * stride + vm] : 0;
+    __syncwarp();
     const u64 c0 = b.config[vm], c1 = b.config[(size_t)stride + vm];
     const u64 emask_lo = b.config[(size_t)2 * stride + vm], emask_hi = b.config[(size_t)3 * stride + vm];
-    u32 ma = (u32)c0, mx = (u32)(c0 >> 32);
-    const u32 rr = (u32)(c1 >> 60);
-    const u32 rr0 = rr & 1, rr1 = 2 + ((rr >> 1) & 1), rr2 = 4 + ((rr >> 2) & 1), rr3 = 6 + ((rr >> 3) & 1);
-    const uint8_t *ds = dataset + (c1 & ((1ull << 60) - 1));
-    u32 mode = b.fprc[vm];
-    uint8_t *sp = b.scratchpads + (size_t)vm * kScratchpadL3;
-    const uint2 *prog = b.program + vm;
-    const u64 *rcp = b.rcp + vm;
-    constexpr u64 kEMant = (1ull << 56) - 1;
-
-    u32 sp0 = mx, sp1 = ma;
-    for (int it = 0; it < kProgramIterations; it++) {
-        const u64 mix = REG(rr0) ^ REG(rr1);
-        sp0 = (sp0 ^ (u32)mix) & kL3Mask64;
-        sp1 = (sp1 ^ (u32)(mix >> 32)) & kL3Mask64;
-        {
-            const ulonglong2 *p0 = reinterpret_cast<const ulonglong2 *>(sp + sp0);
-            const int4 *p1 = reinterpret_cast<const int4 *>(sp + sp1);
-            const ulonglong2 a0 = p0[0], a1 = p0[1], a2 = p0[2], a3 = p0[3];
-            const int4 f01 = p1[0], f23 = p1[1], e01 = p1[2], e23 = p1[3];
-            REG(0) ^= a0.x; REG(1) ^= a0.y; REG(2) ^= a1.x; REG(3) ^= a1.y; REG(4) ^= a2.x; REG(5) ^= a2.y; REG(6) ^= a3.x; REG(7) ^= a3.y;
-            REG(8) = d2u((double)f01.x);  REG(9) = d2u((double)f01.y);  REG(10) = d2u((double)f01.z); REG(11) = d2u((double)f01.w);
-            REG(12) = d2u((double)f23.x); REG(13) = d2u((double)f23.y); REG(14) = d2u((double)f23.z); REG(15) = d2u((double)f23.w);
-            REG(16) = (d2u((double)e01.x) & kEMant) | emask_lo; REG(17) = (d2u((double)e01.y) & kEMant) | emask_hi;
-            REG(18) = (d2u((double)e01.z) & kEMant) | emask_lo; REG(19) = (d2u((double)e01.w) & kEMant) | emask_hi;
-            REG(20) = (d2u((double)e23.x) & kEMant) | emask_lo; REG(21) = (d2u((double)e23.y) & kEMant) | emask_hi;
-            REG(22) = (d2u((double)e23.z) & kEMant) | emask_lo; REG(23) = (d2u((double)e23.w) & kEMant) | emask_hi;
-        }
-
-        uint2 ins = prog[0];
-        for (int pc = 0; pc < kProgramSize; pc++) {
-            const uint2 cur = ins;
-            if (pc + 1 < kProgramSize) ins = prog[(size_t)(pc + 1) * stride];     // fetched under this instruction's work
-            const u32 op = cur.x & 255, dslot = (cur.x >> 8) & 255, src = (cur.x >> 16) & 255, aux = cur.x >> 24;
-            const u64 simm = sext(cur.y);
-            // common operand fetch
-            const u64 d0 = REG(dslot), d1 = REG(dslot + 1);
-            const u32 sidx = src & 31;
-            u64 s0 = REG(sidx);
-            const u64 s1 = REG(sidx | 1);           // a-register high lane for FADD_R / FSUB_R / FMUL_R (src slot is even there)
-            s0 = src < 32 ? s0 : (src == kSrcImm ? simm : 0);
-            u64 v = s0;
-            if (op & X_MEM) {                       // the one scratchpad read of the instruction set
-                const u32 mask = aux == 0 ? kL1Mask : (aux == 1 ? kL2Mask : kL3Mask);
-                v = *reinterpret_cast<const u64 *>(sp + ((u32)(s0 + simm) & mask));
-            }
-            u64 r0 = d0, r1 = d1;
-            switch (op & 0x7f) {
-                case X_NOP: break;
-                case X_IADD_RS: r0 = d0 + (s0 << aux) + simm; break;
-                case X_IADD: r0 = d0 + v; break;
-                case X_ISUB: r0 = d0 - v; break;
-                case X_IMUL: r0 = d0 * v; break;
-                case X_IMULH: r0 = mulh_u(d0, v); break;
-                case X_ISMULH: r0 = mulh_s(d0, v); break;
-                case X_IXOR: r0 = d0 ^ v; break;
-                case X_IROR: { const u32 c = (u32)v & 63; r0 = (d0 >> c) | (d0 << ((64 - c) & 63)); } break;
-                case X_IROL: { const u32 c = (u32)v & 63; r0 = (d0 << c) | (d0 >> ((64 - c) & 63)); } break;
-                case X_INEG: r0 = 0 - d0; break;
-                case X_ISWAP: r0 = s0; REG(sidx) = d0; break;
-                case X_IMUL_RCP: r0 = d0 * rcp[(size_t)aux * stride]; break;
-                case X_IMUL_RCP_SLOW: r0 = d0 * device_reciprocal(cur.y); break;
-                case X_CBRANCH:
-                    r0 = d0 + simm;
-                    if ((r0 & (255ull << aux)) == 0) { pc = (int)src - 1; ins = prog[(size_t)src * stride]; }   // src = target + 1: the loop's pc++ lands there
-                    break;
-                case X_CFROUND: { const u32 c = aux; mode = (u32)((s0 >> c) | (s0 << ((64 - c) & 63))) & 3; } break;
-                case X_ISTORE: {
-                    const u32 mask = aux == 0 ? kL1Mask : (aux == 1 ? kL2Mask : kL3Mask);
-                    *reinterpret_cast<u64 *>(sp + ((u32)(d0 + simm) & mask)) = s0;
-                } break;
-                case X_FSWAP: r0 = d1; r1 = d0; break;
-                case X_FADD: case X_FSUB: {
-                    double lo, hi;
-                    if (op & X_MEM) { lo = (double)(int)(u32)v; hi = (double)(int)(u32)(v >> 32); }
-                    else { lo = u2d(s0); hi = u2d(s1); }
-                    if ((op & 0x7f) == X_FSUB) { lo = -lo; hi = -hi; }
-                    r0 = d2u(add_rm(u2d(d0), lo, mode)); r1 = d2u(add_rm(u2d(d1), hi, mode));
-                } break;
-                case X_FSCAL: r0 = d0 ^ 0x80F0000000000000ull; r1 = d1 ^ 0x80F0000000000000ull; break;
-                case X_FMUL: r0 = d2u(mul_rm(u2d(d0), u2d(s0), mode)); r1 = d2u(mul_rm(u2d(d1), u2d(s1), mode)); break;
-                case X_FDIV: {
-                    const u64 lo = (d2u((double)(int)(u32)v) & kEMant) | emask_lo, hi = (d2u((double)(int)(u32)(v >> 32)) & kEMant) | emask_hi;
-                    r0 = d2u(div_rm(u2d(d0), u2d(lo), mode)); r1 = d2u(div_rm(u2d(d1), u2d(hi), mode));
-                } break;
-                case X_FSQRT: r0 = d2u(sqrt_rm(u2d(d0), mode)); r1 = d2u(sqrt_rm(u2d(d1), mode)); break;
-                default: break;
-            }
-            REG(dslot) = r0;
-            if (op & 0x40) REG(dslot + 1) = r1;
-        }
-
-        mx = (mx ^ (u32)(REG(rr2) ^ REG(rr3))) & kDatasetAlignMask;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(ds + mx));     // the line the NEXT iteration reads
-        {
-            const ulonglong2 *line = reinterpret_cast<const ulonglong2 *>(ds + ma);
-            const ulonglong2 l0 = __ldg(line), l1 = __ldg(line + 1), l2 = __ldg(line + 2), l3 = __ldg(line + 3);
-            const u64 n0 = REG(0) ^ l0.x, n1 = REG(1) ^ l0.y, n2 = REG(2) ^ l1.x, n3 = REG(3) ^ l1.y;
-            const u64 n4 = REG(4) ^ l2.x, n5 = REG(5) ^ l2.y, n6 = REG(6) ^ l3.x, n7 = REG(7) ^ l3.y;
-            REG(0) = n0; REG(1) = n1; REG(2) = n2; REG(3) = n3; REG(4) = n4; REG(5) = n5; REG(6) = n6; REG(7) = n7;
-            ulonglong2 *o1 = reinterpret_cast<ulonglong2 *>(sp + sp1);
-            o1[0] = make_ulonglong2(n0, n1); o1[1] = make_ulonglong2(n2, n3); o1[2] = make_ulonglong2(n4, n5); o1[3] = make_ulonglong2(n6, n7);
-        }
-        { const u32 tmp = mx; mx = ma; ma = tmp; }
-        {
-            ulonglong2 *o0 = reinterpret_cast<ulonglong2 *>(sp + sp0);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const u64 lo = REG(8 + 2 * i) ^ REG(16 + 2 * i), hi = REG(9 + 2 * i) ^ REG(17 + 2 * i);
-                REG(8 + 2 * i) = lo; REG(9 + 2 * i) = hi;
-                o0[i] = make_ulonglong2(lo, hi);
-            }
-        }
-        sp0 = 0; sp1 = 0;
-    }
-#pragma unroll
-    for (int i = 0; i < 24; i++) b.regfile[(size_t)i * stride + vm] = REG(i);
-    b.fprc[vm] = (uint8_t)mode;
-#undef REG
-}
-
-// ---------------------------------------------------------------------------------------------- the VM, one warp per VM
-// All 32 lanes run the same VM, so the interpreter never diverges: the branch on the opcode is warp-uniform and a step
-// costs its own latency, not the worst latency among 32 unrelated programs.  The register file IS the warp: lane l
-// holds slot l (r0-7 | f0-3 lo,hi | e0-3 lo,hi | a0-3 lo,hi), an operand is one shuffle, the two halves of an FP
-// register are processed by their two lanes at once, and the 64-byte scratchpad / dataset lines of the loop prologue
-// and epilogue are single coalesced accesses by lanes 0-7 / 8-15 / 16-23.  The decoded program (2 KiB) and the
-// reciprocals (256 B) sit in shared memory.  A batch is SMs x warps-per-SM VMs: ~10 GB of scratchpads instead of
-// ~150 GB, and a hash takes a fraction of a second instead of many seconds (the verifier's pow check needs that).
-constexpr unsigned kFull = 0xffffffffu;
-__device__ __forceinline__ u64 shfl64(u64 v, int src) { return __shfl_sync(kFull, (unsigned long long)v, src); }
-
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) execute_warp_kernel(BatchBuffers b, u32 n, const uint8_t *__restrict__ dataset) {
-    extern __shared__ uint2 wsm[];               // per warp: 256 instructions + kRcpSlots reciprocals
-    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, vm = blockIdx.x * WARPS + warp;
-    if (vm >= n) return;                         // whole warp leaves together
-    uint2 *prog = wsm + warp * (kProgramSize + kRcpSlots);
-    const u64 *rcp = reinterpret_cast<const u64 *>(prog + kProgramSize);
-    for (int i = lane; i < kProgramSize; i += 32) prog[i] = b.program[(size_t)vm * kProgramSize + i];
-    reinterpret_cast<u64 *>(prog + kProgramSize)[lane] = b.rcp[(size_t)vm * kRcpSlots + lane];
-    __syncwarp();
-    const u32 stride = b.stride;
-    u64 reg = lane >= 24 ? b.regfile[(size_t)lane * stride + vm] : 0;
-    const u64 c0 = b.config[vm], c1 = b.config[(size_t)stride + vm];
-    const u64 emask = b.config[(size_t)(2 + (lane & 1)) * stride + vm];      // lo for even lanes, hi for odd ones
+    const u64 emask_lane = (lane & 1) ? emask_hi : emask_lo;
     u32 ma = (u32)c0, mx = (u32)(c0 >> 32);
     const u32 rr = (u32)(c1 >> 60);
     const int rr0 = rr & 1, rr1 = 2 + ((rr >> 1) & 1), rr2 = 4 + ((rr >> 2) & 1), rr3 = 6 + ((rr >> 3) & 1);
@@ -572,104 +447,111 @@ __global__ void __launch_bounds__(WARPS * 32) execute_warp_kernel(BatchBuffers b
     u32 mode = b.fprc[vm];
     uint8_t *sp = b.scratchpads + (size_t)vm * kScratchpadL3;
     constexpr u64 kEMant = (1ull << 56) - 1;
-    const bool is_r = lane < 8, is_f = lane >= 8 && lane < 16, is_e = lane >= 16 && lane < 24;
+    const uint8_t *rb = reinterpret_cast<const uint8_t *>(regs);
+#define RD(off) (*reinterpret_cast<const u64 *>(rb + (off)))
+#define WR(off, v) (*reinterpret_cast<u64 *>(const_cast<uint8_t *>(rb) + (off)) = (v))
+#define SPAD(addr) (*reinterpret_cast<u64 *>(sp + (addr)))
 
     u32 sp0 = mx, sp1 = ma;
     for (int it = 0; it < kProgramIterations; it++) {
-        const u64 mix = shfl64(reg, rr0) ^ shfl64(reg, rr1);
+        const u64 mix = regs[rr0] ^ regs[rr1];
         sp0 = (sp0 ^ (u32)mix) & kL3Mask64;
         sp1 = (sp1 ^ (u32)(mix >> 32)) & kL3Mask64;
-        if (is_r) reg ^= *reinterpret_cast<const u64 *>(sp + sp0 + 8 * lane);
+        __syncwarp();                                    // everyone has read `mix` before lanes overwrite their slots
+        if (lane < 8) regs[lane] ^= SPAD(sp0 + 8 * lane);
         else if (lane < 24) {
-            const int x = *reinterpret_cast<const int *>(sp + sp1 + 4 * (lane - 8));     // f: bytes 0-31, e: bytes 32-63 of the line
+            const int x = *reinterpret_cast<const int *>(sp + sp1 + 4 * (lane - 8));
             const u64 bits = d2u((double)x);
-            reg = is_e ? ((bits & kEMant) | emask) : bits;
+            regs[lane] = lane >= 16 ? ((bits & kEMant) | emask_lane) : bits;
         }
+        __syncwarp();
 
         for (int pc = 0; pc < kProgramSize; pc++) {
             const uint2 ins = prog[pc];
-            const u32 op = ins.x & 255, dslot = (ins.x >> 8) & 255, src = (ins.x >> 16) & 255, aux = ins.x >> 24;
+            const u32 w = ins.x;
+            const u32 doff = w >> 24, soff = (w >> 16) & 255, aux = (w >> 8) & 255;
             const u64 simm = sext(ins.y);
-            if (op < 0x40 || (op & X_MEM)) {
-                // integer instruction, or an FP one with a memory operand: d = r[dst], s = r[src] | imm | 0
-                u64 s0 = shfl64(reg, (int)(src & 31));
-                s0 = src < 32 ? s0 : (src == kSrcImm ? simm : 0);
-                u64 v = s0;
-                if (op & X_MEM) {
-                    const u32 mask = aux == 0 ? kL1Mask : (aux == 1 ? kL2Mask : kL3Mask);
-                    v = *reinterpret_cast<const u64 *>(sp + ((u32)(s0 + simm) & mask));    // same address in every lane: one broadcast
-                }
-                if (op & 0x40) {        // FADD_M / FSUB_M / FDIV_M: each of the two destination lanes takes its int32 half
-                    const double m = (double)(int)(u32)((lane & 1) ? (v >> 32) : v);
-                    if ((lane & ~1u) == dslot) {
-                        const u32 k = op & 0x3f;
-                        if (k == (X_FDIV & 0x3f)) reg = d2u(div_rm(u2d(reg), u2d((d2u(m) & kEMant) | emask), mode));
-                        else reg = d2u(add_rm(u2d(reg), k == (X_FSUB & 0x3f) ? -m : m, mode));
-                    }
-                    continue;
-                }
-                const u64 d0 = shfl64(reg, (int)dslot);
-                u64 r0 = d0;
-                switch (op & 0x3f) {
-                    case X_IADD_RS: r0 = d0 + (s0 << aux) + simm; break;
-                    case X_IADD: r0 = d0 + v; break;
-                    case X_ISUB: r0 = d0 - v; break;
-                    case X_IMUL: r0 = d0 * v; break;
-                    case X_IMULH: r0 = mulh_u(d0, v); break;
-                    case X_ISMULH: r0 = mulh_s(d0, v); break;
-                    case X_IXOR: r0 = d0 ^ v; break;
-                    case X_IROR: { const u32 c = (u32)v & 63; r0 = (d0 >> c) | (d0 << ((64 - c) & 63)); } break;
-                    case X_IROL: { const u32 c = (u32)v & 63; r0 = (d0 << c) | (d0 >> ((64 - c) & 63)); } break;
-                    case X_INEG: r0 = 0 - d0; break;
-                    case X_ISWAP: r0 = s0; if (lane == src) reg = d0; break;
-                    case X_IMUL_RCP: r0 = d0 * rcp[aux]; break;
-                    case X_IMUL_RCP_SLOW: r0 = d0 * device_reciprocal(ins.y); break;
-                    case X_CBRANCH:
-                        r0 = d0 + simm;
-                        if ((r0 & (255ull << aux)) == 0) pc = (int)src - 1;      // src = target + 1
-                        break;
-                    case X_CFROUND: mode = (u32)((s0 >> aux) | (s0 << ((64 - aux) & 63))) & 3; break;
-                    case X_ISTORE: {
-                        const u32 mask = aux == 0 ? kL1Mask : (aux == 1 ? kL2Mask : kL3Mask);
-                        if (lane == 0) *reinterpret_cast<u64 *>(sp + ((u32)(d0 + simm) & mask)) = s0;
-                        __syncwarp();                                             // orders the store before later loads of other lanes
-                    } break;
-                    default: break;
-                }
-                if (lane == dslot) reg = r0;
-            } else {
-                // register-only FP instruction: the two lanes of the destination work on their halves
-                const bool mine = (lane & ~1u) == dslot;
-                switch (op) {
-                    case X_FSWAP: { const u64 o = __shfl_xor_sync(kFull, (unsigned long long)reg, 1); if (mine) reg = o; } break;
-                    case X_FADD: { const u64 a = shfl64(reg, (int)(src | (lane & 1))); if (mine) reg = d2u(add_rm(u2d(reg), u2d(a), mode)); } break;
-                    case X_FSUB: { const u64 a = shfl64(reg, (int)(src | (lane & 1))); if (mine) reg = d2u(add_rm(u2d(reg), -u2d(a), mode)); } break;
-                    case X_FSCAL: if (mine) reg ^= 0x80F0000000000000ull; break;
-                    case X_FMUL: { const u64 a = shfl64(reg, (int)(src | (lane & 1))); if (mine) reg = d2u(mul_rm(u2d(reg), u2d(a), mode)); } break;
-                    case X_FSQRT: if (mine) reg = d2u(sqrt_rm(u2d(reg), mode)); break;
-                    default: break;
-                }
+#define MEMADDR ((u32)(RD(soff) + simm) & ((1u << aux) - 8u))
+#define FP_M(lo, hi) const u64 mv_ = SPAD(MEMADDR); const double lo = (double)(int)(u32)mv_, hi = (double)(int)(u32)(mv_ >> 32)
+            switch (w & 255) {
+                case W_IADD_RS: WR(doff, RD(doff) + (RD(soff) << aux) + simm); break;
+                case W_ISUB_R: WR(doff, RD(doff) - RD(soff)); break;
+                case W_IMUL_R: WR(doff, RD(doff) * RD(soff)); break;
+                case W_IMULH_R: WR(doff, mulh_u(RD(doff), RD(soff))); break;
+                case W_ISMULH_R: WR(doff, mulh_s(RD(doff), RD(soff))); break;
+                case W_IXOR_R: WR(doff, RD(doff) ^ RD(soff)); break;
+                case W_IROR_R: { const u64 d = RD(doff); const u32 c = (u32)RD(soff) & 63; WR(doff, (d >> c) | (d << ((64 - c) & 63))); } break;
+                case W_IROL_R: { const u64 d = RD(doff); const u32 c = (u32)RD(soff) & 63; WR(doff, (d << c) | (d >> ((64 - c) & 63))); } break;
+                case W_ISWAP: { const u64 d = RD(doff), s = RD(soff); WR(doff, s); WR(soff, d); } break;
+                case W_ISUB_I: WR(doff, RD(doff) - simm); break;
+                case W_IMUL_I: WR(doff, RD(doff) * simm); break;
+                case W_IXOR_I: WR(doff, RD(doff) ^ simm); break;
+                case W_IROR_I: { const u64 d = RD(doff); WR(doff, (d >> aux) | (d << ((64 - aux) & 63))); } break;
+                case W_IROL_I: { const u64 d = RD(doff); WR(doff, (d << aux) | (d >> ((64 - aux) & 63))); } break;
+                case W_INEG: WR(doff, 0 - RD(doff)); break;
+                case W_IMUL_RCP: WR(doff, RD(doff) * rcp[aux]); break;
+                case W_IMUL_RCP_SLOW: WR(doff, RD(doff) * device_reciprocal(ins.y)); break;
+                case W_IADD_M: WR(doff, RD(doff) + SPAD(MEMADDR)); break;
+                case W_ISUB_M: WR(doff, RD(doff) - SPAD(MEMADDR)); break;
+                case W_IMUL_M: WR(doff, RD(doff) * SPAD(MEMADDR)); break;
+                case W_IMULH_M: WR(doff, mulh_u(RD(doff), SPAD(MEMADDR))); break;
+                case W_ISMULH_M: WR(doff, mulh_s(RD(doff), SPAD(MEMADDR))); break;
+                case W_IXOR_M: WR(doff, RD(doff) ^ SPAD(MEMADDR)); break;
+                case W_IADD_A: WR(doff, RD(doff) + SPAD(ins.y)); break;
+                case W_ISUB_A: WR(doff, RD(doff) - SPAD(ins.y)); break;
+                case W_IMUL_A: WR(doff, RD(doff) * SPAD(ins.y)); break;
+                case W_IMULH_A: WR(doff, mulh_u(RD(doff), SPAD(ins.y))); break;
+                case W_ISMULH_A: WR(doff, mulh_s(RD(doff), SPAD(ins.y))); break;
+                case W_IXOR_A: WR(doff, RD(doff) ^ SPAD(ins.y)); break;
+                case W_CBRANCH: {
+                    const u64 r0 = RD(doff) + simm;
+                    WR(doff, r0);
+                    if ((r0 & (255ull << aux)) == 0) pc = (int)soff - 1;       // soff field = target + 1
+                } break;
+                case W_CFROUND: { const u64 s = RD(soff); mode = (u32)((s >> aux) | (s << ((64 - aux) & 63))) & 3; } break;
+                case W_ISTORE: SPAD((u32)(RD(doff) + simm) & ((1u << aux) - 8u)) = RD(soff); break;
+                case W_FSWAP: { const u64 lo = RD(doff), hi = RD(doff + 8); WR(doff, hi); WR(doff + 8, lo); } break;
+                case W_FADD_R: { const double lo = add_rm(u2d(RD(doff)), u2d(RD(soff)), mode), hi = add_rm(u2d(RD(doff + 8)), u2d(RD(soff + 8)), mode);
+                                 WR(doff, d2u(lo)); WR(doff + 8, d2u(hi)); } break;
+                case W_FSUB_R: { const double lo = add_rm(u2d(RD(doff)), -u2d(RD(soff)), mode), hi = add_rm(u2d(RD(doff + 8)), -u2d(RD(soff + 8)), mode);
+                                 WR(doff, d2u(lo)); WR(doff + 8, d2u(hi)); } break;
+                case W_FSCAL: WR(doff, RD(doff) ^ 0x80F0000000000000ull); WR(doff + 8, RD(doff + 8) ^ 0x80F0000000000000ull); break;
+                case W_FMUL_R: { const double lo = mul_rm(u2d(RD(doff)), u2d(RD(soff)), mode), hi = mul_rm(u2d(RD(doff + 8)), u2d(RD(soff + 8)), mode);
+                                 WR(doff, d2u(lo)); WR(doff + 8, d2u(hi)); } break;
+                case W_FSQRT: { const double lo = sqrt_rm(u2d(RD(doff)), mode), hi = sqrt_rm(u2d(RD(doff + 8)), mode); WR(doff, d2u(lo)); WR(doff + 8, d2u(hi)); } break;
+                case W_FADD_M: { FP_M(mlo, mhi); WR(doff, d2u(add_rm(u2d(RD(doff)), mlo, mode))); WR(doff + 8, d2u(add_rm(u2d(RD(doff + 8)), mhi, mode))); } break;
+                case W_FSUB_M: { FP_M(mlo, mhi); WR(doff, d2u(add_rm(u2d(RD(doff)), -mlo, mode))); WR(doff + 8, d2u(add_rm(u2d(RD(doff + 8)), -mhi, mode))); } break;
+                case W_FDIV_M: { FP_M(mlo, mhi);
+                                 const double dlo = u2d((d2u(mlo) & kEMant) | emask_lo), dhi = u2d((d2u(mhi) & kEMant) | emask_hi);
+                                 WR(doff, d2u(div_rm(u2d(RD(doff)), dlo, mode))); WR(doff + 8, d2u(div_rm(u2d(RD(doff + 8)), dhi, mode))); } break;
+                default: break;
             }
+#undef MEMADDR
+#undef FP_M
         }
 
-        mx = (mx ^ (u32)(shfl64(reg, rr2) ^ shfl64(reg, rr3))) & kDatasetAlignMask;
+        mx = (mx ^ (u32)(regs[rr2] ^ regs[rr3])) & kDatasetAlignMask;
         if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(ds + mx));
-        if (is_r) {
-            reg ^= __ldg(reinterpret_cast<const u64 *>(ds + ma) + lane);
-            *reinterpret_cast<u64 *>(sp + sp1 + 8 * lane) = reg;
+        __syncwarp();                                    // program-loop writes (all lanes, same values) settle before the lanes split
+        if (lane < 8) {
+            const u64 v = regs[lane] ^ __ldg(reinterpret_cast<const u64 *>(ds + ma) + lane);
+            regs[lane] = v;
+            SPAD(sp1 + 8 * lane) = v;
+        } else if (lane < 16) {
+            const u64 v = regs[lane] ^ regs[lane + 8];
+            regs[lane] = v;                              // f ^= e; written after the r line: the two may share a scratchpad line
         }
         { const u32 tmp = mx; mx = ma; ma = tmp; }
-        const u64 e_of_f = __shfl_down_sync(kFull, (unsigned long long)reg, 8);   // lane 8+k receives e's slot 16+k
-        __syncwarp();                                                              // r stored before f (they may share a line)
-        if (is_f) {
-            reg ^= e_of_f;
-            *reinterpret_cast<u64 *>(sp + sp0 + 8 * (lane - 8)) = reg;
-        }
+        __syncwarp();
+        if (lane >= 8 && lane < 16) SPAD(sp0 + 8 * (lane - 8)) = regs[lane];
         __syncwarp();
         sp0 = 0; sp1 = 0;
     }
-    if (lane < 24) b.regfile[(size_t)lane * stride + vm] = reg;
+    if (lane < 24) b.regfile[(size_t)lane * stride + vm] = regs[lane];
     if (lane == 0) b.fprc[vm] = (uint8_t)mode;
+#undef RD
+#undef WR
+#undef SPAD
 }
 
 // ---------------------------------------------------------------------------------------------- chain seed / final hash
@@ -760,26 +642,17 @@ cudaError_t launch_fill_scratchpads(const BatchBuffers &b, uint32_t n, cudaStrea
     fill_kernel<<<blocks_for((u64)n * 4, 256), 256, 0, s>>>(reinterpret_cast<u64 *>(b.seed), b.stride, n, b.scratchpads);
     return cudaGetLastError();
 }
-cudaError_t launch_program(const BatchBuffers &b, uint32_t n, bool first_program, bool vm_major, cudaStream_t s) {
-    program_kernel<<<blocks_for(n, 128), 128, 0, s>>>(b, n, first_program, vm_major);
+cudaError_t launch_program(const BatchBuffers &b, uint32_t n, bool first_program, cudaStream_t s) {
+    program_kernel<<<blocks_for(n, 128), 128, 0, s>>>(b, n, first_program);
     return cudaGetLastError();
 }
-int execute_max_ctas_per_sm() {
-    int ctas = 0;
-    cudaFuncSetAttribute(execute_kernel<kExecThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kExecThreads * 8);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, execute_kernel<kExecThreads>, kExecThreads, 32 * kExecThreads * 8) != cudaSuccess) return 0;
-    return ctas;
-}
-cudaError_t launch_execute(const BatchBuffers &b, uint32_t n, const uint64_t *d_dataset, cudaStream_t s) {
-    constexpr size_t smem = 32 * kExecThreads * 8;
-    cudaError_t e = cudaFuncSetAttribute(execute_kernel<kExecThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    execute_kernel<kExecThreads><<<blocks_for(n, kExecThreads), kExecThreads, smem, s>>>(b, n, reinterpret_cast<const uint8_t *>(d_dataset));
-    return cudaGetLastError();
-}
-cudaError_t launch_execute_warp(const BatchBuffers &b, uint32_t n, const uint64_t *d_dataset, cudaStream_t s) {
-    constexpr size_t smem = (size_t)kWarpsPerCta * (kProgramSize + kRcpSlots) * sizeof(uint2);
-    execute_warp_kernel<kWarpsPerCta><<<blocks_for(n, kWarpsPerCta), kWarpsPerCta * 32, smem, s>>>(b, n, reinterpret_cast<const uint8_t *>(d_dataset));
+cudaError_t launch_execute(const BatchBuffers &b, uint32_t n, const uint64_t *d_dataset, int variant, cudaStream_t s) {
+    const uint8_t *ds = reinterpret_cast<const uint8_t *>(d_dataset);
+    switch (variant) {
+        case 1: execute_kernel<2, 24><<<blocks_for(n, 2), 64, 0, s>>>(b, n, ds); break;    // <= 42 registers: 48 warps per SM
+        case 2: execute_kernel<2, 32><<<blocks_for(n, 2), 64, 0, s>>>(b, n, ds); break;    // <= 32 registers: 64 warps per SM
+        default: execute_kernel<1, 32><<<n, 32, 0, s>>>(b, n, ds); break;                  // <= 64 registers: 32 warps per SM
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_chain_seed(const BatchBuffers &b, uint32_t n, cudaStream_t s) {

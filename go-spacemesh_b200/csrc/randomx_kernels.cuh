@@ -9,17 +9,15 @@
 namespace b200post {
 namespace rx {
 
-constexpr int kExecThreads = 128;          // VMs per CTA of the VM kernel (register files live in its shared memory)
-constexpr int kWarpsPerCta = 4;             // warp-per-VM kernel: VMs per CTA
 constexpr int kRcpSlots = 32;              // resolved IMUL_RCP reciprocals kept per VM and program
 
-// Device-resident state of one batch of VMs.  All per-VM arrays are [field][vm] (field-major) so that a warp of 32
-// consecutive VMs touches consecutive addresses; `stride` = capacity rounded up to 32.
+// Device-resident state of one batch of VMs.  The small per-VM arrays are [field][vm] (field-major: the thread-per-VM
+// helper kernels touch consecutive addresses); program and reciprocals are VM-major (one warp copies them to shared memory).
 struct BatchBuffers {
     uint32_t stride = 0;
     uint8_t *scratchpads = nullptr;        // stride x 2 MiB, VM-major (a VM's accesses are private and data-dependent)
-    uint2 *program = nullptr;              // [256][stride] decoded instructions (8 bytes each)
-    uint64_t *rcp = nullptr;               // [kRcpSlots][stride]
+    uint2 *program = nullptr;              // [stride][256] decoded instructions (8 bytes each)
+    uint64_t *rcp = nullptr;               // [stride][kRcpSlots]
     uint64_t *seed = nullptr;              // [8][stride]   the 64-byte generator state / program seed
     uint64_t *regfile = nullptr;           // [32][stride]  r0-7, f0-3, e0-3, a0-3 (lo,hi) after a program
     uint64_t *config = nullptr;            // [4][stride]   ma|mx, readReg bits|datasetOffset, eMask lo, eMask hi
@@ -46,11 +44,10 @@ cudaError_t launch_seed_k2pow(const BatchBuffers &b, uint32_t n, const K2powTemp
 // AesGenerator1R: 2 MiB scratchpad per VM from its seed; the seed advances to the generator's final state
 cudaError_t launch_fill_scratchpads(const BatchBuffers &b, uint32_t n, cudaStream_t s);
 // AesGenerator4R -> 128 bytes of configuration + 256 instructions, decoded into the VM kernel's format
-cudaError_t launch_program(const BatchBuffers &b, uint32_t n, bool first_program, bool vm_major, cudaStream_t s);
-// the VM: 2048 iterations of the 256-instruction program against scratchpad and dataset
-cudaError_t launch_execute(const BatchBuffers &b, uint32_t n, const uint64_t *d_dataset, cudaStream_t s);
-// the same VM with one WARP per VM (program layout vm_major): no divergence, low latency, 1/16 of the memory
-cudaError_t launch_execute_warp(const BatchBuffers &b, uint32_t n, const uint64_t *d_dataset, cudaStream_t s);
+cudaError_t launch_program(const BatchBuffers &b, uint32_t n, bool first_program, cudaStream_t s);
+// the VM: 2048 iterations of the 256-instruction program against scratchpad and dataset, one warp per VM.
+// variant 0: 1-warp CTAs, <= 64 registers (32 VMs/SM); 1: 2-warp CTAs, <= 40 registers (48 VMs/SM, default); 2: <= 32 registers (64 VMs/SM)
+cudaError_t launch_execute(const BatchBuffers &b, uint32_t n, const uint64_t *d_dataset, int variant, cudaStream_t s);
 // seed = Blake2b-512(register file) for the next program of the chain
 cudaError_t launch_chain_seed(const BatchBuffers &b, uint32_t n, cudaStream_t s);
 // AesHash1R over the scratchpad into a0-3, then Blake2b-256(register file) -> hashes
@@ -59,7 +56,6 @@ cudaError_t launch_finalize(const BatchBuffers &b, uint32_t n, cudaStream_t s);
 cudaError_t launch_find_below(const BatchBuffers &b, uint32_t n, const uint8_t *d_difficulty, uint32_t *d_found, cudaStream_t s);
 // one-time: uploads the AES tables / opcode map the kernels read
 cudaError_t upload_tables();
-int execute_max_ctas_per_sm();
 
 }  // namespace rx
 }  // namespace b200post
