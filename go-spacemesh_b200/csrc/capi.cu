@@ -79,6 +79,7 @@ int b200post_set_option(const char *key, int64_t value) {
     if (k == "ctas_per_sm" && value >= 0 && value <= 32) { o.ctas_per_sm = value; return B200POST_OK; }
     if (k == "max_scratch_mib" && value >= 0) { o.max_scratch_mib = value; return B200POST_OK; }
     if (k == "speculate_next" && (value == 0 || value == 1)) { o.speculate_next = value; return B200POST_OK; }
+    if (k == "lowlat_max_labels" && value >= 0 && value <= (1 << 20)) { o.lowlat_max_labels = value; return B200POST_OK; }
     if (k == "rx_vm_mode" && value >= 0 && value <= 2) { o.rx_vm_mode = value; return B200POST_OK; }
     if (k == "rx_vms_per_sm" && value >= 0 && value <= 4096) { o.rx_vms_per_sm = value; return B200POST_OK; }
     if (k == "debug_skip_phase" && value >= 0 && value <= 3) { o.debug_skip_phase = value; return B200POST_OK; }
@@ -99,6 +100,7 @@ int64_t b200post_get_option(const char *key) {
     if (k == "speculate_next") return o.speculate_next;
     if (k == "rx_vms_per_sm") return o.rx_vms_per_sm;
     if (k == "rx_vm_mode") return o.rx_vm_mode;
+    if (k == "lowlat_max_labels") return o.lowlat_max_labels;
     if (k == "debug_skip_phase") return o.debug_skip_phase;
     return -1;
 }

@@ -242,7 +242,26 @@ int DeviceEngine::run_job(const Job &job) {
     int rc_ = B200POST_OK, status = B200POST_OK;
     auto layer_count = [&](uint64_t m) { return (uint32_t)std::min<uint64_t>(S, job.total - m * S); };
 
-    if (variant_ != ROMIX_PIPELINED) {
+    // small jobs (a proof's K2 labels, one VRF-nonce label, ...): the low-latency kernel, one launch
+    const int64_t lowlat_max = options().lowlat_max_labels.load();
+    const bool lowlat = variant_ == ROMIX_PIPELINED && M == 1 && lowlat_max > 0 && job.total <= (uint64_t)lowlat_max &&
+                        job.total <= (uint64_t)prop_.multiProcessorCount * 4 * 32;
+    if (lowlat) {
+        spec_.valid = false;
+        if (job.cancel && *job.cancel) return B200POST_ERR_CANCELLED;
+        for (int b = 0; b < 2; b++) { if ((rc_ = retire(job, b))) return rc_; harvest(b); }
+        const uint32_t n_valid = (uint32_t)job.total;
+        LabelJob lj;
+        if ((rc_ = stage_layer(job, 0, 0, n_valid, &lj))) return rc_;
+        RomixParams rp;
+        rp.V = V_; rp.X = X_[0]; rp.x_stride = alloc_slots_; rp.N = (uint32_t)job.N; rp.n_slots = n_valid; rp.flags = 0;
+        CU_TRY(cudaEventRecord(ev_k2a_[0], stream_));
+        CU_TRY(launch_romix_lowlat(mw_, rp, romix_lowlat_warps(n_valid, prop_.multiProcessorCount), stream_));
+        CU_TRY(cudaEventRecord(ev_k2b_[0], stream_));
+        k2_pending_[0] = true; k2_labels_[0] = n_valid;
+        g_launches += 1;
+        if ((rc_ = finish_layer(job, 0, 0, n_valid, lj))) return rc_;
+    } else if (variant_ != ROMIX_PIPELINED) {
         spec_.valid = false;
         for (uint64_t m = 0; m < M; m++) {
             if (job.cancel && *job.cancel) { status = B200POST_ERR_CANCELLED; break; }

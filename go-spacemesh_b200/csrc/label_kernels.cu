@@ -235,6 +235,51 @@ __global__ void __launch_bounds__(TPB) romix_kernel(const RomixParams p) {
 }
 
 // =================================================================================================
+// K2s: low-latency ROMix for SMALL batches (one proof = K2 = 37 labels; a VRF-nonce check = 1 label).
+// A label is a serial chain — 2N BlockMix steps of two dependent ChaCha20/8 cores, ~100 dependent integer operations
+// each — so its latency floor on this clock is ~7 ms however many lanes are thrown at it (splitting a core over four
+// lanes leaves the chain as long and adds shuffles: a single lane already issues the four independent quarter rounds
+// back to back).  What CAN be removed is everything the throughput kernel adds for a full wave: here a label gets a
+// lane, labels are spread over as many WARPS as there are scheduler slots (148 x 4) so that every label's warp issues
+// every cycle, and the scratchpad rows (n MiB in total) stay in the 126 MB L2, so the dependent phase-2 read is an L2
+// hit.  Slot s is handled by lane s / W of warp s % W (W = warps launched); V is private scratch, label-major here:
+// row j of slot s at V + (s * N + j) * 8 uint4 (n x 128*N bytes in total, whatever W is).
+// =================================================================================================
+__device__ __forceinline__ uint4 ld_l2(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_l2(uint4 *p, const uint4 &v) {
+    asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+template <int MW>
+__global__ void __launch_bounds__(32) romix_lowlat_kernel(const RomixParams p, uint32_t n_warps) {
+    const uint32_t lane = threadIdx.x, warp = blockIdx.x;
+    const uint32_t slot = lane * n_warps + warp;
+    if (slot >= p.n_slots) return;
+    const uint32_t N = p.N, mask = N - 1;
+    uint32_t lo[16], hi[16];
+#pragma unroll
+    for (int k = 0; k < 8; k++) set_chunk(lo, hi, k, p.X[(size_t)k * p.x_stride + slot]);
+    uint4 *const Vt = p.V + (size_t)slot * N * 8;          // label-major: 128*N contiguous bytes per label
+    for (uint32_t i = 0; i < N; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) st_l2(Vt + (size_t)i * 8 + k, ROW_CHUNK(lo, hi, k));
+        blockmix_r1<MW>(lo, hi);
+    }
+    for (uint32_t i = 0; i < N; i++) {
+        const uint32_t j = hi[0] & mask;
+        uint32_t vlo[16], vhi[16];
+#pragma unroll
+        for (int k = 0; k < 8; k++) set_chunk(vlo, vhi, k, ld_l2(Vt + (size_t)j * 8 + k));
+        blockmix_r1_xor<MW>(lo, hi, vlo, vhi);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) p.X[(size_t)k * p.x_stride + slot] = ROW_CHUNK(lo, hi, k);
+}
+
+// =================================================================================================
 // K2p: pipelined ROMix.  Every thread advances TWO labels per step: the label of layer m is in its fill
 // loop (V[i] <- X; X <- BlockMix(X)) while the label of layer m-1 is in its mix loop
 // (X <- BlockMix(X ^ V[Integerify(X)])).  The mix loop's dependent HBM read (~0.6-1.5 us) is issued
@@ -609,6 +654,18 @@ cudaError_t launch_romix(int variant, int rot_mask, int tpb, const RomixParams &
         if (e != cudaSuccess) return e;
     }
     fn<<<(p.n_slots + tpb - 1) / tpb, tpb, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+uint32_t romix_lowlat_warps(uint32_t n_slots, int sm_count) {
+    const uint32_t full = (uint32_t)sm_count * 4;             // one warp per scheduler slot
+    return n_slots < full ? (n_slots ? n_slots : 1) : full;
+}
+cudaError_t launch_romix_lowlat(int rot_mask, const RomixParams &p, uint32_t n_warps, cudaStream_t s) {
+    if (p.n_slots == 0) return cudaSuccess;
+    if (n_warps == 0 || (uint64_t)n_warps * 32 < p.n_slots) return cudaErrorInvalidValue;
+    if (rot_mask == 1) romix_lowlat_kernel<1><<<n_warps, 32, 0, s>>>(p, n_warps);
+    else romix_lowlat_kernel<0><<<n_warps, 32, 0, s>>>(p, n_warps);
     return cudaGetLastError();
 }
 

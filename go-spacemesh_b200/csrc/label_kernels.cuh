@@ -66,6 +66,9 @@ struct VrfCandidate {           // 48 bytes
 cudaError_t launch_pbkdf2_expand(const LabelJob &job, uint4 *X, uint32_t x_stride, uint32_t n_slots, cudaStream_t s);
 cudaError_t launch_romix(int variant, int rot_mask, int tpb, const RomixParams &p, cudaStream_t s);
 cudaError_t launch_romix_pipe(int rot_mask, int tpb, int dr_unroll, const PipeParams &p, cudaStream_t s);
+// K2s, small batches: n_slots labels spread over n_warps = romix_lowlat_warps() one-warp CTAs (p.n_slots need not be a multiple of 32)
+uint32_t romix_lowlat_warps(uint32_t n_slots, int sm_count);
+cudaError_t launch_romix_lowlat(int rot_mask, const RomixParams &p, uint32_t n_warps, cudaStream_t s);
 // rotate-form masks compiled in (post_device.cuh ROT): 0 = all SHF, 1 = 16/8-bit rotates as PRMT
 bool romix_mask_supported(int mw);
 // out16: n_valid x 16 bytes (device).  vrf_difficulty_be: 8 big-endian words (device) or nullptr.

@@ -362,3 +362,32 @@ def test_back_to_back_batches_resume_the_pipeline(b2, orc):
         assert (got == orc.c_labels_range(c, 2, batch, 2000)[0]).all()
     finally:
         b2.set_option("speculate_next", 1)
+
+
+def test_low_latency_kernel_equals_throughput_kernel_and_oracle(b2, orc, gpu_ready):
+    """Small jobs take the low-latency ROMix kernel (labels spread over warps, label-major scratch): same bytes as the
+    pipelined kernel and the oracle, at the sizes where the spreading changes shape (1, K2 = 37, one more than the
+    592 scheduler slots, the switch-over size)."""
+    rng = np.random.default_rng(31)
+    old = b2.get_option("lowlat_max_labels")
+    try:
+        for n in (1, 37, 593, 1500):
+            comms = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+            idx = rng.integers(0, 2**40, n, dtype=np.uint64)
+            idx[0] = 2**64 - 1
+            b2.set_option("lowlat_max_labels", 4096)
+            fast = b2.labels_gather(comms, idx, 8192)
+            b2.set_option("lowlat_max_labels", 0)
+            slow = b2.labels_gather(comms, idx, 8192)
+            assert (fast == slow).all(), n
+            if n <= 593:
+                assert (fast == orc.c_labels_gather(comms, idx, 8192)).all(), n
+        b2.set_option("lowlat_max_labels", 4096)
+        c = b2.commitment(bytes(range(32)), bytes(range(32, 64)))
+        for nn, count in ((8192, 50), (2, 600), (64, 100)):
+            diff = b2.vrf_difficulty(count)
+            got, vrf = b2.labels_range(c, nn, 2**32 - 20, count, vrf_difficulty_=diff)
+            exp, found, i, l32 = orc.c_labels_range(c, nn, 2**32 - 20, count, diff)
+            assert (got == exp).all() and vrf == ((i, l32) if found else None), nn
+    finally:
+        b2.set_option("lowlat_max_labels", old)
