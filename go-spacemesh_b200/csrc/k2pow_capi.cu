@@ -1,4 +1,5 @@
 // k2pow_capi.cu — extern "C" surface of the k2pow (RandomX) engine (declared in include/b200post_k2pow.h).
+#include <algorithm>
 #include <atomic>
 #include <cstring>
 #include <string>
@@ -117,6 +118,52 @@ int b200post_k2pow_search_multi(const uint32_t *providers, int n_providers, cons
     for (int i = 0; i < n_providers; i++) { total += dones[i]; if (hits[i] < *found) *found = hits[i]; }
     if (hashes_done) *hashes_done = total;
     for (int i = 0; i < n_providers; i++) if (rcs[i] != B200POST_OK) { set_error(errs[i]); return rcs[i]; }
+    return B200POST_OK;
+}
+
+int b200post_k2pow_search_groups(uint32_t provider, const b200post_k2pow_params *p, uint32_t n_groups, uint64_t max_nonces_per_group,
+                                 uint64_t *pows, uint64_t *hashes_done, const volatile int *cancel) {
+    if (!p || !pows || n_groups == 0 || n_groups > 256) { set_error("invalid argument"); return B200POST_ERR_INVALID_ARGUMENT; }
+    RandomxEngine *e = randomx_engine_for(provider);
+    if (!e) return provider == B200POST_CPU_PROVIDER_ID ? B200POST_ERR_UNSUPPORTED : B200POST_ERR_NO_DEVICE;
+    const std::string key = key_of(p->cache_key, p->cache_key_len);
+    uint64_t batch = 0;
+    e->batch_size(&batch);
+    for (uint32_t g = 0; g < n_groups; g++) pows[g] = B200POST_K2POW_NOT_FOUND;
+    if (max_nonces_per_group == 0 || max_nonces_per_group > kNonceSpace) max_nonces_per_group = kNonceSpace;
+    std::vector<uint32_t> pending(n_groups);
+    for (uint32_t g = 0; g < n_groups; g++) pending[g] = g;
+    std::vector<uint8_t> in, out;
+    uint64_t next = 0, total = 0;      // every pending group has tried nonces [0, next)
+    while (!pending.empty() && next < max_nonces_per_group) {
+        if (cancel && *cancel) { set_error("cancelled"); return B200POST_ERR_CANCELLED; }
+        // one device batch shared by all groups still searching: `per` consecutive nonces each
+        const uint64_t per = std::min<uint64_t>(std::max<uint64_t>(1, batch / pending.size()), max_nonces_per_group - next);
+        const size_t n = pending.size() * per;
+        in.resize(n * 48); out.resize(n * 32);
+        for (size_t gi = 0; gi < pending.size(); gi++)
+            for (uint64_t k = 0; k < per; k++) {
+                uint8_t *d = &in[(gi * per + k) * 48];
+                const uint64_t pow = next + k;
+                for (int b = 0; b < 7; b++) d[b] = (uint8_t)(pow >> (8 * b));
+                d[7] = (uint8_t)pending[gi];
+                memcpy(d + 8, p->challenge8, 8);
+                memcpy(d + 16, p->node_id, 32);
+            }
+        const int rc = e->hash_inputs(key, in.data(), 48, n, out.data());
+        if (rc != B200POST_OK) return rc;
+        total += n;
+        std::vector<uint32_t> still;
+        for (size_t gi = 0; gi < pending.size(); gi++) {
+            uint64_t hit = B200POST_K2POW_NOT_FOUND;
+            for (uint64_t k = 0; k < per && hit == B200POST_K2POW_NOT_FOUND; k++)
+                if (memcmp(&out[(gi * per + k) * 32], p->difficulty, 32) < 0) hit = next + k;
+            if (hit == B200POST_K2POW_NOT_FOUND) still.push_back(pending[gi]); else pows[pending[gi]] = hit;
+        }
+        pending.swap(still);
+        next += per;
+    }
+    if (hashes_done) *hashes_done = total;
     return B200POST_OK;
 }
 

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/b200post_prove.h"
+#include "../../include/b200post_k2pow.h"
 #include "aes_device.cuh"
 #include "engine.h"
 #include "metrics.h"
@@ -308,11 +309,26 @@ int b200post_generate_proof(const char *data_dir, const uint8_t challenge[32], c
     if (num_labels == 0 || o.nonces % 16 || o.nonces > 4096) { set_error("invalid metadata or nonce count"); return B200POST_ERR_INVALID_ARGUMENT; }
     // k2pow per nonce group (RandomX upstream) through the caller's hook
     std::vector<uint64_t> pows(o.nonces / 16, 0);
-    if (o.pow_prove) {
+    if (o.pow_mode > B200POST_POW_SKIP || (o.pow_mode == B200POST_POW_CALLBACK && !o.pow_prove)) {
+        set_error("pow_mode CALLBACK needs a pow_prove function; to prove without k2pow ask for B200POST_POW_SKIP explicitly");
+        return B200POST_ERR_UNSUPPORTED;
+    }
+    if (o.pow_mode != B200POST_POW_SKIP) {
         uint8_t scaled[32];
         div256_u32(cfg->pow_difficulty, md.num_units, scaled);
-        for (uint32_t g = 0; g < o.nonces / 16; g++)
-            if (o.pow_prove(o.pow_ctx, (uint8_t)g, challenge, scaled, md.node_id, &pows[g]) != 0) { set_error("k2pow hook failed"); return B200POST_ERR_INVALID_ARGUMENT; }
+        if (o.pow_mode == B200POST_POW_CALLBACK) {
+            for (uint32_t g = 0; g < o.nonces / 16; g++)
+                if (o.pow_prove(o.pow_ctx, (uint8_t)g, challenge, scaled, md.node_id, &pows[g]) != 0) { set_error("k2pow hook failed"); return B200POST_ERR_INVALID_ARGUMENT; }
+        } else {
+            // the k2pow step of NIPostBuilder.Proof (activation/nipost.go:171 -> post-service): RandomX nonce search on the device
+            b200post_k2pow_params kp{};
+            kp.cache_key = o.pow_cache_key; kp.cache_key_len = o.pow_cache_key_len;
+            memcpy(kp.challenge8, challenge, 8);
+            memcpy(kp.node_id, md.node_id, 32);
+            memcpy(kp.difficulty, scaled, 32);
+            if ((rc = b200post_k2pow_search_groups(o.provider, &kp, o.nonces / 16, 0, pows.data(), nullptr, cancel))) return rc;
+            for (uint64_t v : pows) if (v == B200POST_K2POW_NOT_FOUND) { set_error("k2pow: nonce space exhausted"); return B200POST_ERR_INVALID_PROOF; }
+        }
     }
     Scanner sc;
     const uint64_t chunk = std::min<uint64_t>(o.chunk_labels, num_labels);

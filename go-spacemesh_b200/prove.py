@@ -20,7 +20,8 @@ POW_PROVE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint8, c
 
 class _ProveOpts(ctypes.Structure):
     _fields_ = [("provider", ctypes.c_uint32), ("nonces", ctypes.c_uint32), ("chunk_labels", ctypes.c_uint64),
-                ("pow_prove", POW_PROVE_FN), ("pow_ctx", ctypes.c_void_p)]
+                ("pow_prove", POW_PROVE_FN), ("pow_ctx", ctypes.c_void_p), ("pow_mode", ctypes.c_uint32),
+                ("pow_cache_key", ctypes.c_char_p), ("pow_cache_key_len", ctypes.c_size_t)]
 
 
 class _ProofOut(ctypes.Structure):
@@ -45,6 +46,8 @@ def _c_cfg(cfg: PostConfig) -> _PostConfig:
     _bind_setup().b200post_default_post_config(ctypes.byref(c))
     c.min_num_units, c.max_num_units, c.labels_per_unit = cfg.min_num_units, cfg.max_num_units, cfg.labels_per_unit
     c.k1, c.k2, c.k3 = cfg.k1, cfg.k2, cfg.k3
+    if getattr(cfg, "pow_difficulty", None) is not None:
+        ctypes.memmove(c.pow_difficulty, cfg.pow_difficulty, 32)
     return c
 
 
@@ -54,11 +57,16 @@ def _err(rc):
 
 
 def generate_proof(data_dir: str, challenge: bytes, cfg: PostConfig, *, provider: int = 0, nonces: int = 16,
-                   chunk_labels: int = 0, pow_prove=None):
-    """PostClient.Proof(ctx, challenge) -> (Post, PostInfo-like metadata); also returns labels scanned."""
+                   chunk_labels: int = 0, pow="builtin"):
+    """PostClient.Proof(ctx, challenge) -> (Post, PostInfo-like metadata); also returns labels scanned.
+    pow: "builtin" (k2pow search on the device, the library default), "skip" (pow = 0, explicit) or a callable
+    (ctx, nonce_group, challenge8, difficulty32, node_id32, pow_out) -> 0."""
     L = _bind()
-    cb = POW_PROVE_FN(pow_prove) if pow_prove else ctypes.cast(None, POW_PROVE_FN)
-    opts = _ProveOpts(provider, nonces, chunk_labels, cb, None)
+    if callable(pow):
+        cb, mode = POW_PROVE_FN(pow), 1
+    else:
+        cb, mode = ctypes.cast(None, POW_PROVE_FN), {"builtin": 0, "skip": 2, "callback-missing": 1}[pow]
+    opts = _ProveOpts(provider, nonces, chunk_labels, cb, None, mode, None, 0)
     out, meta, c = _ProofOut(), _Meta(), _c_cfg(cfg)
     _err(L.b200post_generate_proof(data_dir.encode(), challenge, ctypes.byref(c), ctypes.byref(opts), ctypes.byref(out),
                                    ctypes.byref(meta), None))

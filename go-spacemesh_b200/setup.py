@@ -46,6 +46,7 @@ class PostConfig:            # activation/post.go:27-38
     k1: int = 26
     k2: int = 37
     k3: int = 37
+    pow_difficulty: bytes | None = None   # None = the library default (config/mainnet.go:41's prefix)
 
 
 @dataclass

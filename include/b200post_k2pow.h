@@ -72,6 +72,12 @@ int b200post_k2pow_search_multi(const uint32_t *providers, int n_providers, cons
                                 uint64_t start, uint64_t count, uint64_t *found, uint64_t *hashes_done,
                                 const volatile int *cancel);
 
+/* What the prover needs (one k2pow per group of 16 proving nonces, activation/post.go:64-81 Nonces): the smallest valid
+ * pow of each nonce group 0..n_groups-1 (p->nonce_group is ignored), all groups sharing device batches.  pows[g] =
+ * B200POST_K2POW_NOT_FOUND if none below max_nonces_per_group (0 = the whole 56-bit space). */
+int b200post_k2pow_search_groups(uint32_t provider, const b200post_k2pow_params *p, uint32_t n_groups, uint64_t max_nonces_per_group,
+                                 uint64_t *pows, uint64_t *hashes_done, const volatile int *cancel);
+
 /* The verifier's check: *valid = 1 iff RandomX(input(pow)) < p->difficulty. */
 int b200post_k2pow_verify(uint32_t provider, const b200post_k2pow_params *p, uint64_t pow, int *valid);
 

@@ -37,8 +37,13 @@ typedef struct b200post_prove_opts {
     uint32_t provider;                 /* CUDA ordinal                                                         */
     uint32_t nonces;                   /* PostProvingOpts.Nonces: a positive multiple of 16 (0 = 16), <= 4096  */
     uint64_t chunk_labels;             /* labels per H2D chunk (0 = 2^22 = 64 MiB)                             */
-    b200post_pow_prove_fn pow_prove;   /* NULL = pow 0 for every nonce group                                    */
+    b200post_pow_prove_fn pow_prove;   /* used when pow_mode == B200POST_POW_CALLBACK                            */
     void *pow_ctx;
+    uint32_t pow_mode;                 /* B200POST_POW_BUILTIN (default): k2pow search on the device (b200post_k2pow.h);
+                                          B200POST_POW_CALLBACK: pow_prove; B200POST_POW_SKIP: pow = 0 for every group
+                                          (explicit opt-out: such a proof only verifies with the pow check skipped)  */
+    const uint8_t *pow_cache_key;      /* BUILTIN: RandomX cache key, NULL = the spacemesh default                 */
+    size_t pow_cache_key_len;
 } b200post_prove_opts;
 
 typedef struct b200post_proof_out {    /* types.Post / shared.Proof */
