@@ -225,6 +225,24 @@ def verify_vrf_nonce(nonce: int, node_id: bytes, commitment_atx_id: bytes, num_u
     return bool(valid.value)
 
 
+def vrf_nonce_label(nonce: int, node_id: bytes, commitment_atx_id: bytes, n: int, *, provider: int = 0) -> bytes:
+    """label32 at index `nonce` of the identity's POST — the policy-free half of VerifyVRFNonce."""
+    out = ctypes.create_string_buffer(32)
+    L = lib()
+    L.b200post_vrf_nonce_label.argtypes = [ctypes.c_uint32, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_void_p]
+    _check(L.b200post_vrf_nonce_label(provider, nonce, node_id, commitment_atx_id, n, out))
+    return out.raw
+
+
+def reference_label(commitment_: bytes, index: int, n: int) -> bytes:
+    """The fault detector's independent checker: one label32 on the host CPU (NOT a compute path)."""
+    out = ctypes.create_string_buffer(32)
+    L = lib()
+    L.b200post_reference_label.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
+    _check(L.b200post_reference_label(commitment_, index, n, out))
+    return out.raw
+
+
 def benchmark(n: int = 8192, seconds: float = 2.0, *, provider: int = 0) -> float:
     """PostSupervisor.Benchmark (activation/post_supervisor.go:120-127): labels ("hashes") per second."""
     v = ctypes.c_double(0)

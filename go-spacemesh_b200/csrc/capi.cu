@@ -1,4 +1,5 @@
 // capi.cu — extern "C" surface of libb200post.so (declared in include/b200post.h, include/post_compat.h).
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <string>
@@ -79,6 +80,8 @@ int b200post_set_option(const char *key, int64_t value) {
     if (k == "ctas_per_sm" && value >= 0 && value <= 32) { o.ctas_per_sm = value; return B200POST_OK; }
     if (k == "max_scratch_mib" && value >= 0) { o.max_scratch_mib = value; return B200POST_OK; }
     if (k == "speculate_next" && (value == 0 || value == 1)) { o.speculate_next = value; return B200POST_OK; }
+    if (k == "debug_corrupt_next_batch" && (value == 0 || value == 1)) { o.debug_corrupt_next_batch = value; return B200POST_OK; }
+    if (k == "debug_corrupt_check_all" && (value == 0 || value == 1)) { o.debug_corrupt_check_all = value; return B200POST_OK; }
     if (k == "lowlat_max_labels" && value >= 0 && value <= (1 << 20)) { o.lowlat_max_labels = value; return B200POST_OK; }
     if (k == "rx_vm_mode" && value >= 0 && value <= 2) { o.rx_vm_mode = value; return B200POST_OK; }
     if (k == "rx_vms_per_sm" && value >= 0 && value <= 4096) { o.rx_vms_per_sm = value; return B200POST_OK; }
@@ -204,15 +207,32 @@ int b200post_verify_vrf_nonce(uint32_t provider, uint64_t nonce, const uint8_t n
     return B200POST_OK;
 }
 
+int b200post_vrf_nonce_label(uint32_t provider, uint64_t nonce, const uint8_t node_id[32], const uint8_t commitment_atx_id[32],
+                             uint64_t n, uint8_t label32[32]) {
+    if (!node_id || !commitment_atx_id || !label32) { set_error("invalid argument"); return B200POST_ERR_INVALID_ARGUMENT; }
+    uint8_t commitment[32], all[32];
+    commitment_bytes(node_id, commitment_atx_id, commitment);
+    memset(all, 0xff, 32);
+    b200post_vrf_nonce r;
+    const int rc = b200post_labels_range(provider, commitment, n, nonce, 1, nullptr, all, &r, nullptr);
+    if (rc) return rc;
+    if (!r.found) memset(label32, 0xff, 32); else memcpy(label32, r.label32, 32);   // found is 0 only for the all-ones label
+    return B200POST_OK;
+}
+
 int b200post_benchmark(uint32_t provider, uint64_t n, double seconds, double *labels_per_sec) {
     if (!labels_per_sec || !valid_n(n)) { set_error("invalid argument"); return B200POST_ERR_INVALID_ARGUMENT; }
     uint8_t commitment[32];
     memset(commitment, 0x5a, 32);
     DeviceEngine *e = engine_for(provider);
     if (!e) return provider == B200POST_CPU_PROVIDER_ID ? B200POST_ERR_UNSUPPORTED : B200POST_ERR_NO_DEVICE;
-    // warm-up allocates the scratch; then time whole waves until `seconds` have elapsed
-    uint64_t batch = 1u << 16;
-    int rc = b200post_labels_range(provider, commitment, n, 0, batch, nullptr, nullptr, nullptr, nullptr);
+    // batches of 4 whole layers (the software pipeline needs >= 4 to run filled, and back-to-back calls continue it:
+    // DeviceEngine's speculative next-layer fill); the first call allocates the scratch and is not timed
+    uint64_t slots = 0;
+    int rc = b200post_wave_slots(provider, n, &slots);
+    if (rc) return rc;
+    const uint64_t batch = std::max<uint64_t>(4 * slots, 1u << 16);
+    rc = b200post_labels_range(provider, commitment, n, 0, batch, nullptr, nullptr, nullptr, nullptr);
     if (rc) return rc;
     const auto t0 = std::chrono::steady_clock::now();
     uint64_t done = 0;
@@ -222,7 +242,6 @@ int b200post_benchmark(uint32_t provider, uint64_t n, double seconds, double *la
         if (rc) return rc;
         done += batch;
         el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        if (el < seconds / 8 && batch < (1ull << 24)) batch *= 2;
     } while (el < seconds);
     *labels_per_sec = (double)done / el;
     return B200POST_OK;
@@ -258,6 +277,12 @@ double b200post_timer_elapsed_ms(uint32_t provider) {
 double b200post_last_call_ms(uint32_t provider) {
     DeviceEngine *e = engine_for(provider);
     return e ? e->last_call_ms() : -1.0;
+}
+
+int b200post_reference_label(const uint8_t commitment[32], uint64_t index, uint64_t n, uint8_t out32[32]) {
+    if (!commitment || !out32 || !valid_n(n)) { set_error("invalid argument"); return B200POST_ERR_INVALID_ARGUMENT; }
+    reference_label32(commitment, index, (uint32_t)n, out32);
+    return B200POST_OK;
 }
 
 void b200post_shutdown(void) { shutdown_all(); }

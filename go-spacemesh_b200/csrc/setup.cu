@@ -342,14 +342,18 @@ int b200post_setup_start_session(b200post_setup_manager *m, const volatile int *
         int rc = compute(m, written, count, buf.data(), diff, &nn, cancel, commitment);
         if (rc == B200POST_ERR_CANCELLED) return finish(B200POST_SETUP_STOPPED, rc);
         if (rc) return finish(B200POST_SETUP_ERROR, rc);
-        // ErrReferenceLabelMismatch contract (activation/post.go:299-312): cross-check one label of the batch
-        // through the scattered-index path every self_check_every batches
+        // ErrReferenceLabelMismatch contract (activation/post.go:299-312): every self_check_every batches one label of the
+        // batch is recomputed ON THE HOST CPU (reference_label.cpp: the kernels' own arithmetic header compiled for the
+        // host) and compared with what the device wrote — independent of the device, its kernels' scheduling and memory.
+        if (options().debug_corrupt_next_batch.exchange(0) != 0 && count) buf[((n_batches * 7) % count) * 16 + 3] ^= 0x40;   // fault injection (tests)
         if (n_batches % m->opts.self_check_every == 0) {
-            uint8_t ref[16];
-            const uint32_t prov = m->opts.provider_id == B200POST_PROVIDER_ALL ? 0u : (uint32_t)m->opts.provider_id;
-            const uint64_t pick = written + (n_batches * 2654435761ull) % count;
-            rc = b200post_labels_gather(prov, 1, commitment, &pick, m->opts.scrypt_n, ref);
-            if (rc) return finish(B200POST_SETUP_ERROR, rc);
+            uint8_t ref[32];
+            uint64_t pick = written + (n_batches * 2654435761ull) % count;
+            if (options().debug_corrupt_check_all.load() != 0) {
+                // test hook: check the label the injected fault hit (the sampled one is elsewhere with probability 1 - 1/count)
+                pick = written + (n_batches * 7) % count;
+            }
+            reference_label32(commitment, pick, (uint32_t)m->opts.scrypt_n, ref);
             if (memcmp(ref, buf.data() + (pick - written) * 16, 16)) {
                 metrics().setup_label_mismatch_total++;
                 set_error("reference label mismatch at index " + std::to_string(pick));

@@ -23,6 +23,7 @@ import (
 	"context"
 	"errors"
 	"fmt"
+	"runtime"
 	"sync/atomic"
 	"unsafe"
 )
@@ -42,7 +43,20 @@ var (
 	ErrCancelled   = context.Canceled
 )
 
-func statusErr(rc C.int) error {
+// checked runs ONE C call and, if it failed, reads b200post_last_error() before the goroutine can move: the error text
+// is thread-local in C, and without LockOSThread a second cgo call may land on another OS thread and read a stale or
+// empty message.  Every call whose error text matters goes through here.
+func checked(call func() C.int) (C.int, string) {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	rc := call()
+	if rc == C.B200POST_OK {
+		return rc, ""
+	}
+	return rc, C.GoString(C.b200post_last_error())
+}
+
+func statusErr(rc C.int, msg string) error {
 	switch rc {
 	case C.B200POST_OK:
 		return nil
@@ -53,7 +67,7 @@ func statusErr(rc C.int) error {
 	case C.B200POST_ERR_CANCELLED:
 		return ErrCancelled
 	default:
-		return fmt.Errorf("b200post: status %d: %s", int(rc), C.GoString(C.b200post_last_error()))
+		return fmt.Errorf("b200post: status %d: %s", int(rc), msg)
 	}
 }
 
@@ -75,7 +89,7 @@ func Providers() ([]Provider, error) {
 // Benchmark returns labels ("hashes") per second — drop-in for initialization.Benchmark.
 func Benchmark(provider uint32, scryptN uint64) (int, error) {
 	var v C.double
-	if err := statusErr(C.b200post_benchmark(C.uint32_t(provider), C.uint64_t(scryptN), 2.0, &v)); err != nil {
+	if err := statusErr(checked(func() C.int { return C.b200post_benchmark(C.uint32_t(provider), C.uint64_t(scryptN), 2.0, &v) })); err != nil {
 		return 0, err
 	}
 	return int(v), nil

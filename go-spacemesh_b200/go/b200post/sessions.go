@@ -43,6 +43,7 @@ var (
 	ErrNoProvider       = errors.New("no provider specified")            // activation/post_test.go:113
 	ErrLabelMismatch    = errors.New("reference label mismatch")         // initialization.ErrReferenceLabelMismatch
 	ErrConfigMismatch   = errors.New("post data belongs to another identity or configuration")
+	ErrInvalidPow       = errors.New("invalid k2pow")
 )
 
 type SetupConfig struct { // PostConfig (activation/post.go:27-38)
@@ -65,7 +66,7 @@ const AllProviders = ^uint32(1) // maps to B200POST_PROVIDER_ALL
 
 type SetupManager struct{ h *C.b200post_setup_manager }
 
-func setupErr(rc C.int) error {
+func setupErr(rc C.int, msg string) error {
 	switch rc {
 	case C.B200POST_OK:
 		return nil
@@ -76,15 +77,18 @@ func setupErr(rc C.int) error {
 	case C.B200POST_ERR_LABEL_MISMATCH:
 		return ErrLabelMismatch
 	case C.B200POST_ERR_CONFIG_MISMATCH:
-		return fmt.Errorf("%w: %s", ErrConfigMismatch, C.GoString(C.b200post_last_error()))
+		return fmt.Errorf("%w: %s", ErrConfigMismatch, msg)
 	case C.B200POST_ERR_STATE:
-		msg := C.GoString(C.b200post_last_error())
-		if msg == ErrNotPrepared.Error() {
+		// msg was read on the OS thread that made the failing call (checked): safe to compare
+		switch msg {
+		case ErrNotPrepared.Error():
 			return ErrNotPrepared
+		case ErrSessionInProgess.Error():
+			return ErrSessionInProgess
 		}
-		return fmt.Errorf("%w", errors.New(msg))
+		return errors.New(msg)
 	default:
-		return statusErr(rc)
+		return statusErr(rc, msg)
 	}
 }
 
@@ -95,7 +99,7 @@ func NewSetupManager(cfg SetupConfig) (*SetupManager, error) {
 	c.k1, c.k2, c.k3 = C.uint32_t(cfg.K1), C.uint32_t(cfg.K2), C.uint32_t(cfg.K3)
 	C.memcpy(unsafe.Pointer(&c.pow_difficulty[0]), unsafe.Pointer(&cfg.PowDifficulty[0]), 32)
 	m := &SetupManager{}
-	if err := setupErr(C.b200post_setup_manager_new(&c, &m.h)); err != nil {
+	if err := setupErr(checked(func() C.int { return C.b200post_setup_manager_new(&c, &m.h) })); err != nil {
 		return nil, err
 	}
 	return m, nil
@@ -144,7 +148,7 @@ func (m *SetupManager) Status() (PostSetupState, uint64) {
 	return PostSetupState(st.state), uint64(st.num_labels_written)
 }
 
-func (m *SetupManager) Reset() error { return setupErr(C.b200post_setup_reset(m.h)) }
+func (m *SetupManager) Reset() error { return setupErr(checked(func() C.int { return C.b200post_setup_reset(m.h) })) }
 func (m *SetupManager) Close()       { C.b200post_setup_manager_free(m.h) }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -177,9 +181,25 @@ type VerifyOptions struct {
 
 type Verifier struct{ h *C.b200post_verifier }
 
-func NewVerifier(provider uint32) (*Verifier, error) {
+// VerifierOptions: the k2pow policy is explicit.  The zero value runs the RandomX pow check of
+// verifying.ProofVerifier.Verify (activation/post_verifier.go:150-160) on the device; SkipPow must be asked for.
+type VerifierOptions struct {
+	SkipPow        bool
+	MaxBatchProofs uint32
+}
+
+// NewVerifier = NewPostVerifier (activation/post_verifier.go:191-221) with the builtin k2pow check.
+func NewVerifier(provider uint32) (*Verifier, error) { return NewVerifierWith(provider, VerifierOptions{}) }
+
+func NewVerifierWith(provider uint32, o VerifierOptions) (*Verifier, error) {
 	v := &Verifier{}
-	if err := statusErr(C.b200post_verifier_new(C.uint32_t(provider), nil, &v.h)); err != nil {
+	var co C.b200post_verifier_opts // C struct without Go pointers: may be passed by address
+	co.max_batch_proofs = C.uint32_t(o.MaxBatchProofs)
+	co.pow_mode = C.B200POST_POW_BUILTIN
+	if o.SkipPow {
+		co.pow_mode = C.B200POST_POW_SKIP
+	}
+	if err := statusErr(checked(func() C.int { return C.b200post_verifier_new(C.uint32_t(provider), &co, &v.h) })); err != nil {
 		return nil, err
 	}
 	return v, nil
@@ -198,11 +218,15 @@ func NewVerifierOn(providers []uint32) (*Verifier, error) {
 	return v, nil
 }
 
-func (v *Verifier) Verify(p *Proof, m *ProofMetadata, k1, k2 uint32, scryptN uint64, o VerifyOptions) error {
+func (v *Verifier) Verify(p *Proof, m *ProofMetadata, k1, k2 uint32, powDifficulty [32]byte, scryptN uint64, o VerifyOptions) error {
 	if len(p.Indices) == 0 {
 		return errors.New("proof indices are empty")
 	}
-	cp := C.b200post_proof{nonce: C.uint32_t(p.Nonce), indices: (*C.uint8_t)(unsafe.Pointer(&p.Indices[0])), indices_len: C.size_t(len(p.Indices)), pow: C.uint64_t(p.Pow)}
+	// cgo pointer rules: a Go-allocated struct passed to C must not contain Go pointers, so the variable-length inputs
+	// (packed indices, subset seed) are copied into C memory for the duration of the call.
+	cidx := C.CBytes(p.Indices)
+	defer C.free(cidx)
+	cp := C.b200post_proof{nonce: C.uint32_t(p.Nonce), indices: (*C.uint8_t)(cidx), indices_len: C.size_t(len(p.Indices)), pow: C.uint64_t(p.Pow)}
 	var cm C.b200post_proof_metadata
 	C.memcpy(unsafe.Pointer(&cm.node_id[0]), unsafe.Pointer(&m.NodeId[0]), 32)
 	C.memcpy(unsafe.Pointer(&cm.commitment_atx_id[0]), unsafe.Pointer(&m.CommitmentAtxId[0]), 32)
@@ -216,24 +240,33 @@ func (v *Verifier) Verify(p *Proof, m *ProofMetadata, k1, k2 uint32, scryptN uin
 	case o.SubsetK3 > 0:
 		co.mode, co.k3 = C.B200POST_VERIFY_SUBSET, C.uint32_t(o.SubsetK3)
 		if len(o.SubsetSeed) > 0 {
-			co.seed, co.seed_len = (*C.uint8_t)(unsafe.Pointer(&o.SubsetSeed[0])), C.size_t(len(o.SubsetSeed))
+			cseed := C.CBytes(o.SubsetSeed)
+			defer C.free(cseed)
+			co.seed, co.seed_len = (*C.uint8_t)(cseed), C.size_t(len(o.SubsetSeed))
 		}
 	}
 	if o.Prioritized {
 		co.prioritized = 1
 	}
+	C.memcpy(unsafe.Pointer(&cq.pow_difficulty[0]), unsafe.Pointer(&powDifficulty[0]), 32)
 	var bad C.uint64_t
-	switch rc := C.b200post_verifier_verify(v.h, &cp, &cm, &cq, &co, &bad); rc {
+	rc, msg := checked(func() C.int { return C.b200post_verifier_verify(v.h, &cp, &cm, &cq, &co, &bad) })
+	switch rc {
 	case C.B200POST_OK:
 		return nil
 	case C.B200POST_ERR_INVALID_PROOF:
+		if uint64(bad) == ^uint64(0) {
+			return ErrInvalidPow // the k2pow, not a label
+		}
+		// Index = POSITION in the proof's K2 index list: handler_v1.go:248 stores it as InvalidPostIndexProof.InvalidIdx,
+		// malfeasance.go:165 re-verifies it with verifying.SelectedIndex(int(InvalidIdx))
 		return &ErrInvalidIndex{Index: int(bad)}
 	case C.B200POST_ERR_CLOSED:
 		return ErrVerifierClosed
 	case C.B200POST_ERR_EMPTY_PROOF:
 		return errors.New("proof indices are empty")
 	default:
-		return statusErr(rc)
+		return statusErr(rc, msg)
 	}
 }
 
@@ -243,8 +276,8 @@ func (v *Verifier) Close() error { C.b200post_verifier_close(v.h); return nil }
 // Proof generation scan (the AES half of PostClient.Proof, activation/interface.go:204-207)
 // ---------------------------------------------------------------------------------------------------------
 
-// GenerateProof scans the POST data in dataDir.  pows = the k2pow of each nonce group (RandomX upstream),
-// computed by the caller; this package does not implement RandomX.
+// GenerateProof = PostClient.Proof for data on this host: the k2pow search of every nonce group (RandomX, on the device)
+// followed by the proving scan.  It stands where the RPC to the post-service stands (activation/nipost.go:171).
 func GenerateProof(provider uint32, dataDir string, challenge []byte, cfg SetupConfig, nonces uint32) (*Proof, error) {
 	dir := C.CString(dataDir)
 	defer C.free(unsafe.Pointer(dir))

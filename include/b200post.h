@@ -123,10 +123,27 @@ void b200post_commitment(const uint8_t node_id[32], const uint8_t commitment_atx
 void b200post_vrf_difficulty(uint64_t num_labels, uint8_t out[32]);
 
 /* verifying.VerifyVRFNonce: recompute label32 at `nonce` and compare with the threshold for
- * num_units*labels_per_unit labels.  *valid = 1/0. */
+ * num_units*labels_per_unit labels.  *valid = 1/0.
+ * PARITY: the label is pinned on real data; the DECISION RULE (label32 < floor(2^256 / numLabels), strict) is a
+ * recollection of spacemeshos/post and is NOT pinned — worse, the reference's own checkpoint fixture contradicts it as a
+ * universal rule: 16 of its 42 recorded, network-accepted nonces are the arg-min of their POST yet lie above that
+ * threshold (tests/golden/checkpoint_vrf.json, tests/test_gpu_labels.py lists them).  Do not wire this into
+ * Validator.VRFNonce (activation/validation.go:261-282) before checking the rule against libpost; until then use
+ * b200post_vrf_nonce_label and apply the rule the network uses. */
 int b200post_verify_vrf_nonce(uint32_t provider, uint64_t nonce, const uint8_t node_id[32],
                               const uint8_t commitment_atx_id[32], uint32_t num_units,
                               uint64_t labels_per_unit, uint64_t n, int *valid);
+
+/* The policy-free half of the above: label32 at index `nonce` of the identity's POST (through the GPU), for a caller
+ * that applies its own acceptance rule. */
+int b200post_vrf_nonce_label(uint32_t provider, uint64_t nonce, const uint8_t node_id[32], const uint8_t commitment_atx_id[32],
+                             uint64_t n, uint8_t label32[32]);
+
+/* ONE label32 computed on the host CPU from the same arithmetic header the kernels inline.  This is the independent
+ * checker of the fault detector (the reference compares the provider's output with a CPU label and reports
+ * ErrReferenceLabelMismatch, activation/post.go:299-312; b200post_setup_* does that every self_check_every batches).  It
+ * is NOT a compute path: one label per call on the calling thread (~3 ms at N = 8192), nothing falls back to it. */
+int b200post_reference_label(const uint8_t commitment[32], uint64_t index, uint64_t n, uint8_t out32[32]);
 
 /* initialization.Benchmark: labels/s ("hashes/s") of a short N-scrypt run on `provider`. */
 int b200post_benchmark(uint32_t provider, uint64_t n, double seconds, double *labels_per_sec);

@@ -195,3 +195,28 @@ def test_postcli_compatible_cli(b2, orc, tmp_path):
     assert "VRF nonce" in r.stdout
     r = subprocess.run(args[:-5] + ["-provider", "4294967295", "-yes"], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0 and "CPU" in r.stderr
+
+
+def test_fault_injection_trips_the_cpu_reference_check(su, b2, tmp_path):
+    """ErrReferenceLabelMismatch contract (activation/post.go:299-312): a batch whose bytes differ from the label the HOST
+    computes ends the session in state Error with B200POST_ERR_LABEL_MISMATCH, the call returns (no crash, no hang), and
+    nothing of the bad batch is on disk.  The checker is independent of the device (b200post_reference_label)."""
+    mgr = su.PostSetupManager()
+    o = _opts(su, tmp_path, self_check_every=1)
+    mgr.prepare_initializer(o, NODE, ATX)
+    try:
+        b2.set_option("debug_corrupt_check_all", 1)
+        b2.set_option("debug_corrupt_next_batch", 1)
+        with pytest.raises(b2.B200PostError) as e:
+            mgr.start_session()
+        assert e.value.code == su.ERR_LABEL_MISMATCH and "reference label mismatch" in str(e.value)
+        st = mgr.status()
+        assert st.state == su.STATE_ERROR and st.num_labels_written == 0
+        assert "b200post_setup_label_mismatch_total 1" in b2.metrics_text() or "label_mismatch" in b2.metrics_text()
+        # the one-shot fault is gone: the session can be resumed and completes with correct data
+        mgr.prepare_initializer(o, NODE, ATX)
+        mgr.start_session()
+        assert mgr.status().state == su.STATE_COMPLETE
+    finally:
+        b2.set_option("debug_corrupt_check_all", 0)
+        b2.set_option("debug_corrupt_next_batch", 0)

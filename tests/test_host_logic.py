@@ -158,3 +158,14 @@ def test_metrics_text_exposition(b2):
         assert name in t
     for line in t.splitlines():
         assert line.startswith("#") or len(line.split(" ")) == 2
+
+
+def test_reference_label_checker_matches_oracle(b2, orc, golden):
+    """b200post_reference_label (the fault detector's CPU checker inside the product) == oracle; pinned on real data too."""
+    rng = np.random.default_rng(4)
+    for n in (2, 64, 8192):
+        for idx in (0, 2**32, 2**64 - 1, int(rng.integers(0, 2**62))):
+            c = bytes(rng.integers(0, 256, 32, dtype=np.uint8))
+            assert b2.reference_label(c, idx, n) == orc.c_label32(c, idx, n)
+    for it in golden["checkpoint_vrf"]["items"][:4]:
+        assert b2.reference_label(bytes.fromhex(it["commitment"]), it["vrf_nonce"], it["N"]).hex() == it["label32"]
