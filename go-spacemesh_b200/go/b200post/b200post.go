@@ -136,9 +136,11 @@ func InitializeRange(ctx context.Context, provider uint32, commitment [32]byte, 
 		diffPtr = (*C.uint8_t)(unsafe.Pointer(&difficulty[0]))
 		noncePtr = &nonce
 	}
-	rc := C.b200post_labels_range(C.uint32_t(provider), (*C.uint8_t)(unsafe.Pointer(&commitment[0])), C.uint64_t(scryptN),
+	rc, msg := checked(func() C.int {
+		return C.b200post_labels_range(C.uint32_t(provider), (*C.uint8_t)(unsafe.Pointer(&commitment[0])), C.uint64_t(scryptN),
 		C.uint64_t(start), C.uint64_t(count), outPtr, diffPtr, noncePtr, (*C.int)(unsafe.Pointer(&cancel)))
-	if err := statusErr(rc); err != nil {
+	})
+	if err := statusErr(rc, msg); err != nil {
 		return nil, err
 	}
 	if difficulty == nil || nonce.found == 0 {
@@ -160,9 +162,11 @@ func LabelsGather(provider uint32, commitments []byte, indices []uint64, scryptN
 	if n == 0 {
 		return out, nil
 	}
-	rc := C.b200post_labels_gather(C.uint32_t(provider), C.size_t(n), (*C.uint8_t)(unsafe.Pointer(&commitments[0])),
+	rc, msg := checked(func() C.int {
+		return C.b200post_labels_gather(C.uint32_t(provider), C.size_t(n), (*C.uint8_t)(unsafe.Pointer(&commitments[0])),
 		(*C.uint64_t)(unsafe.Pointer(&indices[0])), C.uint64_t(scryptN), (*C.uint8_t)(unsafe.Pointer(&out[0])))
-	return out, statusErr(rc)
+	})
+	return out, statusErr(rc, msg)
 }
 
 // LabelsGatherIndexed is LabelsGather for items that share few commitments (one identity checked at K2
@@ -179,16 +183,20 @@ func LabelsGatherIndexed(provider uint32, commitments []byte, rows []uint32, ind
 	if len(commitments) == 0 {
 		return nil, errors.New("b200post: no commitments")
 	}
-	rc := C.b200post_labels_gather_indexed(C.uint32_t(provider), C.size_t(n), C.size_t(len(commitments)/32),
+	rc, msg := checked(func() C.int {
+		return C.b200post_labels_gather_indexed(C.uint32_t(provider), C.size_t(n), C.size_t(len(commitments)/32),
 		(*C.uint8_t)(unsafe.Pointer(&commitments[0])), (*C.uint32_t)(unsafe.Pointer(&rows[0])),
 		(*C.uint64_t)(unsafe.Pointer(&indices[0])), C.uint64_t(scryptN), (*C.uint8_t)(unsafe.Pointer(&out[0])))
-	return out, statusErr(rc)
+	})
+	return out, statusErr(rc, msg)
 }
 
 // VerifyVRFNonce is the drop-in for verifying.VerifyVRFNonce (activation/validation.go:277).
 func VerifyVRFNonce(provider uint32, nonce uint64, nodeID, commitmentAtxID []byte, numUnits uint32, labelsPerUnit, scryptN uint64) (bool, error) {
 	var valid C.int
-	rc := C.b200post_verify_vrf_nonce(C.uint32_t(provider), C.uint64_t(nonce), (*C.uint8_t)(unsafe.Pointer(&nodeID[0])),
+	rc, msg := checked(func() C.int {
+		return C.b200post_verify_vrf_nonce(C.uint32_t(provider), C.uint64_t(nonce), (*C.uint8_t)(unsafe.Pointer(&nodeID[0])),
 		(*C.uint8_t)(unsafe.Pointer(&commitmentAtxID[0])), C.uint32_t(numUnits), C.uint64_t(labelsPerUnit), C.uint64_t(scryptN), &valid)
-	return valid != 0, statusErr(rc)
+	})
+	return valid != 0, statusErr(rc, msg)
 }

@@ -124,7 +124,9 @@ func (m *SetupManager) PrepareInitializer(opts SetupOpts, nodeID, commitmentAtxI
 	default:
 		o.provider_id = C.int64_t(*opts.ProviderID)
 	}
-	return setupErr(C.b200post_setup_prepare_initializer(m.h, &o, (*C.uint8_t)(unsafe.Pointer(&nodeID[0])), (*C.uint8_t)(unsafe.Pointer(&commitmentAtxID[0]))))
+	return setupErr(checked(func() C.int {
+		return C.b200post_setup_prepare_initializer(m.h, &o, (*C.uint8_t)(unsafe.Pointer(&nodeID[0])), (*C.uint8_t)(unsafe.Pointer(&commitmentAtxID[0])))
+	}))
 }
 
 // StartSession blocks until the data is complete, ctx is cancelled (context.Canceled, state Stopped) or an error.
@@ -139,7 +141,9 @@ func (m *SetupManager) StartSession(ctx context.Context) error {
 		case <-done:
 		}
 	}()
-	return setupErr(C.b200post_setup_start_session(m.h, (*C.int)(unsafe.Pointer(&cancel))))
+	return setupErr(checked(func() C.int {
+		return C.b200post_setup_start_session(m.h, (*C.int)(unsafe.Pointer(&cancel)))
+	}))
 }
 
 func (m *SetupManager) Status() (PostSetupState, uint64) {
@@ -211,8 +215,10 @@ func NewVerifierOn(providers []uint32) (*Verifier, error) {
 		return nil, errors.New("b200post: no providers")
 	}
 	v := &Verifier{}
-	rc := C.b200post_verifier_new_multi((*C.uint32_t)(unsafe.Pointer(&providers[0])), C.int(len(providers)), nil, &v.h)
-	if err := statusErr(rc); err != nil {
+	rc, msg := checked(func() C.int {
+		return C.b200post_verifier_new_multi((*C.uint32_t)(unsafe.Pointer(&providers[0])), C.int(len(providers)), nil, &v.h)
+	})
+	if err := statusErr(rc, msg); err != nil {
 		return nil, err
 	}
 	return v, nil
@@ -286,7 +292,9 @@ func GenerateProof(provider uint32, dataDir string, challenge []byte, cfg SetupC
 	C.memcpy(unsafe.Pointer(&c.pow_difficulty[0]), unsafe.Pointer(&cfg.PowDifficulty[0]), 32)
 	o := C.b200post_prove_opts{provider: C.uint32_t(provider), nonces: C.uint32_t(nonces)}
 	var out C.b200post_proof_out
-	if err := statusErr(C.b200post_generate_proof(dir, (*C.uint8_t)(unsafe.Pointer(&challenge[0])), &c, &o, &out, nil, nil)); err != nil {
+	if err := statusErr(checked(func() C.int {
+		return C.b200post_generate_proof(dir, (*C.uint8_t)(unsafe.Pointer(&challenge[0])), &c, &o, &out, nil, nil)
+	})); err != nil {
 		return nil, err
 	}
 	return &Proof{Nonce: uint32(out.nonce), Pow: uint64(out.pow), Indices: C.GoBytes(unsafe.Pointer(&out.indices[0]), C.int(out.indices_len))}, nil
