@@ -39,6 +39,7 @@ N_SCRYPT = 8192
 BYTES_PER_LABEL = 2 * 128 * N_SCRYPT + 16          # algorithmic HBM bytes per label
 NUM_LABELS_4SU = 4 * 2**32
 METRIC = "POST labels/sec (scrypt N=8192 init)"
+ALU_OPS_PER_BLOCKMIX = 553                         # alu-pipe SASS instructions per BlockMix of the shipped kernel (profiles/)
 HBM_FALLBACK_GBS = 6650.0                          # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -135,28 +136,53 @@ def cpu_baseline(orc, seconds_target: float = 12.0) -> dict:
                       f"[2 = AVX2 x2 labels, 3 = AVX-512 x4], {cores} pthreads, {t:.1f} s)"}
 
 
-def bench_verify(b2, provider: int, n_proofs: int = 10000, k2: int = 37) -> dict:
+def _valid_proofs(b2, vf, pr, provider: int, n_identities: int, k2: int, labels_per_id: int, k1: int):
+    """Real valid proofs at N = 8192: each identity's small POST (labels_per_id labels) is initialised on the GPU and proven
+    with the product's scan; the verifier must accept them.  Returns [(Proof, ProofMetadata)]."""
+    import numpy as np
+    rng = np.random.default_rng(11)
+    out = []
+    for _ in range(n_identities):
+        node_id, atx, ch = (bytes(rng.integers(0, 256, 32, dtype=np.uint8)) for _ in range(3))
+        labels, _ = b2.labels_range(b2.commitment(node_id, atx), N_SCRYPT, 0, labels_per_id, provider=provider)
+        nonce, packed, pow_, _ = pr.prove_scan(labels, ch, 16, [0], k1, k2, labels_per_id, provider=provider)
+        out.append((vf.Proof(nonce, packed, pow_), vf.ProofMetadata(node_id, atx, ch, 1, labels_per_id)))
+    return out
+
+
+def bench_verify(b2, provider: int, orc=None, n_proofs: int = 10000, k2: int = 37) -> dict:
     """BASELINE.json configs[2]: PostVerifier batch, 10 000 proofs x K2 = 37 indices, N = 8192, one B200.
-    Synthetic proofs (seed 3): distinct identities, indices uniform in a 4-SU space (so verdicts are mostly
-    "invalid"); every requested label is recomputed on the GPU regardless of the verdict.  Timed end to end through b200post_verify_batch with host
-    buffers: index unpack + key derivation (host), H2D, gather kernels, D2H, AES compare (host)."""
+    MIXED batch: half the proofs are VALID (real proofs of small POSTs initialised and proven on this GPU, repeated),
+    half have one index bumped (systest/tests/distributed_post_verification_test.go:254-256) and are rejected at a known
+    position.  Timed end to end through b200post_verify_batch with host buffers: index unpack + key derivation (host),
+    H2D, gather kernels, on-device AES verdict, D2H.  `with_k2pow` adds the RandomX check of every proof (device).
+    The CPU side is MEASURED: the oracle recomputes the K2 labels of a sample of the same proofs on all host cores and
+    judges them (what verifying.ProofVerifier.Verify does per proof on NumCPU/2 workers, activation/post.go:101-111)."""
     import numpy as np
     vf = importlib.import_module("go-spacemesh_b200.verify")
-    rng = np.random.default_rng(3)
-    num_labels = NUM_LABELS_4SU
-    bits = vf.bits_per_index(num_labels)
-    ids = rng.integers(0, 256, (n_proofs, 96), dtype=np.uint8)
-    idx = rng.integers(0, num_labels, (n_proofs, k2), dtype=np.uint64)
-    proofs = [vf.Proof(int(i % 288), vf.pack_indices(idx[i].tolist(), bits), int(i)) for i in range(n_proofs)]
-    metas = [vf.ProofMetadata(ids[i, :32].tobytes(), ids[i, 32:64].tobytes(), ids[i, 64:].tobytes(), 4, 2**32)
-             for i in range(n_proofs)]
-    params = vf.VerifyParams(k1=2**32 - 1, k2=k2, scrypt_n=N_SCRYPT)   # difficulty ~2^62: ~25 % of labels pass
+    pr = importlib.import_module("go-spacemesh_b200.prove")
+    labels_per_id, k1 = 4096, 96
+    bits = vf.bits_per_index(labels_per_id)
+    base = _valid_proofs(b2, vf, pr, provider, 48, k2, labels_per_id, k1)
+    params = vf.VerifyParams(k1=k1, k2=k2, scrypt_n=N_SCRYPT)
+    proofs, metas, expect_bad = [], [], []
+    for i in range(n_proofs):
+        p, m = base[i % len(base)]
+        if i % 2 == 0:
+            proofs.append(p); expect_bad.append(None)
+        else:
+            idx = vf.unpack_indices(p.indices, bits, k2)
+            pos = (i // 2) % k2
+            idx[pos] = (idx[pos] + 1) % labels_per_id
+            proofs.append(vf.Proof(p.nonce, vf.pack_indices(idx, bits), p.pow)); expect_bad.append(pos)
+        metas.append(m)
     batch = vf.PreparedBatch(proofs, metas, params)     # C structs built once: the timed region is the C-ABI call
     warm_walls = []
     for _ in range(2):      # warm-up at full size: grow-only judge buffers sized, any speculative init layer drained
         t0 = time.perf_counter()
-        batch.run(provider)
+        batch.run(provider, "skip")
         warm_walls.append(time.perf_counter() - t0)
+
     def stage_us():
         out = {}
         for ln in b2.metrics_text().splitlines():
@@ -167,18 +193,104 @@ def bench_verify(b2, provider: int, n_proofs: int = 10000, k2: int = 37) -> dict
     launches0 = b2.launch_count()
     s0 = stage_us()
     t0 = time.perf_counter()
-    st, _ = batch.run(provider)
+    st, bad = batch.run(provider, "skip")
     wall = time.perf_counter() - t0
     s1 = stage_us()
-    return {"workload": f"{n_proofs} proofs x K2={k2}, N=8192, 4-SU index space, synthetic (seed 3)",
-            "proofs": n_proofs, "k2": k2, "labels_recomputed": n_proofs * k2, "seconds": wall,
-            "proofs_per_s": n_proofs / wall, "labels_per_s": n_proofs * k2 / wall,
-            "gpu_device_ms": b2.last_call_ms(provider),
-            "host_prepare_ms": (s1.get("verify_prepare_us_total", 0) - s0.get("verify_prepare_us_total", 0)) / 1e3,
-            "gather_judge_wall_ms": (s1.get("verify_gather_judge_us_total", 0) - s0.get("verify_gather_judge_us_total", 0)) / 1e3,
-            "gpu_launches": int(b2.launch_count() - launches0),
-            "warmup_seconds": warm_walls, "invalid": int(sum(1 for x in st if x != 0)),
-            "note": "k2pow (RandomX) check not included; verdict conventions unpinned (DESIGN.md §2)"}
+    n_valid = sum(1 for x in st if x == 0)
+    # a tampered index may still qualify by chance (probability ~ k1 / labels): only rejected ones must name the position
+    positions_ok = all(e is None or s == 0 or b == e for s, b, e in zip(st, bad, expect_bad))
+    valid_ok = all(s == 0 for s, e in zip(st, expect_bad) if e is None)
+    # with the k2pow (RandomX) check of every proof on the device; pow_difficulty = ff..ff so that verdicts do not change
+    batch.run(provider, "builtin")
+    t0 = time.perf_counter()
+    st_pow, _ = batch.run(provider, "builtin")
+    wall_pow = time.perf_counter() - t0
+    # latency of small batches (one proof per Verify call is the reference's shape, activation/post_verifier.go:303-350)
+    latency = []
+    for n in (1, 16, 256):
+        small = vf.PreparedBatch(proofs[:n], metas[:n], params)
+        small.run(provider, "skip")
+        best = min(_timed(lambda: small.run(provider, "skip")) for _ in range(3))
+        latency.append({"proofs": n, "ms": 1e3 * best, "gpu_device_ms": b2.last_call_ms(provider)})
+    res = {"workload": f"{n_proofs} proofs x K2={k2}, N=8192: 50 % valid (real proofs of {len(base)} small POSTs, repeated), 50 % with one index bumped",
+           "proofs": n_proofs, "k2": k2, "labels_recomputed": n_proofs * k2, "seconds": wall,
+           "proofs_per_s": n_proofs / wall, "labels_per_s": n_proofs * k2 / wall,
+           "valid": n_valid, "invalid": n_proofs - n_valid, "valid_proofs_all_accepted": valid_ok,
+           "rejected_at_the_bumped_position": positions_ok,
+           "gpu_device_ms": b2.last_call_ms(provider),
+           "host_prepare_ms": (s1.get("verify_prepare_us_total", 0) - s0.get("verify_prepare_us_total", 0)) / 1e3,
+           "gather_judge_wall_ms": (s1.get("verify_gather_judge_us_total", 0) - s0.get("verify_gather_judge_us_total", 0)) / 1e3,
+           "gpu_launches": int(b2.launch_count() - launches0), "warmup_seconds": warm_walls,
+           "with_k2pow": {"seconds": wall_pow, "proofs_per_s": n_proofs / wall_pow, "same_verdicts": list(st_pow) == list(st),
+                          "note": "one RandomX hash per proof on the device, all proofs of the batch in one k2pow batch"},
+           "latency": latency,
+           "note": "verdict conventions (AES keys, index packing, K3 subset) unpinned (DESIGN.md §2); label function pinned"}
+    if orc is not None:
+        # measured CPU verifier: K2 label recomputations of a sample of the SAME proofs on all host cores + the judge
+        sample = 64
+        comms = np.concatenate([np.tile(np.frombuffer(orc.py_commitment(metas[i].node_id, metas[i].commitment_atx_id), dtype=np.uint8), (k2, 1))
+                                for i in range(sample)])
+        idxs = np.array([v for i in range(sample) for v in vf.unpack_indices(proofs[i].indices, bits, k2)], dtype=np.uint64)
+        threads = orc.default_threads()
+        t0 = time.perf_counter()
+        labs = orc.c_labels_gather(comms, idxs, N_SCRYPT, threads=threads)
+        diff = orc.py_proving_difficulty(k1, labels_per_id)
+        verdicts = []
+        for i in range(sample):
+            ok = all(orc.py_label_passes(labs[i * k2 + j].tobytes(), metas[i].challenge, proofs[i].nonce, proofs[i].pow, diff) for j in range(k2))
+            verdicts.append(ok)
+        cpu_wall = time.perf_counter() - t0
+        res["cpu_baseline"] = {"proofs_per_s": sample / cpu_wall, "cores": threads, "kind": "port", "measured": True,
+                               "sample": f"{sample} of the same proofs: {sample * k2} labels via oracle/post_oracle.c on {threads} threads + AES judge",
+                               "verdicts_equal_gpu": verdicts == [s == 0 for s in st[:sample]]}
+    return res
+
+
+def _timed(fn) -> float:
+    t0 = time.perf_counter()
+    fn()
+    return time.perf_counter() - t0
+
+
+def bench_k2pow(b2, provider: int, with_cpu: bool) -> dict:
+    """BASELINE.json configs[4] on one GPU: k2pow (RandomX) nonce search over one challenge, difficulty 0 so that nothing
+    stops it early; hashes/s over whole device batches (device time from the engine's CUDA events), dataset resident.
+    CPU side: the oracle port (interpreter, fast mode, all host threads) on a bounded sample."""
+    import numpy as np
+    k2 = importlib.import_module("go-spacemesh_b200.k2pow")
+    rng = np.random.default_rng(5)
+    ch, node = bytes(rng.integers(0, 256, 8, dtype=np.uint8)), bytes(rng.integers(0, 256, 32, dtype=np.uint8))
+    t0 = time.perf_counter()
+    k2.prepare(provider=provider)
+    dataset_s = time.perf_counter() - t0
+    n = k2.batch_size(provider)
+    k2.search(0, ch, node, b"\x00" * 32, 0, n, provider=provider)          # warm-up batch
+    launches0 = b2.launch_count()
+    found, done = k2.search(0, ch, node, b"\x00" * 32, n, 2 * n, provider=provider)
+    tm = k2.last_timing(provider)
+    sample = k2.hashes(0, ch, node, 3 * n, 32, provider=provider)
+    res = {"workload": "k2pow nonce search, one challenge, difficulty 0 (no early exit), RandomX fast mode (2080 MiB dataset in HBM)",
+           "hashes": done, "hashes_per_s": done / (tm["total_ms"] / 1e3), "device_ms": tm["total_ms"], "vm_kernel_ms": tm["vm_kernel_ms"],
+           "vm_kernel_share": tm["vm_kernel_ms"] / tm["total_ms"], "batch": n, "batch_latency_ms": tm["total_ms"] / max(1, done // n),
+           "scratchpad_gib": n * 2 / 1024, "dataset_build_s": dataset_s, "gpu_launches": int(b2.launch_count() - launches0),
+           "vm_mode": b2.get_option("rx_vm_mode"),
+           "parity": "RandomX pinned on its official vectors through this engine (tests/test_gpu_k2pow.py); k2pow input layout unpinned"}
+    if with_cpu:
+        from oracle import pyrandomx as orx
+        c = orx.Cache(orx.K2POW_CACHE_KEY)
+        try:
+            threads = orx.default_threads()
+            t0 = time.perf_counter(); c.init_dataset(threads); ds = time.perf_counter() - t0
+            probe, _, secs = c.k2pow_scan(0, ch, node, 3 * n, 32, threads=min(32, threads))
+            res["sample_equals_oracle"] = bool((probe == sample).all())
+            rate = 32 / secs * max(1, threads / min(32, threads))
+            count = int(max(threads * 4, min(rate * 10.0, 1 << 16)))
+            _, _, secs = c.k2pow_scan(0, ch, node, 0, count, threads=threads, want_hashes=False)
+            res["cpu_baseline"] = {"hashes_per_s": count / secs, "cores": threads, "kind": "port",
+                                   "sample": f"{count} hashes, oracle/randomx_oracle.c (interpreter, AES-NI, fast mode; dataset built in {ds:.1f} s), {secs:.1f} s"}
+        finally:
+            c.close()
+    return res
 
 
 def run_reference(args, rank: int, world: int) -> None:
@@ -219,6 +331,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=0, help="labels per step per GPU (0 = 16 layers ~ 2^20, the reference's default ComputeBatchSize)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the configs[2] verify-batch measurement")
+    ap.add_argument("--no-k2pow", action="store_true", help="skip the configs[4] k2pow (RandomX) measurement")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -341,17 +454,27 @@ def main() -> None:
     labels_per_launch = romix_labels / max(romix_k, 1)     # label-equivalents per ROMix launch (engine-counted)
     romix_avg_ms = romix_ms / max(romix_k, 1)
     achieved = labels_per_launch * BYTES_PER_LABEL / (romix_avg_ms / 1e3) / 1e9 if romix_avg_ms > 0 else 0.0
-    traffic = None
+    # dram__bytes of one launch comes from an `ncu --set full` capture (a number measured under ncu is never a bench value,
+    # so it cannot be taken live here); the file records which build it was captured on
+    traffic, traffic_src = None, None
     tfile = ROOT / "profiles" / "romix_dram_bytes_per_launch.json"
     if tfile.exists():
         try:
-            traffic = json.loads(tfile.read_text()).get("dram_bytes_per_launch")
+            tj = json.loads(tfile.read_text())
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("captured_on", "round-1 build (stale for this build)")
         except Exception:  # noqa: BLE001
             traffic = None
 
     verify_extra = None
+    k2pow_extra = None
     if world == 1 and not args.no_verify:
-        verify_extra = bench_verify(b2, local_rank)
+        orc_mod = None
+        if not args.no_cpu_baseline:
+            from oracle import pyoracle as orc_mod
+            orc_mod.build()
+        verify_extra = bench_verify(b2, local_rank, orc_mod)
+    if world == 1 and not args.no_k2pow:
+        k2pow_extra = bench_k2pow(b2, local_rank, with_cpu=not args.no_cpu_baseline)
 
     # ALU ceiling probe (N = 1 only): the same ROMix arithmetic with no scratchpad traffic ("nomem" variant; its
     # outputs are not labels).  The label kernel is integer-issue-bound, so this — not the HBM peak — is the
@@ -387,11 +510,13 @@ def main() -> None:
             "e2e": {"value": e2e_value, "unit": "labels/s", "h2d_bytes_per_step": 32 + 32, "d2h_bytes_per_step": batch * 16 + 48},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "romix_pipe_kernel" if b2.get_option("romix_variant") == 4 else "romix_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          # integer roofline of the label function: 2N BlockMix x 553 alu-pipe instructions (512 XOR/rotate
                          # of two ChaCha20/8 cores + 41 XOR/address, counted in the SASS) = 9.06 M per label, at the
                          # measured 64 ops/clk/SM (profiles/r01_alubench.log) and the maximum SM clock
-                         "int_roofline_labels_per_s": prov["sm_count"] * 64 * 1.965e9 / (16384 * 553),
+                         "int_roofline_labels_per_s": prov["sm_count"] * 64 * (clocks["sm_mhz"] * 1e6 if clocks and clocks.get("sm_mhz") else 1.965e9) / (16384 * ALU_OPS_PER_BLOCKMIX),
+                         "int_roofline_at_max_clock_labels_per_s": prov["sm_count"] * 64 * (clocks["sm_max_mhz"] * 1e6 if clocks and clocks.get("sm_max_mhz") else 1.965e9) / (16384 * ALU_OPS_PER_BLOCKMIX),
+                         "int_roofline_clock": "median SM clock sampled during the timed region" if clocks and clocks.get("sm_mhz") else "nominal 1.965 GHz (no nvidia-smi sample)",
                          "alu_ceiling_labels_per_s": alu_probe,
                          "frac_of_alu_ceiling": (labels_per_launch / (romix_avg_ms / 1e3) / alu_probe) if alu_probe and romix_avg_ms > 0 else None,
                          "bytes_per_label": BYTES_PER_LABEL, "labels_per_launch": labels_per_launch,
@@ -401,13 +526,12 @@ def main() -> None:
         }
         if verify_extra:
             line["verify"] = verify_extra
+        if k2pow_extra:
+            line["k2pow"] = k2pow_extra
         if not args.no_cpu_baseline and world == 1:      # the CPU baseline is an N = 1 measurement
             from oracle import pyoracle as orc
             orc.build()
             line["cpu_baseline"] = cpu_baseline(orc)
-            if verify_extra:
-                # the reference verifies one proof per worker call: K2 label recomputations on host cores
-                line["verify"]["cpu_baseline_proofs_per_s"] = line["cpu_baseline"]["value"] / verify_extra["k2"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
