@@ -10,6 +10,7 @@
 #include "../../include/post_compat.h"
 #include "engine.h"
 #include "host_hash.h"
+#include "randomx_engine.h"
 
 using namespace b200post;
 
@@ -285,7 +286,7 @@ int b200post_reference_label(const uint8_t commitment[32], uint64_t index, uint6
     return B200POST_OK;
 }
 
-void b200post_shutdown(void) { shutdown_all(); }
+void b200post_shutdown(void) { randomx_shutdown_all(); shutdown_all(); }
 
 // ------------------------------------------------------------------------------------------------
 // libpost-compatible symbols (include/post_compat.h)

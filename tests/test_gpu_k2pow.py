@@ -104,3 +104,29 @@ def test_scale_difficulty(k2):
     d = bytes.fromhex("000dfb23b0979b4b" + "00" * 24)
     for units in (1, 4, 7, 1000):
         assert k2.scale_difficulty(d, units) == orx.scale_pow_difficulty(d, units)
+
+
+def test_search_over_several_devices(k2, b2):
+    """b200post_k2pow_search_multi: batch-interleaved nonce ranges, one host thread per device, same answer as one device
+    (BASELINE.json configs[4] shards the nonce range over the box's GPUs; no data-path collective — SURVEY.md §8e)."""
+    gpus = [p["id"] for p in b2.providers()]
+    if len(gpus) < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(8)
+    ch, node = bytes(rng.integers(0, 256, 8, dtype=np.uint8)), bytes(rng.integers(0, 256, 32, dtype=np.uint8))
+    old = b2.get_option("rx_vms_per_sm")
+    try:
+        b2.set_option("rx_vms_per_sm", 2)
+        batch = k2.batch_size()
+        n = 5 * batch + 17
+        hs = k2.hashes(0, ch, node, 0, n)
+        order = sorted(range(n), key=lambda i: bytes(hs[i]))
+        thr = bytes(hs[order[1]])                                   # exactly one nonce of the range is below it
+        found, done = k2.search(0, ch, node, thr, 0, n, providers=gpus[:2])
+        assert found == order[0] and done <= n
+        found1, _ = k2.search(0, ch, node, thr, 0, n, provider=gpus[0])
+        assert found1 == found
+        none, done = k2.search(0, ch, node, b"\x00" * 32, 0, n, providers=gpus[:2])
+        assert none is None and done == n
+    finally:
+        b2.set_option("rx_vms_per_sm", old)
