@@ -3,8 +3,8 @@
 
 Workload (BASELINE.json configs[1]): 4-SU init, scrypt N = 8192, r = p = 1, single B200, labels
 discarded ("/dev/null").  One *step* = one batch of `--batch` consecutive labels of the 2^34-label
-index space (default: 16 layers of resident scratchpads ~ 1.2 M labels; the reference's default
-ComputeBatchSize is 2^20), exactly what one `initialize(start, end)`
+index space (default: 72 layers of resident scratchpads ~ 5.5 M labels ~ 3 s, so that the driver's 20 steps sample
+~10^8 labels / a minute of steady state per arm; the reference's default ComputeBatchSize is 2^20), exactly what one `initialize(start, end)`
 call of the reference's initializer does per ComputeBatchSize batch (activation/post.go:295).
 
   value      labels/s with the output resident in HBM (b200post_labels_range_dev), device-timed
@@ -328,7 +328,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=0, help="labels per step per GPU (0 = 16 layers ~ 2^20, the reference's default ComputeBatchSize)")
+    ap.add_argument("--batch", type=int, default=0, help="labels per step per GPU (0 = 72 layers of resident scratchpads ~ 5.5 M labels ~ 3 s: 20 steps sample ~ 10^8 labels / 60 s of steady state, SURVEY.md §8d cfg2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the configs[2] verify-batch measurement")
     ap.add_argument("--no-k2pow", action="store_true", help="skip the configs[4] k2pow (RandomX) measurement")
@@ -364,7 +364,7 @@ def main() -> None:
 
     wave = b2.wave_slots(N_SCRYPT, provider=local_rank)                    # resident scratchpads per wave
     tpb = b2.get_option("tpb")
-    batch = args.batch or 16 * wave
+    batch = args.batch or 72 * wave
     d_out = torch.empty((batch, 16), dtype=torch.uint8, device=dev)        # labels stay in HBM for `value`
     h_out = np.empty((batch, 16), dtype=np.uint8)                          # host sink for `e2e`
 

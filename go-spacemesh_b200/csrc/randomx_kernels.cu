@@ -250,7 +250,7 @@ enum : uint8_t { W_NOP, W_IADD_RS, W_ISUB_R, W_IMUL_R, W_IMULH_R, W_ISMULH_R, W_
                  W_CBRANCH, W_CFROUND, W_ISTORE,
                  W_FSWAP, W_FADD_R, W_FSUB_R, W_FSCAL, W_FMUL_R, W_FSQRT, W_FADD_M, W_FSUB_M, W_FDIV_M, W_COUNT };
 __device__ __forceinline__ u32 wpack(u32 op, u32 dslot, u32 sslot, u32 aux) { return op | (aux << 8) | ((sslot * 8) << 16) | ((dslot * 8) << 24); }
-constexpr u32 kL1Mask = (kScratchpadL1 - 1) & ~7u, kL2Mask = (kScratchpadL2 - 1) & ~7u, kL3Mask = (kScratchpadL3 - 1) & ~7u;
+constexpr u32 kL3Mask = (kScratchpadL3 - 1) & ~7u;
 constexpr u32 kL3Mask64 = (kScratchpadL3 - 1) & ~63u;
 constexpr u32 kDatasetAlignMask = (u32)((kDatasetBase - 1) & ~63ull);
 
