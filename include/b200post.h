@@ -104,6 +104,17 @@ int b200post_labels_range_multi(const uint32_t *providers, int n_providers, cons
                                 const uint8_t *vrf_difficulty, b200post_vrf_nonce *nonce,
                                 const volatile int *cancel);
 
+/* One PROCESS per GPU (the deployment bench.py measures): each rank initialises its own contiguous shard with
+ * b200post_labels_range and the ranks then agree on the VRF nonce — the path's only exchange step — with an NCCL
+ * all-gather of one 64-byte record per rank and a local lexicographic arg-min (lowest label32, then lowest index).
+ * Rank 0 obtains an id, hands it to the others by whatever channel the host has, every rank calls _init, then _min once
+ * per batch.  libnccl.so.2 is loaded at first use; B200POST_ERR_UNSUPPORTED if it cannot be. */
+typedef struct b200post_vrf_comm b200post_vrf_comm;
+int b200post_vrf_comm_unique_id(uint8_t out128[128]);
+int b200post_vrf_comm_init(uint32_t provider, int rank, int world, const uint8_t id128[128], b200post_vrf_comm **out);
+int b200post_vrf_comm_min(b200post_vrf_comm *comm, const b200post_vrf_nonce *mine, b200post_vrf_nonce *best);
+void b200post_vrf_comm_free(b200post_vrf_comm *comm);
+
 /* labels at scattered (commitment, index) pairs: commitments = n_items x 32 bytes (HOST),
  * indices = n_items u64 (HOST), out16 = n_items x 16 bytes (HOST). */
 int b200post_labels_gather(uint32_t provider, size_t n_items, const uint8_t *commitments,

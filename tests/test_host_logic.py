@@ -169,3 +169,16 @@ def test_reference_label_checker_matches_oracle(b2, orc, golden):
             assert b2.reference_label(c, idx, n) == orc.c_label32(c, idx, n)
     for it in golden["checkpoint_vrf"]["items"][:4]:
         assert b2.reference_label(bytes.fromhex(it["commitment"]), it["vrf_nonce"], it["N"]).hex() == it["label32"]
+
+
+def test_vrf_comm_needs_a_device_and_valid_arguments(b2):
+    """b200post_vrf_comm_* (the C library's NCCL min-reduce for one-process-per-GPU hosts): argument checks on a CPU box."""
+    L = b2.lib()
+    L.b200post_vrf_comm_init.argtypes = [ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+    comm = ctypes.c_void_p()
+    assert L.b200post_vrf_comm_init(0, 2, 2, bytes(128), ctypes.byref(comm)) == b2.ERR_INVALID_ARGUMENT      # rank >= world
+    assert L.b200post_vrf_comm_init(0, 0, 1, None, ctypes.byref(comm)) == b2.ERR_INVALID_ARGUMENT
+    if not b2.providers():
+        rc = L.b200post_vrf_comm_init(0, 0, 1, bytes(128), ctypes.byref(comm))
+        assert rc in (b2.ERR_NO_DEVICE, b2.ERR_UNSUPPORTED) and not comm
+    L.b200post_vrf_comm_free(None)
