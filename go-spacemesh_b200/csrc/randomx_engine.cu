@@ -37,7 +37,7 @@ RandomxEngine::~RandomxEngine() {
 }
 
 void RandomxEngine::release_batch() {
-    cudaFree(buf_.scratchpads); cudaFree(buf_.program); cudaFree(buf_.rcp); cudaFree(buf_.seed); cudaFree(buf_.regfile);
+    cudaFree(buf_.scratchpads); cudaFree(buf_.hot); cudaFree(buf_.program); cudaFree(buf_.rcp); cudaFree(buf_.seed); cudaFree(buf_.regfile);
     cudaFree(buf_.config); cudaFree(buf_.fprc); cudaFree(buf_.hashes);
     buf_ = rx::BatchBuffers{};
     cap_ = 0;
@@ -97,11 +97,12 @@ int RandomxEngine::ensure_batch(uint32_t want) {
     for (uint32_t cap = want;; cap = std::max<uint32_t>(32, cap / 2 / 32 * 32)) {
         size_t free_b = 0, total_b = 0;
         RX_TRY(cudaMemGetInfo(&free_b, &total_b));
-        const size_t per_vm = (size_t)rx::kScratchpadL3 + 256 * 8 + rx::kRcpSlots * 8 + 64 + 256 + 32 + 1 + 32;
+        const size_t per_vm = (size_t)rx::kScratchpadL3 + rx::kScratchpadL1 + 256 * 8 + rx::kRcpSlots * 8 + 64 + 256 + 32 + 1 + 32;
         if ((size_t)cap * per_vm + ((size_t)256 << 20) <= free_b) {
             rx::BatchBuffers b;
             b.stride = cap;
             cudaError_t e = cudaMalloc(&b.scratchpads, (size_t)cap * rx::kScratchpadL3);
+            if (e == cudaSuccess) e = cudaMalloc(&b.hot, (size_t)cap * rx::kScratchpadL1);
             if (e == cudaSuccess) e = cudaMalloc(&b.program, (size_t)cap * 256 * sizeof(uint2));
             if (e == cudaSuccess) e = cudaMalloc(&b.rcp, (size_t)cap * rx::kRcpSlots * 8);
             if (e == cudaSuccess) e = cudaMalloc(&b.seed, (size_t)cap * 64);
@@ -115,6 +116,21 @@ int RandomxEngine::ensure_batch(uint32_t want) {
             release_batch();
         }
         if (cap == 32) { set_error("not enough HBM for one warp of RandomX scratchpads (2 MiB each)"); return B200POST_ERR_OUT_OF_MEMORY; }
+    }
+    // keep the hot plane in L2: a persisting access-policy window on the engine's stream (as much of it as the device allows)
+    if (options().rx_l2_persist.load() != 0) {
+        const size_t hot_bytes = (size_t)cap_ * rx::kScratchpadL1;
+        size_t persist = std::min<size_t>(hot_bytes, (size_t)prop_.persistingL2CacheMaxSize);
+        if (persist && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
+            cudaStreamAttrValue attr{};
+            attr.accessPolicyWindow.base_ptr = buf_.hot;
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(hot_bytes, (size_t)prop_.accessPolicyMaxWindowSize);
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist / (double)attr.accessPolicyWindow.num_bytes);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(stream_, cudaStreamAttributeAccessPolicyWindow, &attr);
+        }
+        cudaGetLastError();
     }
     if ((size_t)cap_ * 32 > stage_cap_) {
         cudaFreeHost(h_stage_); h_stage_ = nullptr; stage_cap_ = 0;

@@ -187,7 +187,7 @@ __global__ void seed_k2pow_kernel(u64 *__restrict__ seed, u32 stride, u32 n, K2p
 
 // ---------------------------------------------------------------------------------------------- scratchpad fill / hash
 // 4 lanes per VM: lane c owns AES column c of the 64-byte generator state (columns 0,2 decrypt, 1,3 encrypt)
-__global__ void __launch_bounds__(256) fill_kernel(u64 *__restrict__ seed, u32 stride, u32 n, uint8_t *__restrict__ scratchpads) {
+__global__ void __launch_bounds__(256) fill_kernel(u64 *__restrict__ seed, u32 stride, u32 n, uint8_t *__restrict__ scratchpads, uint8_t *__restrict__ hot) {
     __shared__ AesSmem sm;
     aes_load(sm);
     const u32 gid = blockIdx.x * blockDim.x + threadIdx.x, vm = gid >> 2, col = gid & 3;
@@ -198,16 +198,17 @@ __global__ void __launch_bounds__(256) fill_kernel(u64 *__restrict__ seed, u32 s
 #pragma unroll
     for (int i = 0; i < 4; i++) k[i] = c_gen1_keys[4 * col + i];
     uint4 *out = reinterpret_cast<uint4 *>(scratchpads + (size_t)vm * kScratchpadL3) + col;
+    uint4 *out_hot = reinterpret_cast<uint4 *>(hot + (size_t)vm * kScratchpadL1) + col;   // the first 16 KiB live in the hot plane
     const bool dec = (col & 1) == 0;
     for (u32 i = 0; i < kScratchpadL3 / 64; i++) {
         if (dec) aes_dec(sm, s, k); else aes_enc(sm, s, k);
-        out[4 * (size_t)i] = make_uint4(s[0], s[1], s[2], s[3]);
+        (i < kScratchpadL1 / 64 ? out_hot : out)[4 * (size_t)i] = make_uint4(s[0], s[1], s[2], s[3]);
     }
     seed[(size_t)(2 * col) * stride + vm] = (u64)s[0] | ((u64)s[1] << 32);
     seed[(size_t)(2 * col + 1) * stride + vm] = (u64)s[2] | ((u64)s[3] << 32);
 }
 // AesHash1R: the scratchpad is the key stream (columns 0,2 encrypt, 1,3 decrypt), two fixed finishing rounds -> a0..a3
-__global__ void __launch_bounds__(256) hash_scratchpad_kernel(u64 *__restrict__ regfile, u32 stride, u32 n, const uint8_t *__restrict__ scratchpads) {
+__global__ void __launch_bounds__(256) hash_scratchpad_kernel(u64 *__restrict__ regfile, u32 stride, u32 n, const uint8_t *__restrict__ scratchpads, const uint8_t *__restrict__ hot) {
     __shared__ AesSmem sm;
     aes_load(sm);
     const u32 gid = blockIdx.x * blockDim.x + threadIdx.x, vm = gid >> 2, col = gid & 3;
@@ -215,16 +216,18 @@ __global__ void __launch_bounds__(256) hash_scratchpad_kernel(u64 *__restrict__ 
     u32 s[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) s[i] = c_hash_state[4 * col + i];
-    const uint4 *in = reinterpret_cast<const uint4 *>(scratchpads + (size_t)vm * kScratchpadL3) + col;
+    const uint4 *in_cold = reinterpret_cast<const uint4 *>(scratchpads + (size_t)vm * kScratchpadL3) + col;
+    const uint4 *in_hot = reinterpret_cast<const uint4 *>(hot + (size_t)vm * kScratchpadL1) + col;
+    auto key_at = [&](u32 i) { return (i < kScratchpadL1 / 64 ? in_hot : in_cold)[4 * (size_t)i]; };
     const bool enc = (col & 1) == 0;
     constexpr u32 kRounds = kScratchpadL3 / 64;
     uint4 nxt[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) nxt[j] = in[4 * (size_t)j];
+    for (int j = 0; j < 4; j++) nxt[j] = key_at(j);
     for (u32 i = 0; i < kRounds; i += 4) {
         uint4 cur[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) { cur[j] = nxt[j]; if (i + 4 + j < kRounds) nxt[j] = in[4 * (size_t)(i + 4 + j)]; }   // keys do not depend on the state: prefetch
+        for (int j = 0; j < 4; j++) { cur[j] = nxt[j]; if (i + 4 + j < kRounds) nxt[j] = key_at(i + 4 + j); }   // keys do not depend on the state: prefetch
 #pragma unroll
         for (int j = 0; j < 4; j++) { const u32 k[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w}; if (enc) aes_enc(sm, s, k); else aes_dec(sm, s, k); }
     }
@@ -423,6 +426,8 @@ __device__ __forceinline__ double u2d(u64 v) { return __longlong_as_double((long
 // what it needs, and every lane executes the whole instruction redundantly (both halves of an FP register too): no
 // cross-lane dependency inside the program loop, no warp synchronisation; the lanes split up only for the 64-byte
 // scratchpad / dataset lines around it.  39 SASS instructions per VM instruction (ncu), issue-bound.
+__device__ __forceinline__ uint8_t *sp_byte(uint8_t *cold, uint8_t *hot, u32 addr) { return (addr < kScratchpadL1 ? hot : cold) + addr; }
+
 template <int WARPS, int MIN_CTAS>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) execute_kernel(BatchBuffers b, u32 n, const uint8_t *__restrict__ dataset) {
     __shared__ uint2 prog_all[WARPS][kProgramSize];
@@ -446,11 +451,13 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) execute_kernel(BatchBuff
     const uint8_t *ds = dataset + (c1 & ((1ull << 60) - 1));
     u32 mode = b.fprc[vm];
     uint8_t *sp = b.scratchpads + (size_t)vm * kScratchpadL3;
+    uint8_t *sph = b.hot + (size_t)vm * kScratchpadL1;      // offsets below 16 KiB (75 % of the accesses) go to the hot plane
     constexpr u64 kEMant = (1ull << 56) - 1;
     const uint8_t *rb = reinterpret_cast<const uint8_t *>(regs);
 #define RD(off) (*reinterpret_cast<const u64 *>(rb + (off)))
 #define WR(off, v) (*reinterpret_cast<u64 *>(const_cast<uint8_t *>(rb) + (off)) = (v))
-#define SPAD(addr) (*reinterpret_cast<u64 *>(sp + (addr)))
+#define SPTR(addr) sp_byte(sp, sph, (addr))
+#define SPAD(addr) (*reinterpret_cast<u64 *>(SPTR(addr)))
 
     u32 sp0 = mx, sp1 = ma;
     for (int it = 0; it < kProgramIterations; it++) {
@@ -460,7 +467,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) execute_kernel(BatchBuff
         __syncwarp();                                    // everyone has read `mix` before lanes overwrite their slots
         if (lane < 8) regs[lane] ^= SPAD(sp0 + 8 * lane);
         else if (lane < 24) {
-            const int x = *reinterpret_cast<const int *>(sp + sp1 + 4 * (lane - 8));
+            const int x = *reinterpret_cast<const int *>(SPTR(sp1 + 4 * (lane - 8)));
             const u64 bits = d2u((double)x);
             regs[lane] = lane >= 16 ? ((bits & kEMant) | emask_lane) : bits;
         }
@@ -552,6 +559,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) execute_kernel(BatchBuff
 #undef RD
 #undef WR
 #undef SPAD
+#undef SPTR
 }
 
 // ---------------------------------------------------------------------------------------------- chain seed / final hash
@@ -639,7 +647,7 @@ cudaError_t launch_seed_k2pow(const BatchBuffers &b, uint32_t n, const K2powTemp
     return cudaGetLastError();
 }
 cudaError_t launch_fill_scratchpads(const BatchBuffers &b, uint32_t n, cudaStream_t s) {
-    fill_kernel<<<blocks_for((u64)n * 4, 256), 256, 0, s>>>(reinterpret_cast<u64 *>(b.seed), b.stride, n, b.scratchpads);
+    fill_kernel<<<blocks_for((u64)n * 4, 256), 256, 0, s>>>(reinterpret_cast<u64 *>(b.seed), b.stride, n, b.scratchpads, b.hot);
     return cudaGetLastError();
 }
 cudaError_t launch_program(const BatchBuffers &b, uint32_t n, bool first_program, cudaStream_t s) {
@@ -660,7 +668,7 @@ cudaError_t launch_chain_seed(const BatchBuffers &b, uint32_t n, cudaStream_t s)
     return cudaGetLastError();
 }
 cudaError_t launch_finalize(const BatchBuffers &b, uint32_t n, cudaStream_t s) {
-    hash_scratchpad_kernel<<<blocks_for((u64)n * 4, 256), 256, 0, s>>>(reinterpret_cast<u64 *>(b.regfile), b.stride, n, b.scratchpads);
+    hash_scratchpad_kernel<<<blocks_for((u64)n * 4, 256), 256, 0, s>>>(reinterpret_cast<u64 *>(b.regfile), b.stride, n, b.scratchpads, b.hot);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     chain_seed_kernel<<<blocks_for(n, 128), 128, 0, s>>>(b, n, true);

@@ -16,6 +16,8 @@ constexpr int kRcpSlots = 32;              // resolved IMUL_RCP reciprocals kept
 struct BatchBuffers {
     uint32_t stride = 0;
     uint8_t *scratchpads = nullptr;        // stride x 2 MiB, VM-major (a VM's accesses are private and data-dependent)
+    uint8_t *hot = nullptr;                // stride x 16 KiB: every VM's first 16 KiB (the "L1" level, 3 of 4 scratchpad operands),
+                                           // packed into one plane that the L2 and the TLB can hold; the 2 MiB areas keep the rest
     uint2 *program = nullptr;              // [stride][256] decoded instructions (8 bytes each)
     uint64_t *rcp = nullptr;               // [stride][kRcpSlots]
     uint64_t *seed = nullptr;              // [8][stride]   the 64-byte generator state / program seed
