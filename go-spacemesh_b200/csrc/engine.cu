@@ -112,7 +112,7 @@ int DeviceEngine::ensure(uint64_t N, uint64_t want_slots) {
     const size_t per_slot = 128 * (size_t)N * pads;
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = (size_t)((double)(free_b + v_bytes_) * 0.90);
+    size_t budget = (size_t)((double)(free_b + v_bytes_) * 0.95);   // 0.95: one layer (148 GiB at defaults) still fits after the k2pow engine (dataset 2 GiB + a batch of scratchpads, ~16 GiB) has allocated first
     const int64_t cap_mib = o.max_scratch_mib.load();
     if (cap_mib > 0) budget = std::min(budget, (size_t)cap_mib << 20);
     const size_t per_cta_layer = per_slot * (size_t)tpb * (size_t)prop_.multiProcessorCount;

@@ -21,7 +21,7 @@ struct Options {
     std::atomic<int64_t> tpb{512};             // pipelined default: one 16-warp CTA per SM (measured best)
     std::atomic<int64_t> dr_unroll{4};         // pipelined kernel: ChaCha double-rounds unrolled (4) or rolled (1)
     std::atomic<int64_t> ctas_per_sm{0};       // 0 = occupancy maximum
-    std::atomic<int64_t> max_scratch_mib{0};   // 0 = 90 % of free HBM
+    std::atomic<int64_t> max_scratch_mib{0};   // 0 = 95 % of free HBM
     std::atomic<int64_t> speculate_next{1};    // pipelined range jobs of >= 4 layers pre-fill the next range's first layer
     std::atomic<int64_t> lowlat_max_labels{4096};   // jobs of at most this many labels take the low-latency ROMix kernel (0 = never)
     std::atomic<int64_t> rx_vms_per_sm{0};     // k2pow: RandomX VMs (2 MiB scratchpads) resident per SM in one batch; 0 = the mode's default

@@ -76,7 +76,7 @@ const char *b200post_last_error(void);
  *   "romix_variant"  4 pipelined (default) | 0 direct | 1 coalesced | 2 bulk(TMA) | 3 nomem (ALU probe, NOT labels)
  *   "rotate_mask"    form of the ChaCha rotates: 0 = all SHF, 1 = the 16- and 8-bit rotates as PRMT
  *   "tpb" 64|128|256|512 (64 and 512 only for the pipelined kernel; default 512) ; "dr_unroll" 4|1 ; "ctas_per_sm" 0 = as many as fit ;
- *   "max_scratch_mib" 0 = 90 % of free HBM ; "debug_skip_phase" diagnostics only.
+ *   "max_scratch_mib" 0 = 95 % of free HBM ; "debug_skip_phase" diagnostics only.
  * Returns B200POST_ERR_INVALID_ARGUMENT for an unknown key or value. */
 int b200post_set_option(const char *key, int64_t value);
 int64_t b200post_get_option(const char *key);
