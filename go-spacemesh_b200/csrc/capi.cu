@@ -84,7 +84,6 @@ int b200post_set_option(const char *key, int64_t value) {
     if (k == "debug_corrupt_next_batch" && (value == 0 || value == 1)) { o.debug_corrupt_next_batch = value; return B200POST_OK; }
     if (k == "debug_corrupt_check_all" && (value == 0 || value == 1)) { o.debug_corrupt_check_all = value; return B200POST_OK; }
     if (k == "lowlat_max_labels" && value >= 0 && value <= (1 << 20)) { o.lowlat_max_labels = value; return B200POST_OK; }
-    if (k == "rx_l2_persist" && (value == 0 || value == 1)) { o.rx_l2_persist = value; return B200POST_OK; }
     if (k == "rx_vm_mode" && value >= 0 && value <= 2) { o.rx_vm_mode = value; return B200POST_OK; }
     if (k == "rx_vms_per_sm" && value >= 0 && value <= 4096) { o.rx_vms_per_sm = value; return B200POST_OK; }
     if (k == "debug_skip_phase" && value >= 0 && value <= 3) { o.debug_skip_phase = value; return B200POST_OK; }
@@ -105,7 +104,6 @@ int64_t b200post_get_option(const char *key) {
     if (k == "speculate_next") return o.speculate_next;
     if (k == "rx_vms_per_sm") return o.rx_vms_per_sm;
     if (k == "rx_vm_mode") return o.rx_vm_mode;
-    if (k == "rx_l2_persist") return o.rx_l2_persist;
     if (k == "lowlat_max_labels") return o.lowlat_max_labels;
     if (k == "debug_skip_phase") return o.debug_skip_phase;
     return -1;

@@ -25,7 +25,6 @@ struct Options {
     std::atomic<int64_t> speculate_next{1};    // pipelined range jobs of >= 4 layers pre-fill the next range's first layer
     std::atomic<int64_t> lowlat_max_labels{4096};   // jobs of at most this many labels take the low-latency ROMix kernel (0 = never)
     std::atomic<int64_t> rx_vms_per_sm{0};     // k2pow: RandomX VMs (2 MiB scratchpads) resident per SM in one batch; 0 = the mode's default
-    std::atomic<int64_t> rx_l2_persist{1};     // k2pow: persisting-L2 window over the scratchpads' hot plane (0 = off, for A/B)
     std::atomic<int64_t> rx_vm_mode{1};        // k2pow VM kernel variant: 0 = 32 VMs/SM (<= 64 regs), 1 = 48 VMs/SM (default), 2 = 64 VMs/SM
     std::atomic<int64_t> debug_corrupt_next_batch{0};   // tests: flip one bit in the next init batch before the self-check (one-shot)
     std::atomic<int64_t> debug_corrupt_check_all{0};    // tests: make the self-check look at the label the injected fault hits
