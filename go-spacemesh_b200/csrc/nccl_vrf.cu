@@ -36,9 +36,12 @@ Nccl *nccl() {
     static Nccl n;
     static std::once_flag once;
     std::call_once(once, [] {
+        // An NCCL already in the process (e.g. the one a PyTorch host bundles) is reused; otherwise the system's is loaded,
+        // privately.  The loader de-duplicates by soname, so a host that also loads another libnccl.so.2 must load it FIRST.
+        n.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
         for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
-            n.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
             if (n.lib) break;
+            n.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
         }
         if (!n.lib) return;
         n.get_id = (fn_get_id)dlsym(n.lib, "ncclGetUniqueId");
@@ -85,9 +88,9 @@ int b200post_vrf_comm_unique_id(uint8_t out128[128]) {
 int b200post_vrf_comm_init(uint32_t provider, int rank, int world, const uint8_t id128[128], b200post_vrf_comm **out) {
     if (!out || !id128 || world < 1 || rank < 0 || rank >= world) { set_error("invalid argument"); return B200POST_ERR_INVALID_ARGUMENT; }
     *out = nullptr;
-    Nccl *n = nccl();
-    if (!n) return B200POST_ERR_UNSUPPORTED;
     if (!engine_for(provider)) return provider == B200POST_CPU_PROVIDER_ID ? B200POST_ERR_UNSUPPORTED : B200POST_ERR_NO_DEVICE;
+    Nccl *n = nccl();                  // loaded only once a device is there to use it
+    if (!n) return B200POST_ERR_UNSUPPORTED;
     if (cudaSetDevice((int)provider) != cudaSuccess) { set_error("cudaSetDevice failed"); return B200POST_ERR_CUDA; }
     b200post_vrf_comm *c = new b200post_vrf_comm;
     c->dev = (int)provider; c->world = world; c->rank = rank;

@@ -178,7 +178,7 @@ def test_vrf_comm_needs_a_device_and_valid_arguments(b2):
     comm = ctypes.c_void_p()
     assert L.b200post_vrf_comm_init(0, 2, 2, bytes(128), ctypes.byref(comm)) == b2.ERR_INVALID_ARGUMENT      # rank >= world
     assert L.b200post_vrf_comm_init(0, 0, 1, None, ctypes.byref(comm)) == b2.ERR_INVALID_ARGUMENT
-    if not b2.providers():
+    if not b2.providers():             # (with a device this would load libnccl into the test process: left to tests/test_gpu_nccl_vrf.py)
         rc = L.b200post_vrf_comm_init(0, 0, 1, bytes(128), ctypes.byref(comm))
-        assert rc in (b2.ERR_NO_DEVICE, b2.ERR_UNSUPPORTED) and not comm
+        assert rc == b2.ERR_NO_DEVICE and not comm
     L.b200post_vrf_comm_free(None)
