@@ -130,3 +130,13 @@ def test_search_over_several_devices(k2, b2):
         assert none is None and done == n
     finally:
         b2.set_option("rx_vms_per_sm", old)
+
+
+def test_committed_golden_fixture(k2, golden):
+    """tests/golden/k2pow.json (oracle/gen_golden_k2pow.py): RandomX's own vectors and oracle-computed k2pow hashes."""
+    g = golden["k2pow"]
+    for it in g["randomx_kat"]:
+        assert k2.randomx_hash(it["key"].encode(), [bytes.fromhex(it["input_hex"])])[0].hex() == it["hash"]
+    for it in g["k2pow"]:
+        got = k2.hashes(it["nonce_group"], bytes.fromhex(it["challenge8"]), bytes.fromhex(it["node_id"]), it["pow"], 1)
+        assert bytes(got[0]).hex() == it["hash"]

@@ -157,3 +157,16 @@ def test_k2pow_input_layout_and_scan(cache000):
     _, found, _ = cache000.k2pow_scan(7, ch, node, 100, 6, difficulty=thr, threads=2)
     assert found == 100 + int(np.argmin([int.from_bytes(bytes(h), "big") for h in hashes]))
     assert rx.scale_pow_difficulty(b"\x00\x0d" + b"\xff" * 30, 4) == ((int.from_bytes(b"\x00\x0d" + b"\xff" * 30, "big")) // 4).to_bytes(32, "big")
+
+
+def test_oracle_reproduces_the_committed_k2pow_fixture():
+    import json
+    from pathlib import Path
+    g = json.loads((Path(__file__).resolve().parent / "golden" / "k2pow.json").read_text())
+    c = rx.Cache(g["cache_key"].encode())
+    try:
+        for it in g["k2pow"]:
+            inp = rx.k2pow_input(it["pow"], it["nonce_group"], bytes.fromhex(it["challenge8"]), bytes.fromhex(it["node_id"]))
+            assert c.hash(inp).hex() == it["hash"]
+    finally:
+        c.close()
