@@ -20,6 +20,15 @@ for lowlat in (4096, 0):
         out["gather"].append({"lowlat_max_labels": lowlat, "labels": n, "device_ms": round(best_dev, 2), "wall_ms": round(best_wall, 2)})
         print(json.dumps(out["gather"][-1]), flush=True)
 pkg.set_option("lowlat_max_labels", 4096)
+out["rotate_form"] = []
+for mask in (0, 1):          # 16/8-bit rotates as SHF (0) or PRMT (1): does the form change the serial chain's latency?
+    pkg.set_option("rotate_mask", mask)
+    comms = rng.integers(0, 256, (37, 32), dtype=np.uint8); idx = rng.integers(0, 2**34, 37, dtype=np.uint64)
+    pkg.labels_gather(comms, idx, 8192)
+    best = min((pkg.labels_gather(comms, idx, 8192), pkg.last_call_ms())[1] for _ in range(3))
+    out["rotate_form"].append({"rotate_mask": mask, "labels": 37, "device_ms": round(best, 3)})
+    print(json.dumps(out["rotate_form"][-1]), flush=True)
+pkg.set_option("rotate_mask", 0)
 k2, num_labels = 37, 2**34
 bits = vf.bits_per_index(num_labels)
 params = vf.VerifyParams(k1=2**31, k2=k2, scrypt_n=8192)
