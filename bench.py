@@ -358,6 +358,11 @@ def main() -> None:
         raise SystemExit("bench.py needs a CUDA device: the label engine has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # the contract is ONE JSON line on stdout: libraries that print there (NCCL announces its version on stdout when
+    # NCCL_DEBUG is set in the environment) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -535,7 +540,10 @@ def main() -> None:
             from oracle import pyoracle as orc
             orc.build()
             line["cpu_baseline"] = cpu_baseline(orc)
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
