@@ -101,8 +101,6 @@ int b200post_k2pow_search_multi(const uint32_t *providers, int n_providers, cons
     std::vector<std::string> errs(n_providers);
     volatile int any_hit = 0;
     std::vector<std::thread> th;
-    const uint64_t old_opt = (uint64_t)options().rx_vms_per_sm.load();
-    (void)old_opt;
     for (int i = 0; i < n_providers; i++)
         th.emplace_back([&, i] {
             const uint64_t first = start + (uint64_t)i * batch;
