@@ -531,7 +531,8 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) execute_kernel(BatchBuff
                 case W_FDIV_M: { FP_M(mlo, mhi);
                                  const double dlo = u2d((d2u(mlo) & kEMant) | emask_lo), dhi = u2d((d2u(mhi) & kEMant) | emask_hi);
                                  WR(doff, d2u(div_rm(u2d(RD(doff)), dlo, mode))); WR(doff + 8, d2u(div_rm(u2d(RD(doff + 8)), dhi, mode))); } break;
-                default: break;
+                case W_NOP: break;
+                default: __builtin_unreachable();     // the decoder emits nothing else: lets the jump table drop its range check
             }
 #undef MEMADDR
 #undef FP_M
