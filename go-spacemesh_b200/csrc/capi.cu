@@ -84,7 +84,7 @@ int b200post_set_option(const char *key, int64_t value) {
     if (k == "debug_corrupt_next_batch" && (value == 0 || value == 1)) { o.debug_corrupt_next_batch = value; return B200POST_OK; }
     if (k == "debug_corrupt_check_all" && (value == 0 || value == 1)) { o.debug_corrupt_check_all = value; return B200POST_OK; }
     if (k == "lowlat_max_labels" && value >= 0 && value <= (1 << 20)) { o.lowlat_max_labels = value; return B200POST_OK; }
-    if (k == "rx_vm_mode" && value >= 0 && value <= 2) { o.rx_vm_mode = value; return B200POST_OK; }
+    if (k == "rx_vm_mode" && value >= 0 && value <= 3) { o.rx_vm_mode = value; return B200POST_OK; }
     if (k == "rx_vms_per_sm" && value >= 0 && value <= 4096) { o.rx_vms_per_sm = value; return B200POST_OK; }
     if (k == "debug_skip_phase" && value >= 0 && value <= 3) { o.debug_skip_phase = value; return B200POST_OK; }
     set_error("unknown option or value out of range: " + k);

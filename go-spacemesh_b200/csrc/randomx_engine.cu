@@ -45,7 +45,7 @@ void RandomxEngine::release_batch() {
 
 uint32_t RandomxEngine::desired_batch() const {
     int64_t per_sm = options().rx_vms_per_sm.load();
-    if (per_sm <= 0) per_sm = options().rx_vm_mode.load() == 0 ? 32 : (options().rx_vm_mode.load() == 1 ? 48 : 64);   // = resident warps per SM of the variant
+    if (per_sm <= 0) { const int64_t m = options().rx_vm_mode.load(); per_sm = m == 0 ? 32 : m == 1 ? 48 : m == 2 ? 64 : 40; }   // = resident warps per SM of the variant
     return (uint32_t)std::min<int64_t>((int64_t)prop_.multiProcessorCount * per_sm, 1 << 20);
 }
 

@@ -394,6 +394,23 @@ __device__ __forceinline__ double mul_rm(double a, double c, u32 mode) {
         default: return __dmul_rz(a, c);
     }
 }
+// both halves of an FP register under ONE branch on the (warp-uniform) rounding mode
+__device__ __forceinline__ void add2_rm(double &r0, double &r1, double a0, double b0, double a1, double b1, u32 mode) {
+    switch (mode) {
+        case 0: r0 = __dadd_rn(a0, b0); r1 = __dadd_rn(a1, b1); break;
+        case 1: r0 = __dadd_rd(a0, b0); r1 = __dadd_rd(a1, b1); break;
+        case 2: r0 = __dadd_ru(a0, b0); r1 = __dadd_ru(a1, b1); break;
+        default: r0 = __dadd_rz(a0, b0); r1 = __dadd_rz(a1, b1); break;
+    }
+}
+__device__ __forceinline__ void mul2_rm(double &r0, double &r1, double a0, double b0, double a1, double b1, u32 mode) {
+    switch (mode) {
+        case 0: r0 = __dmul_rn(a0, b0); r1 = __dmul_rn(a1, b1); break;
+        case 1: r0 = __dmul_rd(a0, b0); r1 = __dmul_rd(a1, b1); break;
+        case 2: r0 = __dmul_ru(a0, b0); r1 = __dmul_ru(a1, b1); break;
+        default: r0 = __dmul_rz(a0, b0); r1 = __dmul_rz(a1, b1); break;
+    }
+}
 // e-group values are positive and finite (spec §4.3.2): directed rounding = round-to-nearest, then step one ulp against
 // the sign of the exact residual.  residual = fma(-q, b, a) is exact for a correctly rounded quotient / root.
 __device__ __forceinline__ double fix_positive(double q, double residual, u32 mode) {
@@ -518,16 +535,16 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) execute_kernel(BatchBuff
                 case W_CFROUND: { const u64 s = RD(soff); mode = (u32)((s >> aux) | (s << ((64 - aux) & 63))) & 3; } break;
                 case W_ISTORE: SPAD((u32)(RD(doff) + simm) & ((1u << aux) - 8u)) = RD(soff); break;
                 case W_FSWAP: { const u64 lo = RD(doff), hi = RD(doff + 8); WR(doff, hi); WR(doff + 8, lo); } break;
-                case W_FADD_R: { const double lo = add_rm(u2d(RD(doff)), u2d(RD(soff)), mode), hi = add_rm(u2d(RD(doff + 8)), u2d(RD(soff + 8)), mode);
+                case W_FADD_R: { double lo, hi; add2_rm(lo, hi, u2d(RD(doff)), u2d(RD(soff)), u2d(RD(doff + 8)), u2d(RD(soff + 8)), mode);
                                  WR(doff, d2u(lo)); WR(doff + 8, d2u(hi)); } break;
-                case W_FSUB_R: { const double lo = add_rm(u2d(RD(doff)), -u2d(RD(soff)), mode), hi = add_rm(u2d(RD(doff + 8)), -u2d(RD(soff + 8)), mode);
+                case W_FSUB_R: { double lo, hi; add2_rm(lo, hi, u2d(RD(doff)), -u2d(RD(soff)), u2d(RD(doff + 8)), -u2d(RD(soff + 8)), mode);
                                  WR(doff, d2u(lo)); WR(doff + 8, d2u(hi)); } break;
                 case W_FSCAL: WR(doff, RD(doff) ^ 0x80F0000000000000ull); WR(doff + 8, RD(doff + 8) ^ 0x80F0000000000000ull); break;
-                case W_FMUL_R: { const double lo = mul_rm(u2d(RD(doff)), u2d(RD(soff)), mode), hi = mul_rm(u2d(RD(doff + 8)), u2d(RD(soff + 8)), mode);
+                case W_FMUL_R: { double lo, hi; mul2_rm(lo, hi, u2d(RD(doff)), u2d(RD(soff)), u2d(RD(doff + 8)), u2d(RD(soff + 8)), mode);
                                  WR(doff, d2u(lo)); WR(doff + 8, d2u(hi)); } break;
                 case W_FSQRT: { const double lo = sqrt_rm(u2d(RD(doff)), mode), hi = sqrt_rm(u2d(RD(doff + 8)), mode); WR(doff, d2u(lo)); WR(doff + 8, d2u(hi)); } break;
-                case W_FADD_M: { FP_M(mlo, mhi); WR(doff, d2u(add_rm(u2d(RD(doff)), mlo, mode))); WR(doff + 8, d2u(add_rm(u2d(RD(doff + 8)), mhi, mode))); } break;
-                case W_FSUB_M: { FP_M(mlo, mhi); WR(doff, d2u(add_rm(u2d(RD(doff)), -mlo, mode))); WR(doff + 8, d2u(add_rm(u2d(RD(doff + 8)), -mhi, mode))); } break;
+                case W_FADD_M: { FP_M(mlo, mhi); double lo, hi; add2_rm(lo, hi, u2d(RD(doff)), mlo, u2d(RD(doff + 8)), mhi, mode); WR(doff, d2u(lo)); WR(doff + 8, d2u(hi)); } break;
+                case W_FSUB_M: { FP_M(mlo, mhi); double lo, hi; add2_rm(lo, hi, u2d(RD(doff)), -mlo, u2d(RD(doff + 8)), -mhi, mode); WR(doff, d2u(lo)); WR(doff + 8, d2u(hi)); } break;
                 case W_FDIV_M: { FP_M(mlo, mhi);
                                  const double dlo = u2d((d2u(mlo) & kEMant) | emask_lo), dhi = u2d((d2u(mhi) & kEMant) | emask_hi);
                                  WR(doff, d2u(div_rm(u2d(RD(doff)), dlo, mode))); WR(doff + 8, d2u(div_rm(u2d(RD(doff + 8)), dhi, mode))); } break;
@@ -660,6 +677,7 @@ cudaError_t launch_execute(const BatchBuffers &b, uint32_t n, const uint64_t *d_
     switch (variant) {
         case 1: execute_kernel<2, 24><<<blocks_for(n, 2), 64, 0, s>>>(b, n, ds); break;    // <= 42 registers: 48 warps per SM
         case 2: execute_kernel<2, 32><<<blocks_for(n, 2), 64, 0, s>>>(b, n, ds); break;    // <= 32 registers: 64 warps per SM
+        case 3: execute_kernel<2, 20><<<blocks_for(n, 2), 64, 0, s>>>(b, n, ds); break;    // <= 51 registers: 40 warps per SM
         default: execute_kernel<1, 32><<<n, 32, 0, s>>>(b, n, ds); break;                  // <= 64 registers: 32 warps per SM
     }
     return cudaGetLastError();
