@@ -450,21 +450,22 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) execute_kernel(BatchBuff
     __shared__ uint2 prog_all[WARPS][kProgramSize];
     __shared__ u64 rcp_all[WARPS][kRcpSlots];
     __shared__ u64 regs_all[WARPS][32];
+    __shared__ u64 emask_all[WARPS][2];      // e-register exponent masks (lo, hi): read by the loop prologue and FDIV_M only
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, vm = blockIdx.x * WARPS + wid;
     if (vm >= n) return;
     uint2 *prog = prog_all[wid];
     u64 *rcp = rcp_all[wid], *regs = regs_all[wid];
+    const u64 *emask = emask_all[wid];
     for (int i = lane; i < kProgramSize; i += 32) prog[i] = b.program[(size_t)vm * kProgramSize + i];
     rcp[lane] = b.rcp[(size_t)vm * kRcpSlots + lane];
     const u32 stride = b.stride;
     regs[lane] = lane >= 24 ? b.regfile[(size_t)lane * stride + vm] : 0;
     __syncwarp();
     const u64 c0 = b.config[vm], c1 = b.config[(size_t)stride + vm];
-    const u64 emask_lo = b.config[(size_t)2 * stride + vm], emask_hi = b.config[(size_t)3 * stride + vm];
-    const u64 emask_lane = (lane & 1) ? emask_hi : emask_lo;
+    if (lane < 2) emask_all[wid][lane] = b.config[(size_t)(2 + lane) * stride + vm];
+    __syncwarp();
     u32 ma = (u32)c0, mx = (u32)(c0 >> 32);
     const u32 rr = (u32)(c1 >> 60);
-    const int rr0 = rr & 1, rr1 = 2 + ((rr >> 1) & 1), rr2 = 4 + ((rr >> 2) & 1), rr3 = 6 + ((rr >> 3) & 1);
     const uint8_t *ds = dataset + (c1 & ((1ull << 60) - 1));
     u32 mode = b.fprc[vm];
     uint8_t *sp = b.scratchpads + (size_t)vm * kScratchpadL3;
@@ -478,7 +479,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) execute_kernel(BatchBuff
 
     u32 sp0 = mx, sp1 = ma;
     for (int it = 0; it < kProgramIterations; it++) {
-        const u64 mix = regs[rr0] ^ regs[rr1];
+        const u64 mix = regs[rr & 1] ^ regs[2 + ((rr >> 1) & 1)];
         sp0 = (sp0 ^ (u32)mix) & kL3Mask64;
         sp1 = (sp1 ^ (u32)(mix >> 32)) & kL3Mask64;
         __syncwarp();                                    // everyone has read `mix` before lanes overwrite their slots
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) execute_kernel(BatchBuff
         else if (lane < 24) {
             const int x = *reinterpret_cast<const int *>(SPTR(sp1 + 4 * (lane - 8)));
             const u64 bits = d2u((double)x);
-            regs[lane] = lane >= 16 ? ((bits & kEMant) | emask_lane) : bits;
+            regs[lane] = lane >= 16 ? ((bits & kEMant) | emask[lane & 1]) : bits;
         }
         __syncwarp();
 
@@ -546,7 +547,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) execute_kernel(BatchBuff
                 case W_FADD_M: { FP_M(mlo, mhi); double lo, hi; add2_rm(lo, hi, u2d(RD(doff)), mlo, u2d(RD(doff + 8)), mhi, mode); WR(doff, d2u(lo)); WR(doff + 8, d2u(hi)); } break;
                 case W_FSUB_M: { FP_M(mlo, mhi); double lo, hi; add2_rm(lo, hi, u2d(RD(doff)), -mlo, u2d(RD(doff + 8)), -mhi, mode); WR(doff, d2u(lo)); WR(doff + 8, d2u(hi)); } break;
                 case W_FDIV_M: { FP_M(mlo, mhi);
-                                 const double dlo = u2d((d2u(mlo) & kEMant) | emask_lo), dhi = u2d((d2u(mhi) & kEMant) | emask_hi);
+                                 const double dlo = u2d((d2u(mlo) & kEMant) | emask[0]), dhi = u2d((d2u(mhi) & kEMant) | emask[1]);
                                  WR(doff, d2u(div_rm(u2d(RD(doff)), dlo, mode))); WR(doff + 8, d2u(div_rm(u2d(RD(doff + 8)), dhi, mode))); } break;
                 case W_NOP: break;
                 default: __builtin_unreachable();     // the decoder emits nothing else: lets the jump table drop its range check
@@ -555,7 +556,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) execute_kernel(BatchBuff
 #undef FP_M
         }
 
-        mx = (mx ^ (u32)(regs[rr2] ^ regs[rr3])) & kDatasetAlignMask;
+        mx = (mx ^ (u32)(regs[4 + ((rr >> 2) & 1)] ^ regs[6 + ((rr >> 3) & 1)])) & kDatasetAlignMask;
         if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(ds + mx));
         __syncwarp();                                    // program-loop writes (all lanes, same values) settle before the lanes split
         if (lane < 8) {
