@@ -445,24 +445,29 @@ __device__ __forceinline__ double u2d(u64 v) { return __longlong_as_double((long
 // scratchpad / dataset lines around it.  39 SASS instructions per VM instruction (ncu), issue-bound.
 __device__ __forceinline__ uint8_t *sp_byte(uint8_t *cold, uint8_t *hot, u32 addr) { return (addr < kScratchpadL1 ? hot : cold) + addr; }
 
-template <int WARPS, int MIN_CTAS>
-__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) execute_kernel(BatchBuffers b, u32 n, const uint8_t *__restrict__ dataset) {
-    __shared__ uint2 prog_all[WARPS][kProgramSize];
-    __shared__ u64 rcp_all[WARPS][kRcpSlots];
-    __shared__ u64 regs_all[WARPS][32];
-    __shared__ u64 emask_all[WARPS][2];      // e-register exponent masks (lo, hi): read by the loop prologue and FDIV_M only
-    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, vm = blockIdx.x * WARPS + wid;
-    if (vm >= n) return;
-    uint2 *prog = prog_all[wid];
-    u64 *rcp = rcp_all[wid], *regs = regs_all[wid];
-    const u64 *emask = emask_all[wid];
+// Per-warp shared state of the VM kernel.  The interpreter body is instantiated once per warp slot of the CTA (W is a
+// template argument), so every shared-memory address in it is a link-time constant plus a field of the instruction word:
+// no per-warp base register, no address arithmetic in the handlers.
+template <int WARPS>
+struct VmShared {
+    uint2 prog[WARPS][kProgramSize];
+    u64 rcp[WARPS][kRcpSlots];
+    u64 regs[WARPS][32];
+    u64 emask[WARPS][2];      // e-register exponent masks (lo, hi): read by the loop prologue and FDIV_M only
+};
+
+template <int WARPS, int W>
+__device__ __forceinline__ void vm_run(VmShared<WARPS> &sh, const BatchBuffers &b, u32 vm, u32 lane, const uint8_t *__restrict__ dataset) {
+    uint2 *prog = sh.prog[W];
+    u64 *rcp = sh.rcp[W], *regs = sh.regs[W];
+    const u64 *emask = sh.emask[W];
     for (int i = lane; i < kProgramSize; i += 32) prog[i] = b.program[(size_t)vm * kProgramSize + i];
     rcp[lane] = b.rcp[(size_t)vm * kRcpSlots + lane];
     const u32 stride = b.stride;
     regs[lane] = lane >= 24 ? b.regfile[(size_t)lane * stride + vm] : 0;
     __syncwarp();
     const u64 c0 = b.config[vm], c1 = b.config[(size_t)stride + vm];
-    if (lane < 2) emask_all[wid][lane] = b.config[(size_t)(2 + lane) * stride + vm];
+    if (lane < 2) sh.emask[W][lane] = b.config[(size_t)(2 + lane) * stride + vm];
     __syncwarp();
     u32 ma = (u32)c0, mx = (u32)(c0 >> 32);
     const u32 rr = (u32)(c1 >> 60);
@@ -494,7 +499,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) execute_kernel(BatchBuff
         for (int pc = 0; pc < kProgramSize; pc++) {
             const uint2 ins = prog[pc];
             const u32 w = ins.x;
-            const u32 doff = w >> 24, soff = (w >> 16) & 255, aux = (w >> 8) & 255;
+            const u32 doff = w >> 24, soff = __byte_perm(w, 0, 0x4442), aux = __byte_perm(w, 0, 0x4441);   // one PRMT each
             const u64 simm = sext(ins.y);
 #define MEMADDR ((u32)(RD(soff) + simm) & ((1u << aux) - 8u))
 #define FP_M(lo, hi) const u64 mv_ = SPAD(MEMADDR); const double lo = (double)(int)(u32)mv_, hi = (double)(int)(u32)(mv_ >> 32)
@@ -579,6 +584,15 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) execute_kernel(BatchBuff
 #undef WR
 #undef SPAD
 #undef SPTR
+}
+
+template <int WARPS, int MIN_CTAS>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) execute_kernel(BatchBuffers b, u32 n, const uint8_t *__restrict__ dataset) {
+    __shared__ VmShared<WARPS> sh;
+    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, vm = blockIdx.x * WARPS + wid;
+    if (vm >= n) return;
+    if (WARPS == 1 || wid == 0) vm_run<WARPS, 0>(sh, b, vm, lane, dataset);
+    else vm_run<WARPS, WARPS - 1>(sh, b, vm, lane, dataset);
 }
 
 // ---------------------------------------------------------------------------------------------- chain seed / final hash
