@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) hash_scratchpad_kernel(u64 *__restrict__ 
 enum : uint8_t { T_IADD_RS, T_IADD_M, T_ISUB_R, T_ISUB_M, T_IMUL_R, T_IMUL_M, T_IMULH_R, T_IMULH_M, T_ISMULH_R, T_ISMULH_M, T_IMUL_RCP,
                  T_INEG_R, T_IXOR_R, T_IXOR_M, T_IROR_R, T_IROL_R, T_ISWAP_R, T_FSWAP_R, T_FADD_R, T_FADD_M, T_FSUB_R, T_FSUB_M,
                  T_FSCAL_R, T_FMUL_R, T_FDIV_M, T_FSQRT_R, T_CBRANCH, T_CFROUND, T_ISTORE, T_NOP, T_COUNT };
-// Decoded instruction (8 bytes): word0 = op | aux << 8 | (src slot * 8) << 16 | (dst slot * 8) << 24, word1 = imm32.
+// Decoded instruction (8 bytes): word0 = (src slot * 8) | op << 8 | aux << 16 | (dst slot * 8) << 24, word1 = imm32.
 // Dense opcodes, one per (operation, operand kind), so each handler touches only what it needs; slot fields are byte
 // offsets into the register file in shared memory (slots: 0-7 r, 8-15 f lo/hi, 16-23 e lo/hi, 24-31 a lo/hi);
 // aux = shift / rotate count / reciprocal slot / log2 of the scratchpad level size.
@@ -251,8 +251,10 @@ enum : uint8_t { W_NOP, W_IADD_RS, W_ISUB_R, W_IMUL_R, W_IMULH_R, W_ISMULH_R, W_
                  W_IADD_M, W_ISUB_M, W_IMUL_M, W_IMULH_M, W_ISMULH_M, W_IXOR_M,
                  W_IADD_A, W_ISUB_A, W_IMUL_A, W_IMULH_A, W_ISMULH_A, W_IXOR_A,
                  W_CBRANCH, W_CFROUND, W_ISTORE,
-                 W_FSWAP, W_FADD_R, W_FSUB_R, W_FSCAL, W_FMUL_R, W_FSQRT, W_FADD_M, W_FSUB_M, W_FDIV_M, W_COUNT };
-__device__ __forceinline__ u32 wpack(u32 op, u32 dslot, u32 sslot, u32 aux) { return op | (aux << 8) | ((sslot * 8) << 16) | ((dslot * 8) << 24); }
+                 W_FSWAP, W_FADD_R, W_FSUB_R, W_FSCAL, W_FMUL_R, W_FSQRT, W_FADD_M, W_FSUB_M, W_FDIV_M,
+                 W_END,       // sentinel the VM kernel appends after the 256th instruction: the program loop has no counter
+                 W_COUNT };
+__device__ __forceinline__ u32 wpack(u32 op, u32 dslot, u32 sslot, u32 aux) { return (sslot * 8) | (op << 8) | (aux << 16) | ((dslot * 8) << 24); }
 constexpr u32 kL3Mask = (kScratchpadL3 - 1) & ~7u;
 constexpr u32 kL3Mask64 = (kScratchpadL3 - 1) & ~63u;
 constexpr u32 kDatasetAlignMask = (u32)((kDatasetBase - 1) & ~63ull);
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(128) program_kernel(BatchBuffers b, u32 n, boo
                     case T_FSQRT_R: w0 = wpack(W_FSQRT, 16 + 2 * (dst & 3), 0, 0); break;
                     case T_CBRANCH: {
                         const u32 shift = (mod >> 4) + 8;
-                        w0 = W_CBRANCH | (shift << 8) | ((u32)(usage[dst][t] + 1) << 16) | ((dst * 8) << 24);   // src field = target + 1 (not scaled)
+                        w0 = (u32)(usage[dst][t] + 1) | (W_CBRANCH << 8) | (shift << 16) | ((dst * 8) << 24);   // src field = target + 1 (not scaled)
                         w1 = (imm | (1u << shift)) & ~(1u << (shift - 1));
 #pragma unroll
                         for (int r = 0; r < 8; r++) usage[r][t] = (short)i;
@@ -378,55 +380,44 @@ __global__ void __launch_bounds__(128) program_kernel(BatchBuffers b, u32 n, boo
 }
 
 // ---------------------------------------------------------------------------------------------- the VM
-__device__ __forceinline__ double add_rm(double a, double c, u32 mode) {
-    switch (mode) {
-        case 0: return __dadd_rn(a, c);
-        case 1: return __dadd_rd(a, c);
-        case 2: return __dadd_ru(a, c);
-        default: return __dadd_rz(a, c);
-    }
+// more than kRcpSlots IMUL_RCP in one program (never observed): kept out of line so its loop does not take registers
+// (uniform ones included) away from the interpreter loop
+__device__ __noinline__ u64 reciprocal_slow(u32 divisor) { return device_reciprocal(divisor); }
+// The rounding mode (fprc) is folded into the interpreter's jump-table index, so every FP handler exists once per
+// mode with the mode a compile-time constant: native directed-rounding DADD/DMUL, no branch on the mode.
+template <int M> __device__ __forceinline__ double add_c(double a, double c) {
+    return M == 0 ? __dadd_rn(a, c) : M == 1 ? __dadd_rd(a, c) : M == 2 ? __dadd_ru(a, c) : __dadd_rz(a, c);
 }
-__device__ __forceinline__ double mul_rm(double a, double c, u32 mode) {
-    switch (mode) {
-        case 0: return __dmul_rn(a, c);
-        case 1: return __dmul_rd(a, c);
-        case 2: return __dmul_ru(a, c);
-        default: return __dmul_rz(a, c);
-    }
-}
-// both halves of an FP register under ONE branch on the (warp-uniform) rounding mode
-__device__ __forceinline__ void add2_rm(double &r0, double &r1, double a0, double b0, double a1, double b1, u32 mode) {
-    switch (mode) {
-        case 0: r0 = __dadd_rn(a0, b0); r1 = __dadd_rn(a1, b1); break;
-        case 1: r0 = __dadd_rd(a0, b0); r1 = __dadd_rd(a1, b1); break;
-        case 2: r0 = __dadd_ru(a0, b0); r1 = __dadd_ru(a1, b1); break;
-        default: r0 = __dadd_rz(a0, b0); r1 = __dadd_rz(a1, b1); break;
-    }
-}
-__device__ __forceinline__ void mul2_rm(double &r0, double &r1, double a0, double b0, double a1, double b1, u32 mode) {
-    switch (mode) {
-        case 0: r0 = __dmul_rn(a0, b0); r1 = __dmul_rn(a1, b1); break;
-        case 1: r0 = __dmul_rd(a0, b0); r1 = __dmul_rd(a1, b1); break;
-        case 2: r0 = __dmul_ru(a0, b0); r1 = __dmul_ru(a1, b1); break;
-        default: r0 = __dmul_rz(a0, b0); r1 = __dmul_rz(a1, b1); break;
-    }
+template <int M> __device__ __forceinline__ double mul_c(double a, double c) {
+    return M == 0 ? __dmul_rn(a, c) : M == 1 ? __dmul_rd(a, c) : M == 2 ? __dmul_ru(a, c) : __dmul_rz(a, c);
 }
 // e-group values are positive and finite (spec §4.3.2): directed rounding = round-to-nearest, then step one ulp against
 // the sign of the exact residual.  residual = fma(-q, b, a) is exact for a correctly rounded quotient / root.
-__device__ __forceinline__ double fix_positive(double q, double residual, u32 mode) {
+template <int M> __device__ __forceinline__ double fix_positive(double q, double residual) {
+    if (M == 0) return q;
+    long long bits = __double_as_longlong(q);
+    if (M == 2) bits += residual > 0.0 ? 1 : 0;
+    else bits -= residual < 0.0 ? 1 : 0;
+    return __longlong_as_double(bits);
+}
+// FDIV_M / FSQRT_R keep the mode a run-time value: their slow paths are large and they are 10 of 256 instructions;
+// four copies of them would push the interpreter past the 32 KB instruction cache
+__device__ __forceinline__ double fix_positive_rt(double q, double residual, u32 mode) {
     long long bits = __double_as_longlong(q);
     const bool down = (mode == 1 || mode == 3) && residual < 0.0, up = mode == 2 && residual > 0.0;
     bits += up ? 1 : 0;
     bits -= down ? 1 : 0;
     return __longlong_as_double(bits);
 }
-__device__ __forceinline__ double div_rm(double a, double c, u32 mode) {
+__device__ __forceinline__ double div_rt(double a, double c, u32 mode) { const double q = __ddiv_rn(a, c); return fix_positive_rt(q, __fma_rn(-q, c, a), mode); }
+__device__ __forceinline__ double sqrt_rt(double a, u32 mode) { const double r = __dsqrt_rn(a); return fix_positive_rt(r, __fma_rn(-r, r, a), mode); }
+template <int M> __device__ __forceinline__ double div_c(double a, double c) {
     const double q = __ddiv_rn(a, c);
-    return fix_positive(q, __fma_rn(-q, c, a), mode);
+    return M == 0 ? q : fix_positive<M>(q, __fma_rn(-q, c, a));
 }
-__device__ __forceinline__ double sqrt_rm(double a, u32 mode) {
-    const double s = __dsqrt_rn(a);
-    return fix_positive(s, __fma_rn(-s, s, a), mode);
+template <int M> __device__ __forceinline__ double sqrt_c(double a) {
+    const double r = __dsqrt_rn(a);
+    return M == 0 ? r : fix_positive<M>(r, __fma_rn(-r, r, a));
 }
 __device__ __forceinline__ u64 d2u(double v) { return (u64)__double_as_longlong(v); }
 __device__ __forceinline__ double u2d(u64 v) { return __longlong_as_double((long long)v); }
@@ -445,40 +436,57 @@ __device__ __forceinline__ double u2d(u64 v) { return __longlong_as_double((long
 // scratchpad / dataset lines around it.  39 SASS instructions per VM instruction (ncu), issue-bound.
 __device__ __forceinline__ uint8_t *sp_byte(uint8_t *cold, uint8_t *hot, u32 addr) { return (addr < kScratchpadL1 ? hot : cold) + addr; }
 
-// Per-warp shared state of the VM kernel.  The interpreter body is instantiated once per warp slot of the CTA (W is a
-// template argument), so every shared-memory address in it is a link-time constant plus a field of the instruction word:
-// no per-warp base register, no address arithmetic in the handlers.
+// Per-warp shared state of the VM kernel.  The interpreter addresses it with explicit 32-bit shared-window addresses
+// kept in ordinary registers (ld.shared / st.shared below): left to itself the compiler re-derives the window base
+// (S2R CgaCtaId + 2 more) in every handler once the program loop has a jump table in it.  regs is 256-byte aligned so
+// "(word & 0xf8) | base" is the source operand's address in one LOP3; everything else is base + constant + field.
 template <int WARPS>
-struct VmShared {
-    uint2 prog[WARPS][kProgramSize];
-    u64 rcp[WARPS][kRcpSlots];
-    u64 regs[WARPS][32];
-    u64 emask[WARPS][2];      // e-register exponent masks (lo, hi): read by the loop prologue and FDIV_M only
+struct alignas(256) VmWarpShared {
+    u64 regs[32];
+    u64 rcp[kRcpSlots];
+    u64 emask[2];                      // e-register exponent masks (lo, hi): read by the loop prologue and FDIV_M only
+    u32 self[2];                       // shared-window address of regs, read back through a volatile load (see vm_run)
+    uint2 prog[kProgramSize + 1];      // + W_END
 };
+template <int WARPS>
+struct VmShared { VmWarpShared<WARPS> w[WARPS]; };
 
-template <int WARPS, int W>
-__device__ __forceinline__ void vm_run(VmShared<WARPS> &sh, const BatchBuffers &b, u32 vm, u32 lane, const uint8_t *__restrict__ dataset) {
-    uint2 *prog = sh.prog[W];
-    u64 *rcp = sh.rcp[W], *regs = sh.regs[W];
-    const u64 *emask = sh.emask[W];
+__device__ __forceinline__ u64 lds64(u32 a) { u64 v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint2 lds64v2(u32 a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void lds128(u32 a, u64 &lo, u64 &hi) { asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(a) : "memory"); }
+__device__ __forceinline__ void sts128(u32 a, u64 lo, u64 hi) { asm volatile("st.shared.v2.u64 [%0], {%1, %2};" ::"r"(a), "l"(lo), "l"(hi) : "memory"); }
+__device__ __forceinline__ void sts64(u32 a, u64 v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+
+template <int WARPS>
+__device__ __forceinline__ void vm_run(VmWarpShared<WARPS> &sh, const BatchBuffers &b, u32 vm, u32 lane, const uint8_t *__restrict__ dataset) {
+    uint2 *prog = sh.prog;
+    u64 *rcp = sh.rcp, *regs = sh.regs;
+    const u64 *emask = sh.emask;
     for (int i = lane; i < kProgramSize; i += 32) prog[i] = b.program[(size_t)vm * kProgramSize + i];
+    if (lane == 0) prog[kProgramSize] = make_uint2((u32)W_END << 8, 0);
     rcp[lane] = b.rcp[(size_t)vm * kRcpSlots + lane];
     const u32 stride = b.stride;
     regs[lane] = lane >= 24 ? b.regfile[(size_t)lane * stride + vm] : 0;
     __syncwarp();
     const u64 c0 = b.config[vm], c1 = b.config[(size_t)stride + vm];
-    if (lane < 2) sh.emask[W][lane] = b.config[(size_t)(2 + lane) * stride + vm];
+    if (lane < 2) sh.emask[lane] = b.config[(size_t)(2 + lane) * stride + vm];
     __syncwarp();
     u32 ma = (u32)c0, mx = (u32)(c0 >> 32);
     const u32 rr = (u32)(c1 >> 60);
     const uint8_t *ds = dataset + (c1 & ((1ull << 60) - 1));
-    u32 mode = b.fprc[vm];
+    u32 mode = (u32)b.fprc[vm] << 6;                        // kept pre-shifted: it is OR-ed into the jump-table index
     uint8_t *sp = b.scratchpads + (size_t)vm * kScratchpadL3;
     uint8_t *sph = b.hot + (size_t)vm * kScratchpadL1;      // offsets below 16 KiB (75 % of the accesses) go to the hot plane
     constexpr u64 kEMant = (1ull << 56) - 1;
-    const uint8_t *rb = reinterpret_cast<const uint8_t *>(regs);
-#define RD(off) (*reinterpret_cast<const u64 *>(rb + (off)))
-#define WR(off, v) (*reinterpret_cast<u64 *>(const_cast<uint8_t *>(rb) + (off)) = (v))
+    // the window address of regs, laundered through shared memory: ptxas sees through a mov and re-derives base + offset
+    // inside the loop; it cannot see through a volatile load
+    if (lane == 0) sh.self[0] = (u32)__cvta_generic_to_shared(regs);
+    __syncwarp();
+    const u32 rbase = *reinterpret_cast<volatile u32 *>(&sh.self[0]);
+    constexpr u32 kRcpOff = offsetof(VmWarpShared<WARPS>, rcp), kEmaskOff = offsetof(VmWarpShared<WARPS>, emask),
+                  kProgOff = offsetof(VmWarpShared<WARPS>, prog);
+#define RDA(addr) lds64(addr)
+#define WRA(addr, v) sts64((addr), (v))
 #define SPTR(addr) sp_byte(sp, sph, (addr))
 #define SPAD(addr) (*reinterpret_cast<u64 *>(SPTR(addr)))
 
@@ -496,70 +504,83 @@ __device__ __forceinline__ void vm_run(VmShared<WARPS> &sh, const BatchBuffers &
         }
         __syncwarp();
 
-        for (int pc = 0; pc < kProgramSize; pc++) {
-            const uint2 ins = prog[pc];
+        for (u32 pc = rbase + kProgOff;;) {
+            const uint2 ins = lds64v2(pc);
+            pc += 8;
             const u32 w = ins.x;
-            const u32 doff = w >> 24, soff = __byte_perm(w, 0, 0x4442), aux = __byte_perm(w, 0, 0x4441);   // one PRMT each
+            const u32 da = rbase + (w >> 24), sa = (w & 0xf8u) | rbase, aux = __byte_perm(w, 0, 0x4442);   // LEA.HI, LOP3, PRMT
             const u64 simm = sext(ins.y);
-#define MEMADDR ((u32)(RD(soff) + simm) & ((1u << aux) - 8u))
+#define MEMADDR ((u32)(RDA(sa) + simm) & ((1u << aux) - 8u))
 #define FP_M(lo, hi) const u64 mv_ = SPAD(MEMADDR); const double lo = (double)(int)(u32)mv_, hi = (double)(int)(u32)(mv_ >> 32)
-            switch (w & 255) {
-                case W_IADD_RS: WR(doff, RD(doff) + (RD(soff) << aux) + simm); break;
-                case W_ISUB_R: WR(doff, RD(doff) - RD(soff)); break;
-                case W_IMUL_R: WR(doff, RD(doff) * RD(soff)); break;
-                case W_IMULH_R: WR(doff, mulh_u(RD(doff), RD(soff))); break;
-                case W_ISMULH_R: WR(doff, mulh_s(RD(doff), RD(soff))); break;
-                case W_IXOR_R: WR(doff, RD(doff) ^ RD(soff)); break;
-                case W_IROR_R: { const u64 d = RD(doff); const u32 c = (u32)RD(soff) & 63; WR(doff, (d >> c) | (d << ((64 - c) & 63))); } break;
-                case W_IROL_R: { const u64 d = RD(doff); const u32 c = (u32)RD(soff) & 63; WR(doff, (d << c) | (d >> ((64 - c) & 63))); } break;
-                case W_ISWAP: { const u64 d = RD(doff), s = RD(soff); WR(doff, s); WR(soff, d); } break;
-                case W_ISUB_I: WR(doff, RD(doff) - simm); break;
-                case W_IMUL_I: WR(doff, RD(doff) * simm); break;
-                case W_IXOR_I: WR(doff, RD(doff) ^ simm); break;
-                case W_IROR_I: { const u64 d = RD(doff); WR(doff, (d >> aux) | (d << ((64 - aux) & 63))); } break;
-                case W_IROL_I: { const u64 d = RD(doff); WR(doff, (d << aux) | (d >> ((64 - aux) & 63))); } break;
-                case W_INEG: WR(doff, 0 - RD(doff)); break;
-                case W_IMUL_RCP: WR(doff, RD(doff) * rcp[aux]); break;
-                case W_IMUL_RCP_SLOW: WR(doff, RD(doff) * device_reciprocal(ins.y)); break;
-                case W_IADD_M: WR(doff, RD(doff) + SPAD(MEMADDR)); break;
-                case W_ISUB_M: WR(doff, RD(doff) - SPAD(MEMADDR)); break;
-                case W_IMUL_M: WR(doff, RD(doff) * SPAD(MEMADDR)); break;
-                case W_IMULH_M: WR(doff, mulh_u(RD(doff), SPAD(MEMADDR))); break;
-                case W_ISMULH_M: WR(doff, mulh_s(RD(doff), SPAD(MEMADDR))); break;
-                case W_IXOR_M: WR(doff, RD(doff) ^ SPAD(MEMADDR)); break;
-                case W_IADD_A: WR(doff, RD(doff) + SPAD(ins.y)); break;
-                case W_ISUB_A: WR(doff, RD(doff) - SPAD(ins.y)); break;
-                case W_IMUL_A: WR(doff, RD(doff) * SPAD(ins.y)); break;
-                case W_IMULH_A: WR(doff, mulh_u(RD(doff), SPAD(ins.y))); break;
-                case W_ISMULH_A: WR(doff, mulh_s(RD(doff), SPAD(ins.y))); break;
-                case W_IXOR_A: WR(doff, RD(doff) ^ SPAD(ins.y)); break;
-                case W_CBRANCH: {
-                    const u64 r0 = RD(doff) + simm;
-                    WR(doff, r0);
-                    if ((r0 & (255ull << aux)) == 0) pc = (int)soff - 1;       // soff field = target + 1
+#define ANY_MODE(op) case op: case op + 64: case op + 128: case op + 192
+#define PER_MODE(op, ...) \
+    case op: { constexpr int M = 0; __VA_ARGS__ } break; \
+    case op + 64: { constexpr int M = 1; __VA_ARGS__ } break; \
+    case op + 128: { constexpr int M = 2; __VA_ARGS__ } break; \
+    case op + 192: { constexpr int M = 3; __VA_ARGS__ } break;
+#define FP_LOAD_D u64 dl_, dh_; lds128(da, dl_, dh_); const double dlo = u2d(dl_), dhi = u2d(dh_)
+#define FP_LOAD_S u64 sl_, sh_; lds128(sa, sl_, sh_); const double slo = u2d(sl_), shi = u2d(sh_)
+            static_assert(W_COUNT <= 64, "the opcode shares the jump-table index with the rounding mode");
+            switch (((w >> 8) & 63) | mode) {
+                ANY_MODE(W_IADD_RS): WRA(da, RDA(da) + (RDA(sa) << aux) + simm); break;
+                ANY_MODE(W_ISUB_R): WRA(da, RDA(da) - RDA(sa)); break;
+                ANY_MODE(W_IMUL_R): WRA(da, RDA(da) * RDA(sa)); break;
+                ANY_MODE(W_IMULH_R): WRA(da, mulh_u(RDA(da), RDA(sa))); break;
+                ANY_MODE(W_ISMULH_R): WRA(da, mulh_s(RDA(da), RDA(sa))); break;
+                ANY_MODE(W_IXOR_R): WRA(da, RDA(da) ^ RDA(sa)); break;
+                ANY_MODE(W_IROR_R): { const u64 d = RDA(da); const u32 c = (u32)RDA(sa) & 63; WRA(da, (d >> c) | (d << ((64 - c) & 63))); } break;
+                ANY_MODE(W_IROL_R): { const u64 d = RDA(da); const u32 c = (u32)RDA(sa) & 63; WRA(da, (d << c) | (d >> ((64 - c) & 63))); } break;
+                ANY_MODE(W_ISWAP): { const u64 d = RDA(da), s = RDA(sa); WRA(da, s); WRA(sa, d); } break;
+                ANY_MODE(W_ISUB_I): WRA(da, RDA(da) - simm); break;
+                ANY_MODE(W_IMUL_I): WRA(da, RDA(da) * simm); break;
+                ANY_MODE(W_IXOR_I): WRA(da, RDA(da) ^ simm); break;
+                ANY_MODE(W_IROR_I): { const u64 d = RDA(da); WRA(da, (d >> aux) | (d << ((64 - aux) & 63))); } break;
+                ANY_MODE(W_IROL_I): { const u64 d = RDA(da); WRA(da, (d << aux) | (d >> ((64 - aux) & 63))); } break;
+                ANY_MODE(W_INEG): WRA(da, 0 - RDA(da)); break;
+                ANY_MODE(W_IMUL_RCP): WRA(da, RDA(da) * RDA(rbase + kRcpOff + aux * 8)); break;
+                ANY_MODE(W_IMUL_RCP_SLOW): WRA(da, RDA(da) * reciprocal_slow(ins.y)); break;
+                ANY_MODE(W_IADD_M): WRA(da, RDA(da) + SPAD(MEMADDR)); break;
+                ANY_MODE(W_ISUB_M): WRA(da, RDA(da) - SPAD(MEMADDR)); break;
+                ANY_MODE(W_IMUL_M): WRA(da, RDA(da) * SPAD(MEMADDR)); break;
+                ANY_MODE(W_IMULH_M): WRA(da, mulh_u(RDA(da), SPAD(MEMADDR))); break;
+                ANY_MODE(W_ISMULH_M): WRA(da, mulh_s(RDA(da), SPAD(MEMADDR))); break;
+                ANY_MODE(W_IXOR_M): WRA(da, RDA(da) ^ SPAD(MEMADDR)); break;
+                ANY_MODE(W_IADD_A): WRA(da, RDA(da) + SPAD(ins.y)); break;
+                ANY_MODE(W_ISUB_A): WRA(da, RDA(da) - SPAD(ins.y)); break;
+                ANY_MODE(W_IMUL_A): WRA(da, RDA(da) * SPAD(ins.y)); break;
+                ANY_MODE(W_IMULH_A): WRA(da, mulh_u(RDA(da), SPAD(ins.y))); break;
+                ANY_MODE(W_ISMULH_A): WRA(da, mulh_s(RDA(da), SPAD(ins.y))); break;
+                ANY_MODE(W_IXOR_A): WRA(da, RDA(da) ^ SPAD(ins.y)); break;
+                ANY_MODE(W_CBRANCH): {
+                    const u64 r0 = RDA(da) + simm;
+                    WRA(da, r0);
+                    if ((r0 & (255ull << aux)) == 0) pc = rbase + kProgOff + (w & 255u) * 8;       // low byte = target + 1
                 } break;
-                case W_CFROUND: { const u64 s = RD(soff); mode = (u32)((s >> aux) | (s << ((64 - aux) & 63))) & 3; } break;
-                case W_ISTORE: SPAD((u32)(RD(doff) + simm) & ((1u << aux) - 8u)) = RD(soff); break;
-                case W_FSWAP: { const u64 lo = RD(doff), hi = RD(doff + 8); WR(doff, hi); WR(doff + 8, lo); } break;
-                case W_FADD_R: { double lo, hi; add2_rm(lo, hi, u2d(RD(doff)), u2d(RD(soff)), u2d(RD(doff + 8)), u2d(RD(soff + 8)), mode);
-                                 WR(doff, d2u(lo)); WR(doff + 8, d2u(hi)); } break;
-                case W_FSUB_R: { double lo, hi; add2_rm(lo, hi, u2d(RD(doff)), -u2d(RD(soff)), u2d(RD(doff + 8)), -u2d(RD(soff + 8)), mode);
-                                 WR(doff, d2u(lo)); WR(doff + 8, d2u(hi)); } break;
-                case W_FSCAL: WR(doff, RD(doff) ^ 0x80F0000000000000ull); WR(doff + 8, RD(doff + 8) ^ 0x80F0000000000000ull); break;
-                case W_FMUL_R: { double lo, hi; mul2_rm(lo, hi, u2d(RD(doff)), u2d(RD(soff)), u2d(RD(doff + 8)), u2d(RD(soff + 8)), mode);
-                                 WR(doff, d2u(lo)); WR(doff + 8, d2u(hi)); } break;
-                case W_FSQRT: { const double lo = sqrt_rm(u2d(RD(doff)), mode), hi = sqrt_rm(u2d(RD(doff + 8)), mode); WR(doff, d2u(lo)); WR(doff + 8, d2u(hi)); } break;
-                case W_FADD_M: { FP_M(mlo, mhi); double lo, hi; add2_rm(lo, hi, u2d(RD(doff)), mlo, u2d(RD(doff + 8)), mhi, mode); WR(doff, d2u(lo)); WR(doff + 8, d2u(hi)); } break;
-                case W_FSUB_M: { FP_M(mlo, mhi); double lo, hi; add2_rm(lo, hi, u2d(RD(doff)), -mlo, u2d(RD(doff + 8)), -mhi, mode); WR(doff, d2u(lo)); WR(doff + 8, d2u(hi)); } break;
-                case W_FDIV_M: { FP_M(mlo, mhi);
-                                 const double dlo = u2d((d2u(mlo) & kEMant) | emask[0]), dhi = u2d((d2u(mhi) & kEMant) | emask[1]);
-                                 WR(doff, d2u(div_rm(u2d(RD(doff)), dlo, mode))); WR(doff + 8, d2u(div_rm(u2d(RD(doff + 8)), dhi, mode))); } break;
-                case W_NOP: break;
+                ANY_MODE(W_CFROUND): { const u64 s = RDA(sa); mode = ((u32)((s >> aux) | (s << ((64 - aux) & 63))) & 3) << 6; } break;
+                ANY_MODE(W_ISTORE): SPAD((u32)(RDA(da) + simm) & ((1u << aux) - 8u)) = RDA(sa); break;
+                ANY_MODE(W_FSWAP): { u64 lo, hi; lds128(da, lo, hi); sts128(da, hi, lo); } break;
+                ANY_MODE(W_FSCAL): { u64 lo, hi; lds128(da, lo, hi); sts128(da, lo ^ 0x80F0000000000000ull, hi ^ 0x80F0000000000000ull); } break;
+                PER_MODE(W_FADD_R, FP_LOAD_D; FP_LOAD_S; sts128(da, d2u(add_c<M>(dlo, slo)), d2u(add_c<M>(dhi, shi)));)
+                PER_MODE(W_FSUB_R, FP_LOAD_D; FP_LOAD_S; sts128(da, d2u(add_c<M>(dlo, -slo)), d2u(add_c<M>(dhi, -shi)));)
+                PER_MODE(W_FMUL_R, FP_LOAD_D; FP_LOAD_S; sts128(da, d2u(mul_c<M>(dlo, slo)), d2u(mul_c<M>(dhi, shi)));)
+                ANY_MODE(W_FSQRT): { FP_LOAD_D; const u32 m = mode >> 6; sts128(da, d2u(sqrt_rt(dlo, m)), d2u(sqrt_rt(dhi, m))); } break;
+                PER_MODE(W_FADD_M, FP_M(mlo, mhi); FP_LOAD_D; sts128(da, d2u(add_c<M>(dlo, mlo)), d2u(add_c<M>(dhi, mhi)));)
+                PER_MODE(W_FSUB_M, FP_M(mlo, mhi); FP_LOAD_D; sts128(da, d2u(add_c<M>(dlo, -mlo)), d2u(add_c<M>(dhi, -mhi)));)
+                ANY_MODE(W_FDIV_M): { FP_M(mlo, mhi); FP_LOAD_D; u64 el, eh; lds128(rbase + kEmaskOff, el, eh);
+                         const double vlo = u2d((d2u(mlo) & kEMant) | el), vhi = u2d((d2u(mhi) & kEMant) | eh);
+                         const u32 m = mode >> 6; sts128(da, d2u(div_rt(dlo, vlo, m)), d2u(div_rt(dhi, vhi, m))); } break;
+                ANY_MODE(W_NOP): break;
+                ANY_MODE(W_END): goto program_done;
                 default: __builtin_unreachable();     // the decoder emits nothing else: lets the jump table drop its range check
             }
+#undef ANY_MODE
+#undef PER_MODE
+#undef FP_LOAD_D
+#undef FP_LOAD_S
 #undef MEMADDR
 #undef FP_M
         }
+    program_done:
 
         mx = (mx ^ (u32)(regs[4 + ((rr >> 2) & 1)] ^ regs[6 + ((rr >> 3) & 1)])) & kDatasetAlignMask;
         if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(ds + mx));
@@ -579,9 +600,9 @@ __device__ __forceinline__ void vm_run(VmShared<WARPS> &sh, const BatchBuffers &
         sp0 = 0; sp1 = 0;
     }
     if (lane < 24) b.regfile[(size_t)lane * stride + vm] = regs[lane];
-    if (lane == 0) b.fprc[vm] = (uint8_t)mode;
-#undef RD
-#undef WR
+    if (lane == 0) b.fprc[vm] = (uint8_t)(mode >> 6);
+#undef RDA
+#undef WRA
 #undef SPAD
 #undef SPTR
 }
@@ -591,8 +612,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) execute_kernel(BatchBuff
     __shared__ VmShared<WARPS> sh;
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, vm = blockIdx.x * WARPS + wid;
     if (vm >= n) return;
-    if (WARPS == 1 || wid == 0) vm_run<WARPS, 0>(sh, b, vm, lane, dataset);
-    else vm_run<WARPS, WARPS - 1>(sh, b, vm, lane, dataset);
+    vm_run<WARPS>(sh.w[wid], b, vm, lane, dataset);
 }
 
 // ---------------------------------------------------------------------------------------------- chain seed / final hash
