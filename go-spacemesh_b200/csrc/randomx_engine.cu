@@ -117,8 +117,9 @@ int RandomxEngine::ensure_batch(uint32_t want) {
         }
         if (cap == 32) { set_error("not enough HBM for one warp of RandomX scratchpads (2 MiB each)"); return B200POST_ERR_OUT_OF_MEMORY; }
     }
-    // (A persisting-L2 access-policy window over the hot plane was measured: 4 361 vs 4 370 H/s, no gain — the VM kernel is
-    // issue-bound — and the L2 set-aside slowed the label kernels of a following verify batch by a third; not used.)
+    // (A persisting-L2 access-policy window over the hot plane was measured twice: 4 361 vs 4 370 H/s with the first
+    // warp-per-VM kernel and 6 367 vs 6 377 H/s with the current one, no gain; the L2 set-aside also slowed the label
+    // kernels of a following verify batch by a third.  Not used.)
     if ((size_t)cap_ * 32 > stage_cap_) {
         cudaFreeHost(h_stage_); h_stage_ = nullptr; stage_cap_ = 0;
         RX_TRY(cudaMallocHost(&h_stage_, (size_t)cap_ * 32));
