@@ -393,13 +393,6 @@ template <int M> __device__ __forceinline__ double mul_c(double a, double c) {
 }
 // e-group values are positive and finite (spec §4.3.2): directed rounding = round-to-nearest, then step one ulp against
 // the sign of the exact residual.  residual = fma(-q, b, a) is exact for a correctly rounded quotient / root.
-template <int M> __device__ __forceinline__ double fix_positive(double q, double residual) {
-    if (M == 0) return q;
-    long long bits = __double_as_longlong(q);
-    if (M == 2) bits += residual > 0.0 ? 1 : 0;
-    else bits -= residual < 0.0 ? 1 : 0;
-    return __longlong_as_double(bits);
-}
 // FDIV_M / FSQRT_R keep the mode a run-time value: their slow paths are large and they are 10 of 256 instructions;
 // four copies of them would push the interpreter past the 32 KB instruction cache
 __device__ __forceinline__ double fix_positive_rt(double q, double residual, u32 mode) {
@@ -411,14 +404,6 @@ __device__ __forceinline__ double fix_positive_rt(double q, double residual, u32
 }
 __device__ __forceinline__ double div_rt(double a, double c, u32 mode) { const double q = __ddiv_rn(a, c); return fix_positive_rt(q, __fma_rn(-q, c, a), mode); }
 __device__ __forceinline__ double sqrt_rt(double a, u32 mode) { const double r = __dsqrt_rn(a); return fix_positive_rt(r, __fma_rn(-r, r, a), mode); }
-template <int M> __device__ __forceinline__ double div_c(double a, double c) {
-    const double q = __ddiv_rn(a, c);
-    return M == 0 ? q : fix_positive<M>(q, __fma_rn(-q, c, a));
-}
-template <int M> __device__ __forceinline__ double sqrt_c(double a) {
-    const double r = __dsqrt_rn(a);
-    return M == 0 ? r : fix_positive<M>(r, __fma_rn(-r, r, a));
-}
 __device__ __forceinline__ u64 d2u(double v) { return (u64)__double_as_longlong(v); }
 __device__ __forceinline__ double u2d(u64 v) { return __longlong_as_double((long long)v); }
 
@@ -433,7 +418,10 @@ __device__ __forceinline__ double u2d(u64 v) { return __longlong_as_double((long
 // word are byte offsets, opcodes are dense with one opcode per (operation, operand kind) so a handler touches only
 // what it needs, and every lane executes the whole instruction redundantly (both halves of an FP register too): no
 // cross-lane dependency inside the program loop, no warp synchronisation; the lanes split up only for the 64-byte
-// scratchpad / dataset lines around it.  39 SASS instructions per VM instruction (ncu), issue-bound.
+// scratchpad / dataset lines around it.  The dispatch is a jump table indexed by opcode | rounding mode, both operands
+// are requested before the branch; 24 SASS instructions per VM instruction and 23 KB of code — the 32 KB instruction
+// cache is a hard budget for an interpreter: a 58 KB build with 30 % fewer instructions per step was slower.
+// 6.6 kH/s (profiles/r02_rx_execute_v3_ncu.md, r02_k2pow_variants.md).
 __device__ __forceinline__ uint8_t *sp_byte(uint8_t *cold, uint8_t *hot, u32 addr) { return (addr < kScratchpadL1 ? hot : cold) + addr; }
 
 // Per-warp shared state of the VM kernel.  The interpreter addresses it with explicit 32-bit shared-window addresses
@@ -510,7 +498,9 @@ __device__ __forceinline__ void vm_run(VmWarpShared<WARPS> &sh, const BatchBuffe
             const u32 w = ins.x;
             const u32 da = rbase + (w >> 24), sa = (w & 0xf8u) | rbase, aux = __byte_perm(w, 0, 0x4442);   // LEA.HI, LOP3, PRMT
             const u64 simm = sext(ins.y);
-#define MEMADDR ((u32)(RDA(sa) + simm) & ((1u << aux) - 8u))
+            const u64 dv = lds64(da), sv = lds64(sa);        // both operands are requested before the jump-table load and the
+                                                             // branch: a handler starts with them in flight (slot fields are valid for every opcode)
+#define MEMADDR (((u32)sv + ins.y) & ((1u << aux) - 8u))
 #define FP_M(lo, hi) const u64 mv_ = SPAD(MEMADDR); const double lo = (double)(int)(u32)mv_, hi = (double)(int)(u32)(mv_ >> 32)
 #define ANY_MODE(op) case op: case op + 64: case op + 128: case op + 192
 #define PER_MODE(op, ...) \
@@ -518,48 +508,48 @@ __device__ __forceinline__ void vm_run(VmWarpShared<WARPS> &sh, const BatchBuffe
     case op + 64: { constexpr int M = 1; __VA_ARGS__ } break; \
     case op + 128: { constexpr int M = 2; __VA_ARGS__ } break; \
     case op + 192: { constexpr int M = 3; __VA_ARGS__ } break;
-#define FP_LOAD_D u64 dl_, dh_; lds128(da, dl_, dh_); const double dlo = u2d(dl_), dhi = u2d(dh_)
-#define FP_LOAD_S u64 sl_, sh_; lds128(sa, sl_, sh_); const double slo = u2d(sl_), shi = u2d(sh_)
+#define FP_LOAD_D const double dlo = u2d(dv), dhi = u2d(RDA(da + 8))
+#define FP_LOAD_S const double slo = u2d(sv), shi = u2d(RDA(sa + 8))
             static_assert(W_COUNT <= 64, "the opcode shares the jump-table index with the rounding mode");
             switch (((w >> 8) & 63) | mode) {
-                ANY_MODE(W_IADD_RS): WRA(da, RDA(da) + (RDA(sa) << aux) + simm); break;
-                ANY_MODE(W_ISUB_R): WRA(da, RDA(da) - RDA(sa)); break;
-                ANY_MODE(W_IMUL_R): WRA(da, RDA(da) * RDA(sa)); break;
-                ANY_MODE(W_IMULH_R): WRA(da, mulh_u(RDA(da), RDA(sa))); break;
-                ANY_MODE(W_ISMULH_R): WRA(da, mulh_s(RDA(da), RDA(sa))); break;
-                ANY_MODE(W_IXOR_R): WRA(da, RDA(da) ^ RDA(sa)); break;
-                ANY_MODE(W_IROR_R): { const u64 d = RDA(da); const u32 c = (u32)RDA(sa) & 63; WRA(da, (d >> c) | (d << ((64 - c) & 63))); } break;
-                ANY_MODE(W_IROL_R): { const u64 d = RDA(da); const u32 c = (u32)RDA(sa) & 63; WRA(da, (d << c) | (d >> ((64 - c) & 63))); } break;
-                ANY_MODE(W_ISWAP): { const u64 d = RDA(da), s = RDA(sa); WRA(da, s); WRA(sa, d); } break;
-                ANY_MODE(W_ISUB_I): WRA(da, RDA(da) - simm); break;
-                ANY_MODE(W_IMUL_I): WRA(da, RDA(da) * simm); break;
-                ANY_MODE(W_IXOR_I): WRA(da, RDA(da) ^ simm); break;
-                ANY_MODE(W_IROR_I): { const u64 d = RDA(da); WRA(da, (d >> aux) | (d << ((64 - aux) & 63))); } break;
-                ANY_MODE(W_IROL_I): { const u64 d = RDA(da); WRA(da, (d << aux) | (d >> ((64 - aux) & 63))); } break;
-                ANY_MODE(W_INEG): WRA(da, 0 - RDA(da)); break;
-                ANY_MODE(W_IMUL_RCP): WRA(da, RDA(da) * RDA(rbase + kRcpOff + aux * 8)); break;
-                ANY_MODE(W_IMUL_RCP_SLOW): WRA(da, RDA(da) * reciprocal_slow(ins.y)); break;
-                ANY_MODE(W_IADD_M): WRA(da, RDA(da) + SPAD(MEMADDR)); break;
-                ANY_MODE(W_ISUB_M): WRA(da, RDA(da) - SPAD(MEMADDR)); break;
-                ANY_MODE(W_IMUL_M): WRA(da, RDA(da) * SPAD(MEMADDR)); break;
-                ANY_MODE(W_IMULH_M): WRA(da, mulh_u(RDA(da), SPAD(MEMADDR))); break;
-                ANY_MODE(W_ISMULH_M): WRA(da, mulh_s(RDA(da), SPAD(MEMADDR))); break;
-                ANY_MODE(W_IXOR_M): WRA(da, RDA(da) ^ SPAD(MEMADDR)); break;
-                ANY_MODE(W_IADD_A): WRA(da, RDA(da) + SPAD(ins.y)); break;
-                ANY_MODE(W_ISUB_A): WRA(da, RDA(da) - SPAD(ins.y)); break;
-                ANY_MODE(W_IMUL_A): WRA(da, RDA(da) * SPAD(ins.y)); break;
-                ANY_MODE(W_IMULH_A): WRA(da, mulh_u(RDA(da), SPAD(ins.y))); break;
-                ANY_MODE(W_ISMULH_A): WRA(da, mulh_s(RDA(da), SPAD(ins.y))); break;
-                ANY_MODE(W_IXOR_A): WRA(da, RDA(da) ^ SPAD(ins.y)); break;
+                ANY_MODE(W_IADD_RS): WRA(da, dv + (sv << aux) + simm); break;
+                ANY_MODE(W_ISUB_R): WRA(da, dv - sv); break;
+                ANY_MODE(W_IMUL_R): WRA(da, dv * sv); break;
+                ANY_MODE(W_IMULH_R): WRA(da, mulh_u(dv, sv)); break;
+                ANY_MODE(W_ISMULH_R): WRA(da, mulh_s(dv, sv)); break;
+                ANY_MODE(W_IXOR_R): WRA(da, dv ^ sv); break;
+                ANY_MODE(W_IROR_R): { const u64 d = dv; const u32 c = (u32)sv & 63; WRA(da, (d >> c) | (d << ((64 - c) & 63))); } break;
+                ANY_MODE(W_IROL_R): { const u64 d = dv; const u32 c = (u32)sv & 63; WRA(da, (d << c) | (d >> ((64 - c) & 63))); } break;
+                ANY_MODE(W_ISWAP): { const u64 d = dv, s = sv; WRA(da, s); WRA(sa, d); } break;
+                ANY_MODE(W_ISUB_I): WRA(da, dv - simm); break;
+                ANY_MODE(W_IMUL_I): WRA(da, dv * simm); break;
+                ANY_MODE(W_IXOR_I): WRA(da, dv ^ simm); break;
+                ANY_MODE(W_IROR_I): { const u64 d = dv; WRA(da, (d >> aux) | (d << ((64 - aux) & 63))); } break;
+                ANY_MODE(W_IROL_I): { const u64 d = dv; WRA(da, (d << aux) | (d >> ((64 - aux) & 63))); } break;
+                ANY_MODE(W_INEG): WRA(da, 0 - dv); break;
+                ANY_MODE(W_IMUL_RCP): WRA(da, dv * RDA(rbase + kRcpOff + aux * 8)); break;
+                ANY_MODE(W_IMUL_RCP_SLOW): WRA(da, dv * reciprocal_slow(ins.y)); break;
+                ANY_MODE(W_IADD_M): WRA(da, dv + SPAD(MEMADDR)); break;
+                ANY_MODE(W_ISUB_M): WRA(da, dv - SPAD(MEMADDR)); break;
+                ANY_MODE(W_IMUL_M): WRA(da, dv * SPAD(MEMADDR)); break;
+                ANY_MODE(W_IMULH_M): WRA(da, mulh_u(dv, SPAD(MEMADDR))); break;
+                ANY_MODE(W_ISMULH_M): WRA(da, mulh_s(dv, SPAD(MEMADDR))); break;
+                ANY_MODE(W_IXOR_M): WRA(da, dv ^ SPAD(MEMADDR)); break;
+                ANY_MODE(W_IADD_A): WRA(da, dv + SPAD(ins.y)); break;
+                ANY_MODE(W_ISUB_A): WRA(da, dv - SPAD(ins.y)); break;
+                ANY_MODE(W_IMUL_A): WRA(da, dv * SPAD(ins.y)); break;
+                ANY_MODE(W_IMULH_A): WRA(da, mulh_u(dv, SPAD(ins.y))); break;
+                ANY_MODE(W_ISMULH_A): WRA(da, mulh_s(dv, SPAD(ins.y))); break;
+                ANY_MODE(W_IXOR_A): WRA(da, dv ^ SPAD(ins.y)); break;
                 ANY_MODE(W_CBRANCH): {
-                    const u64 r0 = RDA(da) + simm;
+                    const u64 r0 = dv + simm;
                     WRA(da, r0);
                     if ((r0 & (255ull << aux)) == 0) pc = rbase + kProgOff + (w & 255u) * 8;       // low byte = target + 1
                 } break;
-                ANY_MODE(W_CFROUND): { const u64 s = RDA(sa); mode = ((u32)((s >> aux) | (s << ((64 - aux) & 63))) & 3) << 6; } break;
-                ANY_MODE(W_ISTORE): SPAD((u32)(RDA(da) + simm) & ((1u << aux) - 8u)) = RDA(sa); break;
-                ANY_MODE(W_FSWAP): { u64 lo, hi; lds128(da, lo, hi); sts128(da, hi, lo); } break;
-                ANY_MODE(W_FSCAL): { u64 lo, hi; lds128(da, lo, hi); sts128(da, lo ^ 0x80F0000000000000ull, hi ^ 0x80F0000000000000ull); } break;
+                ANY_MODE(W_CFROUND): { const u64 s = sv; mode = ((u32)((s >> aux) | (s << ((64 - aux) & 63))) & 3) << 6; } break;
+                ANY_MODE(W_ISTORE): SPAD(((u32)dv + ins.y) & ((1u << aux) - 8u)) = sv; break;
+                ANY_MODE(W_FSWAP): sts128(da, RDA(da + 8), dv); break;
+                ANY_MODE(W_FSCAL): sts128(da, dv ^ 0x80F0000000000000ull, RDA(da + 8) ^ 0x80F0000000000000ull); break;
                 PER_MODE(W_FADD_R, FP_LOAD_D; FP_LOAD_S; sts128(da, d2u(add_c<M>(dlo, slo)), d2u(add_c<M>(dhi, shi)));)
                 PER_MODE(W_FSUB_R, FP_LOAD_D; FP_LOAD_S; sts128(da, d2u(add_c<M>(dlo, -slo)), d2u(add_c<M>(dhi, -shi)));)
                 PER_MODE(W_FMUL_R, FP_LOAD_D; FP_LOAD_S; sts128(da, d2u(mul_c<M>(dlo, slo)), d2u(mul_c<M>(dhi, shi)));)
