@@ -419,7 +419,7 @@ __device__ __forceinline__ double u2d(u64 v) { return __longlong_as_double((long
 // what it needs, and every lane executes the whole instruction redundantly (both halves of an FP register too): no
 // cross-lane dependency inside the program loop, no warp synchronisation; the lanes split up only for the 64-byte
 // scratchpad / dataset lines around it.  The dispatch is a jump table indexed by opcode | rounding mode, both operands
-// are requested before the branch; 24 SASS instructions per VM instruction and 23 KB of code — the 32 KB instruction
+// are requested before the branch and lane 0 interprets alone; 25 SASS instructions per VM instruction and 23 KB of code — the 32 KB instruction
 // cache is a hard budget for an interpreter: a 58 KB build with 30 % fewer instructions per step was slower.
 // 6.6 kH/s (profiles/r02_rx_execute_v3_ncu.md, r02_k2pow_variants.md).
 __device__ __forceinline__ uint8_t *sp_byte(uint8_t *cold, uint8_t *hot, u32 addr) { return (addr < kScratchpadL1 ? hot : cold) + addr; }
@@ -492,7 +492,11 @@ __device__ __forceinline__ void vm_run(VmWarpShared<WARPS> &sh, const BatchBuffe
         }
         __syncwarp();
 
-        for (u32 pc = rbase + kProgOff;;) {
+        // The program is interpreted by lane 0 ALONE (the other lanes wait at the reconvergence point below): every lane
+        // would compute the same values, but 32 same-address 64-bit stores cost 2-4 shared-memory wavefronts each and kept
+        // the LSU data pipe 72 % busy (ncu) — the resource that flattened throughput beyond 40 VMs per SM.  One active
+        // lane: one wavefront per access, same issue cost.
+        if (lane == 0) for (u32 pc = rbase + kProgOff;;) {
             const uint2 ins = lds64v2(pc);
             pc += 8;
             const u32 w = ins.x;
@@ -571,6 +575,8 @@ __device__ __forceinline__ void vm_run(VmWarpShared<WARPS> &sh, const BatchBuffe
 #undef FP_M
         }
     program_done:
+        __syncwarp();
+        mode = __shfl_sync(0xffffffffu, mode, 0);
 
         mx = (mx ^ (u32)(regs[4 + ((rr >> 2) & 1)] ^ regs[6 + ((rr >> 3) & 1)])) & kDatasetAlignMask;
         if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(ds + mx));
