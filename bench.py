@@ -469,7 +469,7 @@ def main() -> None:
     if tfile.exists():
         try:
             tj = json.loads(tfile.read_text())
-            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("captured_on", "round-1 build (stale for this build)")
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("captured_on", "build not recorded in the file")
         except Exception:  # noqa: BLE001
             traffic = None
 
