@@ -82,7 +82,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -92,11 +92,16 @@ class ClockSampler:
                 sm.append(float(f[0])); mx.append(float(f[1]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[2]))
+            except ValueError:
+                pass
             for name, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        sm.sort()
+        sm.sort(); pw.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w": pw[len(pw) // 2] if pw else None,          # median board power during the timed region
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
@@ -532,6 +537,8 @@ def main() -> None:
                          "kernel_share_of_step": (romix_ms / calls_ms) if calls_ms else None},
             "clocks": clocks,
         }
+        if clocks and clocks.get("power_w"):      # rank 0's board power x ranks: every rank runs the same kernel on the same part
+            line["labels_per_joule"] = value / (clocks["power_w"] * world)
         if verify_extra:
             line["verify"] = verify_extra
         if k2pow_extra:
