@@ -85,7 +85,8 @@ int b200post_k2pow_verify(uint32_t provider, const b200post_k2pow_params *p, uin
  * and of its VM kernel alone (the dominant kernel).  Any pointer may be NULL. */
 int b200post_randomx_last_timing(uint32_t provider, double *total_ms, double *vm_kernel_ms, uint64_t *hashes, uint64_t *vm_launches);
 
-/* VMs (hashes) one device batch holds under the current options ("rx_vms_per_sm", default 256). */
+/* VMs (hashes) one device batch holds under the current options ("rx_vm_mode", default 1 = 48 VMs per SM: 7 104 on a
+ * 148-SM B200; "rx_vms_per_sm" overrides the count; shrunk to what fits in free HBM at 2 MiB + 16 KiB per VM). */
 int b200post_randomx_batch_size(uint32_t provider, uint64_t *vms);
 
 #ifdef __cplusplus
