@@ -59,6 +59,22 @@ def test_k2pow_hashes_equal_oracle_on_1200_nonces(k2, oracle_default):
         assert bad.size == 0, f"{bad.size} of {count} hashes differ, first at pow {start + int(bad[0])}"
 
 
+def test_every_vm_kernel_variant_equals_the_oracle(k2, b2, oracle_default):
+    """rx_vm_mode 0..3 are four builds of the same interpreter (1- and 2-warp CTAs, 32 / 40 / 48 / 64-register budgets):
+    each must give the oracle's hashes, including an odd count that leaves a 2-warp CTA half empty."""
+    rng = np.random.default_rng(11)
+    ch, node = bytes(rng.integers(0, 256, 8, dtype=np.uint8)), bytes(rng.integers(0, 256, 32, dtype=np.uint8))
+    exp, _, _ = oracle_default.k2pow_scan(3, ch, node, 12345, 71)
+    before = b2.get_option("rx_vm_mode")
+    try:
+        for mode in (0, 1, 2, 3):
+            b2.set_option("rx_vm_mode", mode)
+            got = k2.hashes(3, ch, node, 12345, 71)
+            assert (got == exp).all(), f"rx_vm_mode {mode}: {(got != exp).any(axis=1).sum()} of 71 hashes differ"
+    finally:
+        b2.set_option("rx_vm_mode", before)
+
+
 def test_search_finds_the_first_valid_nonce_and_verify_agrees(k2, oracle_default):
     rng = np.random.default_rng(6)
     ch, node = bytes(rng.integers(0, 256, 8, dtype=np.uint8)), bytes(rng.integers(0, 256, 32, dtype=np.uint8))
